@@ -1,0 +1,159 @@
+/*
+ * utmos_b200.h -- C ABI of the B200-native greedy maximum-coverage selection path of utmos.
+ *
+ * One shared library (utmos_b200/libutmos_b200.so, CUDA sm_100a) exports exactly these symbols.  The host
+ * side (Python, ctypes: utmos_b200/_native.py) is the only caller.  Plain pointers and sizes only; the
+ * caller owns every host buffer, the library owns every device buffer until utmos_destroy().  Every
+ * function returns 0 on success or a negative UTMOS_E* code; utmos_last_error() returns the message of the
+ * last failure on the calling thread.  One host thread per context; all CUDA streams are internal.
+ *
+ * The reference has no FFI: the boundary this ABI replaces is the set of NumPy call sites below
+ * (file:line into the reference tree).
+ *
+ *   utmos_append_packed        utmos/select.py:272-280   np.unpackbits + .any(axis=1) filter of one .jl part
+ *   utmos_append_dense_u8/f32  utmos/select.py:37        row iteration of the hdf5 'data' dataset
+ *                              utmos/select.py:219-231   (bool, or float32 GT*AF flavour)
+ *   utmos_finalize             utmos/select.py:281-284   var_count column sums; :314-320 concat / AF matrix
+ *   utmos_select_begin         utmos/select.py:168-187   sample_mask / sample_weights hand-over
+ *   utmos_select_steps         utmos/select.py:24-53     calculate_scores (scores, mask, weights, argmax)
+ *                              utmos/select.py:91-112    greedy_select loop and its three stop rules
+ *   utmos_convert_gt           utmos/convert.py:57-87    is_het|is_hom_alt, het/hom totals, max-alt AF, packbits
+ */
+#ifndef UTMOS_B200_H
+#define UTMOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct utmos_ctx utmos_ctx;
+
+/* error codes */
+#define UTMOS_OK 0
+#define UTMOS_E_CUDA (-1)     /* a CUDA runtime call failed (message has the CUDA error string) */
+#define UTMOS_E_ARG (-2)      /* invalid argument / call order */
+#define UTMOS_E_NOGPU (-3)    /* no usable CUDA device: there is no CPU fallback */
+#define UTMOS_E_DATA (-4)     /* input data the path cannot represent (e.g. NaN / negative AF on a used row) */
+#define UTMOS_E_NOMEM (-5)    /* device memory exhausted */
+#define UTMOS_E_DEVICE (-6)   /* device-side watchdog tripped (grid barrier timeout) */
+
+/* AF flavour of a context (utmos/select.py:317-320 float64, :218-223 float32 hdf5 flavour) */
+#define UTMOS_AF_NONE 0
+#define UTMOS_AF_F64 1
+#define UTMOS_AF_F32 2
+
+/* utmos_create flags */
+#define UTMOS_F_NO_TRANSPOSE 1u      /* never build the sample-major copy (probe the variant-major matrix) */
+#define UTMOS_F_STEP_KERNELS 2u      /* per-step kernel launches (CUDA graph) instead of the persistent kernel */
+#define UTMOS_F_FORCE_TRANSPOSE 4u   /* fail instead of falling back when the sample-major copy does not fit */
+
+/* stop reasons reported by utmos_select_steps (utmos/select.py:91, :51-52/:93-96, :110-112) */
+#define UTMOS_STOP_NONE 0            /* max_steps of this call done; selection can continue */
+#define UTMOS_STOP_ZERO 1            /* best masked+weighted score == 0: "Ran out of new variants (multi-allelics)" */
+#define UTMOS_STOP_ALL 2             /* tot_captured >= num_vars after the emitted row: "Ran out of new variants" */
+
+const char *utmos_last_error(void);
+const char *utmos_version(void);
+int utmos_device_count(int *count_out);
+
+/* Pinned host memory for callers that want zero-staging H2D copies (numpy arrays can wrap it). */
+int utmos_host_alloc(void **ptr_out, int64_t bytes);
+int utmos_host_free(void *ptr);
+
+/*
+ * Create a selection context on CUDA device `device` for `n_samples` samples.  `rows_hint` (>= 0) sizes
+ * the first device allocation; appends beyond it grow the buffer.
+ */
+int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t rows_hint, int af_mode,
+                 uint32_t flags);
+int utmos_destroy(utmos_ctx *ctx);
+
+/*
+ * Append one .jl part: `n_rows` rows of `pitch_bytes` (>= ceil(S/8)) bytes, MSB-first bit packed
+ * (np.packbits, utmos/convert.py:85), with one float64 AF per row (may be NULL when af_mode == NONE).
+ * Rows without any of the first S bits set are dropped together with their AF (utmos/select.py:276-280).
+ * `rows` / `af` are HOST pointers (pageable or pinned).  The _device variant takes DEVICE pointers on
+ * the context's device (used by the benchmark's resident-input timing).
+ */
+int utmos_append_packed(utmos_ctx *ctx, const uint8_t *rows, int64_t n_rows, int64_t pitch_bytes,
+                        const double *af);
+int utmos_append_packed_device(utmos_ctx *ctx, const uint8_t *d_rows, int64_t n_rows, int64_t pitch_bytes,
+                               const double *d_af);
+
+/*
+ * Append a dense hdf5 chunk: n_rows x S bytes (bool, nonzero = present) or n_rows x S float32 holding
+ * GT*AF (utmos/select.py:219-231); for the float flavour the per-row AF is recovered from the row.
+ * Host pointers; chunks are streamed through pinned staging on a side stream.  Every row is kept (the
+ * file's row count is num_vars, select.py:153; the uninformative-row filter ran before the file was written).
+ */
+int utmos_append_dense_u8(utmos_ctx *ctx, const uint8_t *chunk, int64_t n_rows);
+int utmos_append_dense_f32(utmos_ctx *ctx, const float *chunk, int64_t n_rows);
+
+/*
+ * Close ingestion: builds the sample-major copy (unless it does not fit / is disabled), the per-sample
+ * totals and the initial gains.  num_vars_out = informative rows (utmos/select.py:153, data.shape[0]);
+ * var_count_out[S] = per-sample totals over all informative rows (utmos/select.py:281-284).
+ */
+int utmos_finalize(utmos_ctx *ctx, int64_t *num_vars_out, int64_t *var_count_out);
+
+/*
+ * (Re)start a selection: mask[S] (1 selectable, 2 excluded, 0 already used; utmos/select.py:168-175) and
+ * weights[S] or NULL (utmos/select.py:181-187).  Resets coverage, so one context can run many selections.
+ */
+int utmos_select_begin(utmos_ctx *ctx, const uint8_t *mask, const double *weights);
+
+/*
+ * Run up to max_steps greedy steps, continuing from the current state.  For every emitted report row i:
+ * idx_out[i] = sample index (first index among equal scores, np.argmax, utmos/select.py:48),
+ * new_out[i] = new_count (utmos/select.py:49), score_out[i] = winning score after mask and weights
+ * (may be NULL).  *n_out rows were written (<= max_steps); *stop_out is a UTMOS_STOP_* value.
+ */
+int utmos_select_steps(utmos_ctx *ctx, int64_t max_steps, int64_t *idx_out, int64_t *new_out,
+                       double *score_out, int64_t *n_out, int *stop_out);
+
+/*
+ * utmos/convert.py:57-87 on a host int8 tensor gt[V][S][ploidy] (missing allele = -1).
+ * packed_out: V x ceil(S/8) bytes, MSB-first (np.packbits); af_out[V] (NaN when no allele is called);
+ * singleton_out[V] (may be NULL) = count(allele 1)==1 || count(allele 0)==1 (convert.py:58-60).
+ */
+int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_samples, int64_t ploidy,
+                     uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
+                     uint8_t *singleton_out);
+
+/* ---- introspection (tests, benchmark) ---- */
+
+/* Current per-sample state: gain counts (new_count each sample would get now) and unweighted, unmasked scores. */
+int utmos_debug_gains(utmos_ctx *ctx, int64_t *count_out, double *score_out);
+
+/* info[0]=num_vars, [1]=row pitch bytes, [2]=has sample-major copy, [3]=device bytes in use,
+ * [4]=fixed-point scale (AF flavours), [5]=AF values not exactly representable (count), [6]=kernels launched,
+ * [7]=persistent kernel used (0/1) */
+int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
+
+/* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:
+ * ms[0]=h2d copies, [1]=ingest kernels, [2]=transpose, [3]=column reduce / gain init, [4]=select loop */
+int utmos_timings(utmos_ctx *ctx, double *ms, int n, int reset);
+
+/* ---- host-side codecs of the hdf5 chunk streamer (no device work) ----
+ * hdf5 filter 32000 "lzf" as written by h5py for compression="lzf" (utmos/select.py:208-238).
+ * decompress: returns decoded length or -1; compress: returns encoded length or 0 if it does not fit. */
+int64_t utmos_lzf_decompress(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_cap);
+int64_t utmos_lzf_compress(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_cap);
+
+/* ---- synthetic benchmark / test input generated in HBM (utmos_b200/synth.py holds the NumPy mirror) ----
+ * Raw device buffers for the resident-input benchmark leg, and a deterministic cohort generator:
+ * rows row0..row0+n_rows-1 in the .jl layout (MSB-first, pitch ceil(S/8)) + per-row AF, from host tables
+ * cdf_thr[kmax+1] (allele-count CDF thresholds) and p_thr[kmax+1] (carrier probability thresholds). */
+int utmos_device_alloc(int device, void **ptr_out, int64_t bytes);
+int utmos_device_free(int device, void *ptr);
+int utmos_device_to_host(int device, void *dst, const void *d_src, int64_t bytes);
+int utmos_synth_packed_device(int device, uint64_t seed, int64_t row0, int64_t n_rows, int64_t n_samples,
+                              const uint64_t *cdf_thr, const uint32_t *p_thr, int64_t kmax, uint8_t *d_rows,
+                              double *d_af);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UTMOS_B200_H */

@@ -1,0 +1,158 @@
+"""CPU-side tests: the C-ABI library loads and exports its surface, host parsers, hdf5 reader, CLI plumbing."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import select_oracle as orc
+from tests import helpers as H
+from utmos_b200 import _native, h5lite, synth, vcf
+from utmos_b200 import select as usel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "utmos_b200.h")).read()
+    declared = set(re.findall(r"\b(utmos_[a-z0-9_]+)\s*\(", header))
+    declared.discard("utmos_ctx")
+    lib = _native.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.SYMBOLS)
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _native.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeError) as err:
+        _native.DeviceMatrix(8)
+    assert err.value.code == _native.E_NOGPU
+    with pytest.raises(_native.NativeError):
+        _native.convert_gt(np.zeros((2, 3, 2), dtype=np.int8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "utmos_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, name
+
+
+def test_lzf_roundtrip_and_fixture_decode():
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 2, 3, 17, 300, 5000, 70000):
+        for kind in range(3):
+            if kind == 0:
+                data = rng.integers(0, 2, n, dtype=np.uint8)
+            elif kind == 1:
+                data = np.repeat(rng.integers(0, 255, max(1, n // 40), dtype=np.uint8), 40)[:n]
+            else:
+                data = rng.integers(0, 256, n, dtype=np.uint8)
+            comp = _native.lzf_compress(data.tobytes())
+            if comp is not None:
+                assert _native.lzf_decompress(comp, len(data)).tobytes() == data.tobytes()
+
+
+def test_h5lite_reads_reference_fixtures():
+    parts = H.load_jl_parts(["chunk2.jl"])
+    dense, _, _ = orc.unpack_and_filter(parts[0]["GT"], 2504)
+    with h5lite.H5File(H.fixture("tiny.hdf5")) as h5:
+        assert set(h5.keys()) == {"data", "samples", "var_count"}
+        data = h5["data"]
+        assert data.shape == dense.shape and data.dtype == np.dtype(bool) and data.chunks == (99, 2504)
+        assert np.array_equal(data.read(), dense)
+        assert np.array_equal(h5["var_count"].read(), dense.sum(axis=0))
+        assert list(h5["samples"].read().astype(str)) == list(np.asarray(parts[0]["samples"]).astype(str))
+        first_rows = [first for first, _ in data.iter_chunks()]
+        assert first_rows == list(range(0, 995, 99))
+    parts = H.load_jl_parts(["chunk0.jl", "chunk1.jl"])
+    matrix, var_count = orc.load_parts(parts, 2504, float32_af=True)
+    with h5lite.H5File(H.fixture("tiny.af.hdf5")) as h5:
+        assert h5["data"].dtype == np.float32
+        assert np.array_equal(h5["data"].read(), matrix)
+        assert np.array_equal(h5["var_count"].read(), var_count)
+
+
+@pytest.mark.parametrize("name", ["chunk0", "chunk1"])
+def test_vcf_reader_and_convert_oracle_reproduce_fixture_jl(name):
+    """chunkN.vcf.gz -> GT bits and het/hom stats of chunkN.jl (AF: fixture holds the older definition)."""
+    gold = H.load_jl_parts([name + ".jl"])[0]
+    blocks = list(vcf.read_vcf_genotypes(H.fixture(name + ".vcf.gz"), 400))
+    samples = blocks[0][0]
+    gts = np.concatenate([b[1] for b in blocks])
+    assert gts.shape == (1000, 2504, 2)
+    assert list(samples) == list(np.asarray(gold["samples"]).astype(str))
+    out = orc.convert_gt_c(gts)
+    assert np.array_equal(out["GT"], gold["GT"])
+    assert out["stats"]["num_het"] == gold["stats"]["num_het"]
+    assert out["stats"]["num_hom"] == gold["stats"]["num_hom"]
+    # biallelic rows: max-alt AF == allele-1 AF, which is what the fixture stores
+    multi = (gts > 1).any(axis=(1, 2))
+    assert np.array_equal(out["AF"][~multi], gold["AF"][~multi])
+
+
+def test_vcf_gt_token_forms():
+    assert vcf._parse_gt("0|1") == (0, 1)
+    assert vcf._parse_gt("1/2") == (1, 2)
+    assert vcf._parse_gt("./.") == (-1, -1)
+    assert vcf._parse_gt(".|1") == (-1, 1)
+    assert vcf._parse_gt("1") == (1, -1)
+    assert vcf._parse_gt("10|12") == (10, 12)
+    assert vcf._parse_gt("0/1/1") == (0, 1)
+
+
+def test_convert_oracle_edge_genotypes():
+    gt = np.array([[[0, 0], [0, 1], [1, 1], [-1, 1], [2, 1], [-1, -1], [2, 2], [1, -1]]], dtype=np.int8)
+    out = orc.convert_gt_c(gt)
+    bits = np.unpackbits(out["GT"], axis=1, count=8)[0]
+    assert list(bits) == [0, 1, 1, 0, 1, 0, 1, 0]
+    assert out["stats"] == {"num_het": 2, "num_hom": 2}
+    assert out["AF"][0, 0] == 6 / 12                      # allele 1: 6 of 12 called alleles; allele 2: 3
+    empty = orc.convert_gt_c(np.full((1, 4, 2), -1, dtype=np.int8))
+    assert np.isnan(empty["AF"][0, 0])
+
+
+def test_count_resolution_and_sample_lists(tmp_path):
+    assert usel.resolve_select_count(-1, 2504) == 2504
+    assert usel.resolve_select_count(0.02, 2504) == 50
+    assert usel.resolve_select_count(0.01, 2504) == 25
+    assert usel.resolve_select_count(0, 2504) == 1
+    assert usel.resolve_select_count(1.0, 2504) == 1
+    assert usel.resolve_select_count(10, 2504) == 10
+    for c in (-1, 0, 0.005, 0.02, 0.9999, 1, 1.5, 20, 5000):
+        assert usel.resolve_select_count(c, 2504) == orc.resolve_count(c, 2504)
+    lst = tmp_path / "names.txt"
+    lst.write_text("A\nB \nC\n")
+    assert usel.parse_sample_lists([str(lst), "X,Y"]) == ["A", "B", "C", "X", "Y"]
+    assert usel.parse_sample_lists(None) == []
+    wts = usel.parse_weights(H.fixture("weights.txt"))
+    assert float(wts.loc["HG00280", "weight"]) == 4 and float(wts.loc["NA20320", "weight"]) == 10
+    assert usel.parse_weights(None) is None
+
+
+def test_cli_argument_errors(tmp_path):
+    for argv in (["a.hdf5", "b.hdf5"], [], ["nothere.txt"]):
+        with pytest.raises(SystemExit) as err:
+            args = usel.parse_args(argv)
+            usel.load_files(args.in_files, args.lowmem, args.buffer, args.af)
+        assert err.value.code == 1
+    args = usel.parse_args(["x.hdf5"])
+    assert args.lowmem == 1
+    args = usel.parse_args(["--lowmem", "y.hdf5"])
+    assert args.lowmem == 1 and args.in_files == ["y.hdf5"]
+    args = usel.parse_args(["--subset", "a", "--subset", "b", "--exclude", "c", "f.jl"])
+    assert args.subset == ["a", "b"] and args.exclude == ["c"] and args.count == 0.02
+
+
+def test_synth_mirror_is_deterministic_and_informative():
+    gt1, af1 = synth.mirror_rows(3, 100, 500, 333)
+    gt2, af2 = synth.mirror_rows(3, 0, 600, 333)
+    assert np.array_equal(gt1, gt2[100:600]) and np.array_equal(af1, af2[100:600])
+    bits = np.unpackbits(gt1, axis=1, count=333)
+    assert bits.any(axis=1).all()
+    assert not np.unpackbits(gt1, axis=1)[:, 333:].any()
+    assert ((af1 > 0) & (af1 <= 1)).all()

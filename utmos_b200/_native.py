@@ -1,0 +1,310 @@
+"""ctypes binding of libutmos_b200.so (include/utmos_b200.h).  The only bridge to the CUDA code.
+
+There is deliberately no fallback: if the shared library is missing, or no B200 is visible, every
+compute entry point raises ``NativeError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libutmos_b200.so")
+
+AF_NONE, AF_F64, AF_F32 = 0, 1, 2
+F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE = 1, 2, 4
+STOP_NONE, STOP_ZERO, STOP_ALL = 0, 1, 2
+E_NOGPU = -3
+
+# every symbol include/utmos_b200.h declares (tests check the library exports all of them)
+SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
+           "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
+           "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_finalize", "utmos_select_begin",
+           "utmos_select_steps", "utmos_convert_gt", "utmos_debug_gains", "utmos_info", "utmos_timings",
+           "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_device_alloc", "utmos_device_free",
+           "utmos_device_to_host", "utmos_synth_packed_device"]
+
+
+class NativeError(RuntimeError):
+    """A call into libutmos_b200.so failed."""
+
+    def __init__(self, code, message):
+        super().__init__(f"libutmos_b200 error {code}: {message}")
+        self.code = code
+
+
+_LIB = None
+
+
+def lib():
+    """Load the shared library (built in-tree by `python -m utmos_b200.build`)."""
+    global _LIB  # pylint: disable=global-statement
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(-100, f"{LIB_PATH} is missing: build it with `python -m utmos_b200.build` "
+                                "(needs nvcc; there is no CPU fallback)")
+    dll = ctypes.CDLL(LIB_PATH)
+    i64, i32, u32, p = ctypes.c_int64, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    sig = {
+        "utmos_last_error": (ctypes.c_char_p, []),
+        "utmos_version": (ctypes.c_char_p, []),
+        "utmos_device_count": (i32, [ctypes.POINTER(i32)]),
+        "utmos_host_alloc": (i32, [pp, i64]),
+        "utmos_host_free": (i32, [p]),
+        "utmos_create": (i32, [pp, i32, i64, i64, i32, u32]),
+        "utmos_destroy": (i32, [p]),
+        "utmos_append_packed": (i32, [p, p, i64, i64, p]),
+        "utmos_append_packed_device": (i32, [p, p, i64, i64, p]),
+        "utmos_append_dense_u8": (i32, [p, p, i64]),
+        "utmos_append_dense_f32": (i32, [p, p, i64]),
+        "utmos_finalize": (i32, [p, ctypes.POINTER(i64), p]),
+        "utmos_select_begin": (i32, [p, p, p]),
+        "utmos_select_steps": (i32, [p, i64, p, p, p, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
+        "utmos_convert_gt": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p]),
+        "utmos_debug_gains": (i32, [p, p, p]),
+        "utmos_info": (i32, [p, p, i32]),
+        "utmos_timings": (i32, [p, p, i32, i32]),
+        "utmos_lzf_decompress": (i64, [p, i64, p, i64]),
+        "utmos_lzf_compress": (i64, [p, i64, p, i64]),
+        "utmos_device_alloc": (i32, [i32, pp, i64]),
+        "utmos_device_free": (i32, [i32, p]),
+        "utmos_device_to_host": (i32, [i32, p, p, i64]),
+        "utmos_synth_packed_device": (i32, [i32, ctypes.c_uint64, i64, i64, i64, p, p, i64, p, p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(dll, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = dll
+    return dll
+
+
+def check(code):
+    """Raise NativeError for a non-zero return code."""
+    if code != 0:
+        raise NativeError(code, lib().utmos_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    """Number of visible CUDA devices (0 on a CPU box)."""
+    n = ctypes.c_int(0)
+    check(lib().utmos_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def _ptr(arr):
+    return None if arr is None else arr.ctypes.data_as(ctypes.c_void_p)
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint8 array (zero-staging H2D copies)."""
+
+    def __init__(self, nbytes):
+        self._ptr = ctypes.c_void_p()
+        check(lib().utmos_host_alloc(ctypes.byref(self._ptr), int(nbytes)))
+        self.nbytes = int(nbytes)
+        buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes)
+
+    def close(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            lib().utmos_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+class DeviceMatrix:
+    """Bit-packed presence matrix resident in HBM plus the greedy-selection state machine.
+
+    Stands in for the dense ``data['data']`` ndarray / h5py dataset of the reference: exposes ``.shape``
+    ``(num_vars, num_samples)`` and ``.dtype`` (bool, float64 or float32), which is all ``select_main`` and
+    ``run_selection`` look at (utmos/select.py:153, :429-433).
+    """
+
+    def __init__(self, n_samples, af_mode=AF_NONE, rows_hint=0, device=0, flags=0):
+        self._ctx = ctypes.c_void_p()
+        self.n_samples = int(n_samples)
+        self.af_mode = af_mode
+        self.num_vars = None
+        self.var_count = None
+        flags |= int(os.environ.get("UTMOS_B200_FLAGS", "0"))     # test / debugging override of the kernel flavour
+        check(lib().utmos_create(ctypes.byref(self._ctx), device, self.n_samples, int(rows_hint), af_mode, flags))
+
+    # -- ingestion ---------------------------------------------------------------------------------
+    def append_packed(self, gt, af=None):
+        """One .jl part: uint8 [V, >=ceil(S/8)] MSB-first rows (+ float64 AF per row)."""
+        gt = np.ascontiguousarray(gt, dtype=np.uint8)
+        if gt.ndim != 2:
+            raise ValueError("GT must be 2-D")
+        if af is not None:
+            af = np.ascontiguousarray(np.asarray(af, dtype=np.float64).reshape(-1))
+            if len(af) != gt.shape[0]:
+                raise ValueError("AF length does not match GT rows")
+        if self.af_mode == AF_NONE:
+            af = None
+        check(lib().utmos_append_packed(self._ctx, _ptr(gt), gt.shape[0], gt.shape[1], _ptr(af)))
+
+    def append_packed_device(self, d_rows, n_rows, pitch, d_af=None):
+        """Rows already resident in HBM (raw device pointers as ints)."""
+        check(lib().utmos_append_packed_device(self._ctx, ctypes.c_void_p(d_rows), n_rows, pitch,
+                                               ctypes.c_void_p(d_af) if d_af else None))
+
+    def append_dense(self, chunk):
+        """One hdf5 chunk: bool/uint8 [n, S] or float32 [n, S] (GT*AF)."""
+        if chunk.dtype == np.float32:
+            chunk = np.ascontiguousarray(chunk)
+            check(lib().utmos_append_dense_f32(self._ctx, _ptr(chunk), chunk.shape[0]))
+        else:
+            chunk = np.ascontiguousarray(chunk).view(np.uint8)
+            check(lib().utmos_append_dense_u8(self._ctx, _ptr(chunk), chunk.shape[0]))
+
+    def finalize(self):
+        """Close ingestion; returns var_count (int64[S])."""
+        nv = ctypes.c_int64(0)
+        vc = np.zeros(self.n_samples, dtype=np.int64)
+        check(lib().utmos_finalize(self._ctx, ctypes.byref(nv), _ptr(vc)))
+        self.num_vars = nv.value
+        self.var_count = vc
+        return vc
+
+    # -- what the reference looks at ---------------------------------------------------------------
+    @property
+    def shape(self):
+        return (self.num_vars, self.n_samples)
+
+    @property
+    def dtype(self):
+        return {AF_NONE: np.dtype(bool), AF_F64: np.dtype(np.float64), AF_F32: np.dtype(np.float32)}[self.af_mode]
+
+    # -- selection ---------------------------------------------------------------------------------
+    def begin(self, mask, weights=None):
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.float64)
+        check(lib().utmos_select_begin(self._ctx, _ptr(mask), _ptr(weights)))
+
+    def steps(self, max_steps):
+        """Up to max_steps greedy steps -> (idx int64[n], new int64[n], score float64[n], stop)."""
+        cap = max(1, min(int(max_steps), self.n_samples))
+        idx = np.zeros(cap, dtype=np.int64)
+        new = np.zeros(cap, dtype=np.int64)
+        score = np.zeros(cap, dtype=np.float64)
+        n = ctypes.c_int64(0)
+        stop = ctypes.c_int(0)
+        check(lib().utmos_select_steps(self._ctx, int(max_steps), _ptr(idx), _ptr(new), _ptr(score),
+                                       ctypes.byref(n), ctypes.byref(stop)))
+        return idx[:n.value], new[:n.value], score[:n.value], stop.value
+
+    # -- introspection -----------------------------------------------------------------------------
+    def gains(self):
+        cnt = np.zeros(self.n_samples, dtype=np.int64)
+        score = np.zeros(self.n_samples, dtype=np.float64)
+        check(lib().utmos_debug_gains(self._ctx, _ptr(cnt), _ptr(score)))
+        return cnt, score
+
+    def info(self):
+        arr = np.zeros(8, dtype=np.int64)
+        check(lib().utmos_info(self._ctx, _ptr(arr), 8))
+        keys = ["num_vars", "row_pitch_bytes", "has_sample_major", "device_bytes", "fixed_scale", "af_inexact",
+                "kernel_launches", "persistent"]
+        return dict(zip(keys, (int(x) for x in arr)))
+
+    def timings(self, reset=False):
+        arr = np.zeros(5, dtype=np.float64)
+        check(lib().utmos_timings(self._ctx, _ptr(arr), 5, 1 if reset else 0))
+        return dict(zip(["h2d_ms", "ingest_ms", "transpose_ms", "gain_ms", "select_ms"], (float(x) for x in arr)))
+
+    def close(self):
+        if self._ctx is not None and self._ctx.value:
+            lib().utmos_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+def convert_gt(gt, device=0):
+    """utmos/convert.py:57-87 on the GPU.  gt: int8 [V, S, ploidy].  Returns (packed, af(V,1), num_het, num_hom,
+    singleton flags)."""
+    gt = np.ascontiguousarray(gt, dtype=np.int8)
+    if gt.ndim != 3:
+        raise ValueError("GT tensor must be [variants, samples, ploidy]")
+    n_vars, n_samples, ploidy = gt.shape
+    packed = np.zeros((n_vars, (n_samples + 7) // 8), dtype=np.uint8)
+    af = np.zeros(n_vars, dtype=np.float64)
+    single = np.zeros(n_vars, dtype=np.uint8)
+    het = ctypes.c_int64(0)
+    hom = ctypes.c_int64(0)
+    check(lib().utmos_convert_gt(device, _ptr(gt), n_vars, n_samples, ploidy, _ptr(packed), _ptr(af),
+                                 ctypes.byref(het), ctypes.byref(hom), _ptr(single)))
+    return packed, af.reshape(-1, 1), het.value, hom.value, single.astype(bool)
+
+
+def lzf_decompress(data, out_len):
+    """liblzf-format block -> bytes of exactly out_len (hdf5 filter 32000; host code in the native lib)."""
+    src = np.frombuffer(data, dtype=np.uint8)
+    dst = np.empty(out_len, dtype=np.uint8)
+    got = lib().utmos_lzf_decompress(_ptr(src), len(src), _ptr(dst), out_len)
+    if got != out_len:
+        raise ValueError(f"lzf: expected {out_len} bytes, decoded {got}")
+    return dst
+
+
+def lzf_compress(data):
+    """bytes -> liblzf-format block, or None when it does not shrink (stored raw, filter_mask bit 0)."""
+    src = np.frombuffer(data, dtype=np.uint8)
+    dst = np.empty(max(len(src) - 1, 1), dtype=np.uint8)
+    got = lib().utmos_lzf_compress(_ptr(src), len(src), _ptr(dst), len(dst))
+    if got <= 0:
+        return None
+    return dst[:got].tobytes()
+
+
+class DeviceBuffer:
+    """Raw cudaMalloc'd buffer (benchmark inputs resident in HBM)."""
+
+    def __init__(self, nbytes, device=0):
+        self.device = device
+        self.nbytes = int(nbytes)
+        self._ptr = ctypes.c_void_p()
+        check(lib().utmos_device_alloc(device, ctypes.byref(self._ptr), self.nbytes))
+
+    @property
+    def ptr(self):
+        return self._ptr.value
+
+    def to_host(self, out=None):
+        if out is None:
+            out = np.empty(self.nbytes, dtype=np.uint8)
+        check(lib().utmos_device_to_host(self.device, _ptr(out), self._ptr, self.nbytes))
+        return out
+
+    def close(self):
+        if self._ptr is not None and self._ptr.value:
+            lib().utmos_device_free(self.device, self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+
+def synth_packed_device(seed, row0, n_rows, n_samples, cdf_thr, p_thr, d_rows, d_af, device=0):
+    """Fill device buffers with synthetic cohort rows (see utmos_b200/synth.py for the tables / mirror)."""
+    cdf_thr = np.ascontiguousarray(cdf_thr, dtype=np.uint64)
+    p_thr = np.ascontiguousarray(p_thr, dtype=np.uint32)
+    check(lib().utmos_synth_packed_device(device, seed, row0, n_rows, n_samples, _ptr(cdf_thr), _ptr(p_thr),
+                                          len(cdf_thr) - 1, ctypes.c_void_p(d_rows.ptr), ctypes.c_void_p(d_af.ptr)))

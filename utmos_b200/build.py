@@ -1,0 +1,53 @@
+"""Build libutmos_b200.so (nvcc, sm_100a only) in-tree.  `python -m utmos_b200.build [--force]`."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libutmos_b200.so")
+SOURCES = ["api.cu", "ingest.cu", "select.cu", "convert.cu", "hostio.cu", "synth.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "utmos_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+         "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a and link the shared library.  Returns the library path."""
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, proc in procs:
+        out, _ = proc.communicate()
+        log.append(f"==== {src}\n{out}")
+        if proc.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {src}")
+    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as fh:
+        fh.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

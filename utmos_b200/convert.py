@@ -1,0 +1,91 @@
+"""convert vcfs to lightweight numpy arrays
+
+Host-side mirror of utmos/convert.py (same CLI, same ``read_vcf`` return value); the numeric core -- presence,
+het/hom totals, max-alt allele frequency, bit packing, singleton flags -- runs in the K1 CUDA kernel
+(csrc/convert.cu) through ``_native.convert_gt``.
+"""
+import argparse
+import json
+import logging
+
+import joblib
+import numpy as np
+
+from utmos_b200 import _native
+from utmos_b200.logutil import setup_logging
+from utmos_b200.vcf import read_vcf_genotypes
+
+
+def parse_args(args):
+    """
+    Pull the command line parameters (utmos/convert.py:16-40)
+    """
+    parser = argparse.ArgumentParser(prog="convert", description=__doc__.split("\n")[0],
+                                     formatter_class=argparse.RawDescriptionHelpFormatter)
+    parser.add_argument("in_file", type=str, help="Input VCF")
+    parser.add_argument("out_file", type=str, help="Output joblib")
+    parser.add_argument("--no-singleton", action="store_true", help="Remove singleton variants")
+    parser.add_argument("--lowmem", action="store_true",
+                        help="Lower memory usage with hdf5 temporary files (%(default)s)")
+    parser.add_argument("-B", "--buffer", type=int, default=50000,
+                        help="Number of variants read at a time (%(default)s)")
+    parser.add_argument("-c", "--compress", type=int, default=5, help="joblib compress level 1-9 (%(default)s)")
+    args = parser.parse_args(args)
+    setup_logging()
+    logging.info("Params:\n%s", json.dumps(vars(args), indent=4))
+    return args
+
+
+def read_vcf(in_file, lowmem=False, chunk_length=2000, no_singleton=False, device=0):
+    """
+    Read a vcf's genotypes and return numpy arrays (utmos/convert.py:43-88).
+
+    ``lowmem`` is accepted for compatibility: genotype blocks of ``chunk_length`` variants are always
+    streamed through the GPU, so host memory never holds more than one block of int8 genotypes.
+    """
+    del lowmem
+    logging.info("Reading VCF")
+    packed_parts, af_parts = [], []
+    num_hets = num_homs = 0
+    samples = None
+    removed = 0
+    for samples, gts in read_vcf_genotypes(in_file, chunk_length):
+        if gts.shape[0] == 0:
+            continue
+        packed, af, het, hom, single = _native.convert_gt(gts, device)
+        if no_singleton:
+            # utmos/convert.py:58-62 drops singleton rows BEFORE presence / stats / AF are computed
+            removed += int(single.sum())
+            keep = ~single
+            if not keep.all():
+                if keep.any():
+                    packed, af, het, hom, _ = _native.convert_gt(gts[keep], device)
+                else:
+                    packed, af, het, hom = packed[:0], af[:0], 0, 0
+        num_hets += het
+        num_homs += hom
+        packed_parts.append(packed)
+        af_parts.append(af)
+    if samples is None:
+        raise ValueError(f"{in_file}: empty VCF")
+    if no_singleton:
+        logging.info("Removing %d singletons", removed)
+    logging.info(f"{num_hets} hets")
+    logging.info(f"{num_homs} homs")
+    pitch = (len(samples) + 7) // 8
+    data = {"samples": samples.astype(str)}
+    data["GT"] = np.concatenate(packed_parts) if packed_parts else np.zeros((0, pitch), dtype=np.uint8)
+    data["AF"] = np.concatenate(af_parts) if af_parts else np.zeros((0, 1), dtype=np.float64)
+    data["stats"] = {"num_het": np.int64(num_hets), "num_hom": np.int64(num_homs)}
+    return data
+
+
+def cvt_main(cmdargs):
+    """
+    Main (utmos/convert.py:91-99)
+    """
+    args = parse_args(cmdargs)
+    data = read_vcf(args.in_file, args.lowmem, args.buffer, args.no_singleton)
+    logging.info("Saving genotypes")
+    joblib.dump(data, args.out_file, compress=args.compress)
+    logging.info("Finished conversion")

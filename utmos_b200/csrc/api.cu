@@ -1,0 +1,768 @@
+// api.cu -- context management and the extern "C" surface declared in include/utmos_b200.h.
+//
+// HBM layout owned by a context (S samples, V informative rows):
+//   rows   uint32 [V][pitchW]        variant-major bit matrix, pitchW = ceil(S/32) rounded up to 4 words
+//   cols   uint32 [S32][colPitchW]   sample-major copy (built at finalize when it fits), colPitchW =
+//                                    ceil(V/32) rounded up to 8 words
+//   af     double [V]                per-row allele frequency (AF flavours only)
+//   q_lo/q_hi uint64 [V]             AF * 2^scale as two limbs of L bits (AF flavours only)
+//   live0/live uint32 [colPitchW]    scoring rows at step 0 / rows not yet covered
+//   gain0_* / gain_*  [S]            per-sample gains at step 0 / current
+//   mask u8[S], weights f64[S], out_{idx,new,score}[S], SelState
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace utmos {
+
+static thread_local std::string g_error;
+
+void set_error(const std::string &msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)err, cudaGetErrorString(err), file, line, what);
+    g_error = buf;
+    cudaGetLastError();   // clear the sticky-less error state
+    if (err == cudaErrorMemoryAllocation) return UTMOS_E_NOMEM;
+    if (err == cudaErrorNoDevice || err == cudaErrorInsufficientDriver) return UTMOS_E_NOGPU;
+    return UTMOS_E_CUDA;
+}
+
+namespace {
+constexpr size_t kStageBytes = 64ull << 20;      // per staging buffer (two pinned host + two device)
+constexpr int kGraphSteps = 32;                  // step pairs per CUDA graph replay
+enum { T_H2D = 0, T_INGEST = 1, T_TRANSPOSE = 2, T_GAIN = 3, T_SELECT = 4, T_COUNT = 5 };
+
+struct Pending {
+    int cat;
+    cudaEvent_t a, b;
+};
+}  // namespace
+
+}  // namespace utmos
+
+using namespace utmos;
+
+struct utmos_ctx {
+    int device = 0;
+    int n_sms = 0;
+    long long S = 0;
+    int nW = 0, pitchW = 0;
+    int af_mode = UTMOS_AF_NONE;
+    uint32_t flags = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+
+    uint32_t *d_rows = nullptr;
+    double *d_af = nullptr;
+    long long rows_cap = 0;
+    long long rows_upper = 0;          // upper bound of rows stored (kept rows are only known on the device)
+    long long *d_nrows = nullptr;      // [0] rows stored, [1] scratch
+    IngestScratch scratch;
+
+    void *h_stage[2] = {nullptr, nullptr};
+    void *d_stage[2] = {nullptr, nullptr};
+    double *h_af_stage[2] = {nullptr, nullptr};
+    double *d_af_stage[2] = {nullptr, nullptr};
+    long long af_stage_rows = 0;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+    bool stage_used[2] = {false, false};
+    int stage_next = 0;
+
+    bool finalized = false;
+    long long V = 0, colPitchW = 0;
+    int L = 0, scale = 0;
+    uint32_t *d_cols = nullptr, *d_live = nullptr, *d_live0 = nullptr;
+    unsigned int *d_gain_cnt = nullptr, *d_gain0_cnt = nullptr, *d_var_count = nullptr;
+    unsigned long long *d_gain_lo = nullptr, *d_gain_hi = nullptr, *d_gain0_lo = nullptr, *d_gain0_hi = nullptr;
+    unsigned long long *d_q_lo = nullptr, *d_q_hi = nullptr;
+    uint8_t *d_mask = nullptr;
+    double *d_weights = nullptr;
+    bool has_weights = false;
+    long long *d_out_idx = nullptr, *d_out_new = nullptr;
+    double *d_out_score = nullptr, *d_dbg_score = nullptr;
+    SelState *d_state = nullptr;
+    unsigned int *d_bar = nullptr;
+    ArgPartial *d_partials = nullptr;
+    int grid = 0, block = 0;
+    bool selecting = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool persistent_used = false;
+    unsigned int af_inexact = 0;
+
+    int n_launch = 0;
+    double ms[T_COUNT] = {0, 0, 0, 0, 0};
+    std::vector<Pending> pending;
+    size_t dev_bytes = 0;
+};
+
+namespace {
+
+int dev_alloc(utmos_ctx *c, void **p, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    UT_CUDA(cudaMalloc(p, bytes));
+    c->dev_bytes += bytes;
+    return UTMOS_OK;
+}
+
+template <typename T>
+void dev_free(utmos_ctx *c, T *&p, size_t bytes)
+{
+    if (p) {
+        cudaFree(p);
+        c->dev_bytes -= std::min(c->dev_bytes, bytes ? bytes : (size_t)16);
+        p = nullptr;
+    }
+}
+
+void t_begin(utmos_ctx *c, int cat, cudaStream_t s)
+{
+    Pending p;
+    p.cat = cat;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    cudaEventRecord(p.a, s);
+    c->pending.push_back(p);
+}
+
+void t_end(utmos_ctx *c, cudaStream_t s) { cudaEventRecord(c->pending.back().b, s); }
+
+void t_resolve(utmos_ctx *c)      // call only after the streams have been synchronised
+{
+    for (auto &p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->ms[p.cat] += ms;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    c->pending.clear();
+    cudaGetLastError();
+}
+
+int sync_all(utmos_ctx *c)
+{
+    UT_CUDA(cudaStreamSynchronize(c->copy_stream));
+    UT_CUDA(cudaStreamSynchronize(c->stream));
+    t_resolve(c);
+    return UTMOS_OK;
+}
+
+int grow_rows(utmos_ctx *c, long long need)
+{
+    if (need <= c->rows_cap) return UTMOS_OK;
+    long long cap = std::max(need, c->rows_cap + c->rows_cap / 2);
+    cap = std::max(cap, 1024ll);
+    uint32_t *nr = nullptr;
+    double *na = nullptr;
+    const size_t row_bytes = (size_t)c->pitchW * 4;
+    UT_TRY(dev_alloc(c, (void **)&nr, (size_t)cap * row_bytes));
+    if (c->af_mode != UTMOS_AF_NONE) UT_TRY(dev_alloc(c, (void **)&na, (size_t)cap * 8));
+    if (c->d_rows) {
+        // rows already ingested are copied over stream-ordered behind the ingest kernels
+        UT_CUDA(cudaMemcpyAsync(nr, c->d_rows, (size_t)c->rows_upper * row_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (na) UT_CUDA(cudaMemcpyAsync(na, c->d_af, (size_t)c->rows_upper * 8, cudaMemcpyDeviceToDevice, c->stream));
+        UT_CUDA(cudaStreamSynchronize(c->stream));
+        dev_free(c, c->d_rows, (size_t)c->rows_cap * row_bytes);
+        dev_free(c, c->d_af, (size_t)c->rows_cap * 8);
+    }
+    c->d_rows = nr;
+    c->d_af = na;
+    c->rows_cap = cap;
+    return UTMOS_OK;
+}
+
+int ensure_stage(utmos_ctx *c, long long af_rows)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (!c->d_stage[i]) {
+            UT_TRY(dev_alloc(c, &c->d_stage[i], kStageBytes));
+            UT_CUDA(cudaMallocHost(&c->h_stage[i], kStageBytes));
+            UT_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+            UT_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    if (af_rows > c->af_stage_rows) {
+        UT_CUDA(cudaStreamSynchronize(c->stream));
+        UT_CUDA(cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; ++i) {
+            dev_free(c, c->d_af_stage[i], (size_t)c->af_stage_rows * 8);
+            if (c->h_af_stage[i]) cudaFreeHost(c->h_af_stage[i]);
+            UT_TRY(dev_alloc(c, (void **)&c->d_af_stage[i], (size_t)af_rows * 8));
+            UT_CUDA(cudaMallocHost((void **)&c->h_af_stage[i], (size_t)af_rows * 8));
+        }
+        c->af_stage_rows = af_rows;
+    }
+    return UTMOS_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// host chunk pipeline: (pageable -> pinned staging ->) cudaMemcpyAsync on the copy stream -> ingest kernels
+int append_host(utmos_ctx *c, int kind, const void *src, long long n_rows, long long pitch_in, const double *af)
+{
+    if (c->finalized) { set_error("append after finalize"); return UTMOS_E_ARG; }
+    if (n_rows < 0 || (n_rows > 0 && !src)) { set_error("append: bad rows pointer / count"); return UTMOS_E_ARG; }
+    if (n_rows == 0) return UTMOS_OK;
+    const bool want_af = c->af_mode != UTMOS_AF_NONE;
+    if (kind == RAW_PACKED_MSB && want_af && !af) { set_error("append_packed: AF required for an AF context"); return UTMOS_E_ARG; }
+    UT_TRY(grow_rows(c, c->rows_upper + n_rows));
+    const long long chunk_rows = std::max(1ll, (long long)(kStageBytes / (size_t)pitch_in));
+    if ((size_t)pitch_in > kStageBytes) { set_error("append: one row exceeds the staging buffer"); return UTMOS_E_ARG; }
+    const bool need_af_stage = (kind == RAW_PACKED_MSB && want_af) || kind == RAW_DENSE_F32;
+    UT_TRY(ensure_stage(c, need_af_stage ? std::min(chunk_rows, n_rows) : 0));
+    const bool src_pinned = is_pinned(src);
+    const bool af_pinned = af && is_pinned(af);
+    for (long long r0 = 0; r0 < n_rows; r0 += chunk_rows) {
+        const long long n = std::min(chunk_rows, n_rows - r0);
+        const int b = c->stage_next;
+        c->stage_next ^= 1;
+        const size_t bytes = (size_t)n * (size_t)pitch_in;
+        const uint8_t *chunk = (const uint8_t *)src + (size_t)r0 * (size_t)pitch_in;
+        if (c->stage_used[b]) {
+            UT_CUDA(cudaEventSynchronize(c->ev_consumed[b]));                 // pinned host buffer reusable
+            UT_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+        }
+        t_begin(c, T_H2D, c->copy_stream);
+        if (src_pinned) {
+            UT_CUDA(cudaMemcpyAsync(c->d_stage[b], chunk, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            memcpy(c->h_stage[b], chunk, bytes);
+            UT_CUDA(cudaMemcpyAsync(c->d_stage[b], c->h_stage[b], bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        const double *d_af_chunk = nullptr;
+        if (kind == RAW_PACKED_MSB && want_af) {
+            if (af_pinned) {
+                UT_CUDA(cudaMemcpyAsync(c->d_af_stage[b], af + r0, (size_t)n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+            } else {
+                memcpy(c->h_af_stage[b], af + r0, (size_t)n * 8);
+                UT_CUDA(cudaMemcpyAsync(c->d_af_stage[b], c->h_af_stage[b], (size_t)n * 8, cudaMemcpyHostToDevice,
+                                        c->copy_stream));
+            }
+            d_af_chunk = c->d_af_stage[b];
+        } else if (kind == RAW_DENSE_F32) {
+            d_af_chunk = c->d_af_stage[b];      // filled by the flag kernel
+        }
+        t_end(c, c->copy_stream);
+        UT_CUDA(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        UT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+        t_begin(c, T_INGEST, c->stream);
+        UT_TRY(launch_ingest(c->stream, c->scratch, kind, c->d_stage[b], n, pitch_in, d_af_chunk, (int)c->S, c->pitchW,
+                             c->d_rows, want_af ? c->d_af : nullptr, c->d_nrows, &c->n_launch));
+        t_end(c, c->stream);
+        UT_CUDA(cudaEventRecord(c->ev_consumed[b], c->stream));
+        c->stage_used[b] = true;
+    }
+    c->rows_upper += n_rows;
+    return UTMOS_OK;
+}
+
+void free_select_state(utmos_ctx *c)
+{
+    const size_t S = (size_t)c->S;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    dev_free(c, c->d_cols, (size_t)((c->S + 31) / 32 * 32) * (size_t)c->colPitchW * 4);
+    dev_free(c, c->d_live, (size_t)c->colPitchW * 4);
+    dev_free(c, c->d_live0, (size_t)c->colPitchW * 4);
+    dev_free(c, c->d_gain_cnt, S * 4);
+    dev_free(c, c->d_gain0_cnt, S * 4);
+    dev_free(c, c->d_var_count, S * 4);
+    dev_free(c, c->d_gain_lo, S * 8);
+    dev_free(c, c->d_gain_hi, S * 8);
+    dev_free(c, c->d_gain0_lo, S * 8);
+    dev_free(c, c->d_gain0_hi, S * 8);
+    dev_free(c, c->d_q_lo, (size_t)c->V * 8);
+    dev_free(c, c->d_q_hi, (size_t)c->V * 8);
+    dev_free(c, c->d_mask, S);
+    dev_free(c, c->d_weights, S * 8);
+    dev_free(c, c->d_out_idx, S * 8);
+    dev_free(c, c->d_out_new, S * 8);
+    dev_free(c, c->d_out_score, S * 8);
+    dev_free(c, c->d_dbg_score, S * 8);
+    dev_free(c, c->d_bar, 64);
+    dev_free(c, c->d_partials, sizeof(ArgPartial) * 2048);
+}
+
+SelParams make_params(const utmos_ctx *c, bool step0)
+{
+    SelParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = c->d_rows;
+    p.cols = c->V > 0 ? c->d_cols : nullptr;
+    p.live = step0 ? c->d_live0 : c->d_live;
+    p.gain_cnt = step0 ? c->d_gain0_cnt : c->d_gain_cnt;
+    p.gain_lo = step0 ? c->d_gain0_lo : c->d_gain_lo;
+    p.gain_hi = step0 ? c->d_gain0_hi : c->d_gain_hi;
+    p.q_lo = c->d_q_lo;
+    p.q_hi = c->d_q_hi;
+    p.mask = c->d_mask;
+    p.weights = c->has_weights ? c->d_weights : nullptr;
+    p.out_idx = c->d_out_idx;
+    p.out_new = c->d_out_new;
+    p.out_score = c->d_out_score;
+    p.st = c->d_state;
+    p.V = c->V;
+    p.colPitchW = c->colPitchW;
+    p.S = (int)c->S;
+    p.pitchW = c->pitchW;
+    p.nW = c->nW;
+    p.L = c->L;
+    p.scale = c->scale;
+    p.af = c->af_mode != UTMOS_AF_NONE;
+    return p;
+}
+
+int build_graph(utmos_ctx *c)
+{
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    const SelParams p = make_params(c, false);
+    cudaGraph_t graph = nullptr;
+    UT_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = UTMOS_OK;
+    for (int i = 0; i < kGraphSteps && rc == UTMOS_OK; ++i) rc = launch_step_pair(c->stream, p, c->n_sms, nullptr);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != UTMOS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    UT_CUDA(e);
+    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    UT_CUDA(e);
+    return UTMOS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+const char *utmos_last_error(void) { return g_error.c_str(); }
+
+const char *utmos_version(void) { return "utmos_b200 0.1.0 (sm_100a)"; }
+
+int utmos_device_count(int *count_out)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (count_out) *count_out = n;
+    return UTMOS_OK;
+}
+
+int utmos_host_alloc(void **ptr_out, int64_t bytes)
+{
+    if (!ptr_out || bytes < 0) { set_error("host_alloc: bad arguments"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaMallocHost(ptr_out, (size_t)std::max<int64_t>(bytes, 16)));
+    return UTMOS_OK;
+}
+
+int utmos_host_free(void *ptr)
+{
+    if (ptr) UT_CUDA(cudaFreeHost(ptr));
+    return UTMOS_OK;
+}
+
+int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t rows_hint, int af_mode, uint32_t flags)
+{
+    if (!ctx_out) { set_error("create: ctx_out is null"); return UTMOS_E_ARG; }
+    *ctx_out = nullptr;
+    if (n_samples <= 0 || n_samples > 0x7fffff00ll) { set_error("create: n_samples out of range"); return UTMOS_E_ARG; }
+    if (af_mode < UTMOS_AF_NONE || af_mode > UTMOS_AF_F32) { set_error("create: bad af_mode"); return UTMOS_E_ARG; }
+    int n = 0;
+    utmos_device_count(&n);
+    if (n <= 0) { set_error("no CUDA device visible: utmos_b200 has no CPU fallback"); return UTMOS_E_NOGPU; }
+    if (device < 0 || device >= n) { set_error("create: device index out of range"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    UT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                  ", this library is built for sm_100a (B200) only");
+        return UTMOS_E_NOGPU;
+    }
+    utmos_ctx *c = new utmos_ctx();
+    c->device = device;
+    c->n_sms = prop.multiProcessorCount;
+    c->S = n_samples;
+    c->nW = (int)((n_samples + 31) / 32);
+    c->pitchW = (c->nW + 3) / 4 * 4;
+    c->af_mode = af_mode;
+    c->flags = flags;
+    int rc = UTMOS_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__);
+            break;
+        }
+        if ((rc = dev_alloc(c, (void **)&c->d_nrows, 16)) != UTMOS_OK) break;
+        if (cudaMemset(c->d_nrows, 0, 16) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
+        if ((rc = dev_alloc(c, (void **)&c->d_state, sizeof(SelState))) != UTMOS_OK) break;
+        if (cudaMemset(c->d_state, 0, sizeof(SelState)) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
+        if (rows_hint > 0) rc = grow_rows(c, rows_hint);
+    } while (0);
+    if (rc != UTMOS_OK) { utmos_destroy(c); return rc; }
+    *ctx_out = c;
+    return UTMOS_OK;
+}
+
+int utmos_destroy(utmos_ctx *c)
+{
+    if (!c) return UTMOS_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    t_resolve(c);
+    free_select_state(c);
+    ingest_scratch_free(c->scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->d_af_stage[i]) cudaFree(c->d_af_stage[i]);
+        if (c->h_af_stage[i]) cudaFreeHost(c->h_af_stage[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+    }
+    if (c->d_rows) cudaFree(c->d_rows);
+    if (c->d_af) cudaFree(c->d_af);
+    if (c->d_nrows) cudaFree(c->d_nrows);
+    if (c->d_state) cudaFree(c->d_state);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    cudaGetLastError();
+    delete c;
+    return UTMOS_OK;
+}
+
+int utmos_append_packed(utmos_ctx *c, const uint8_t *rows, int64_t n_rows, int64_t pitch_bytes, const double *af)
+{
+    if (!c) { set_error("null context"); return UTMOS_E_ARG; }
+    if (pitch_bytes < (c->S + 7) / 8) { set_error("append_packed: pitch smaller than ceil(S/8)"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    return append_host(c, RAW_PACKED_MSB, rows, n_rows, pitch_bytes, af);
+}
+
+int utmos_append_packed_device(utmos_ctx *c, const uint8_t *d_rows, int64_t n_rows, int64_t pitch_bytes,
+                               const double *d_af)
+{
+    if (!c) { set_error("null context"); return UTMOS_E_ARG; }
+    if (c->finalized) { set_error("append after finalize"); return UTMOS_E_ARG; }
+    if (pitch_bytes < (c->S + 7) / 8) { set_error("append_packed: pitch smaller than ceil(S/8)"); return UTMOS_E_ARG; }
+    if (n_rows <= 0) return UTMOS_OK;
+    const bool want_af = c->af_mode != UTMOS_AF_NONE;
+    if (want_af && !d_af) { set_error("append_packed_device: AF required for an AF context"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    UT_TRY(grow_rows(c, c->rows_upper + n_rows));
+    t_begin(c, T_INGEST, c->stream);
+    UT_TRY(launch_ingest(c->stream, c->scratch, RAW_PACKED_MSB, d_rows, n_rows, pitch_bytes, d_af, (int)c->S, c->pitchW,
+                         c->d_rows, want_af ? c->d_af : nullptr, c->d_nrows, &c->n_launch));
+    t_end(c, c->stream);
+    c->rows_upper += n_rows;
+    return UTMOS_OK;
+}
+
+int utmos_append_dense_u8(utmos_ctx *c, const uint8_t *chunk, int64_t n_rows)
+{
+    if (!c) { set_error("null context"); return UTMOS_E_ARG; }
+    if (c->af_mode != UTMOS_AF_NONE) { set_error("append_dense_u8: bool data needs an af_mode NONE context"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    return append_host(c, RAW_DENSE_U8, chunk, n_rows, c->S, nullptr);
+}
+
+int utmos_append_dense_f32(utmos_ctx *c, const float *chunk, int64_t n_rows)
+{
+    if (!c) { set_error("null context"); return UTMOS_E_ARG; }
+    if (c->af_mode == UTMOS_AF_NONE) { set_error("append_dense_f32: float data needs an AF context"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    return append_host(c, RAW_DENSE_F32, chunk, n_rows, c->S * 4, nullptr);
+}
+
+int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
+{
+    if (!c) { set_error("null context"); return UTMOS_E_ARG; }
+    if (c->finalized) { set_error("finalize called twice"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    UT_TRY(sync_all(c));
+    long long v = 0;
+    UT_CUDA(cudaMemcpy(&v, c->d_nrows, 8, cudaMemcpyDeviceToHost));
+    c->V = v;
+    if (v >= (1ll << 40)) { set_error("finalize: too many rows"); return UTMOS_E_ARG; }
+    const size_t S = (size_t)c->S;
+    const long long S32 = (c->S + 31) / 32 * 32;
+    c->colPitchW = std::max(8ll, ((v + 31) / 32 + 7) / 8 * 8);
+    const bool af = c->af_mode != UTMOS_AF_NONE;
+    // limb width: sums of up to V limbs must stay below 2^63 (see oracle_fixed_scale)
+    int lg = 0;
+    while ((1ll << lg) < v + 1) ++lg;
+    c->L = std::min(48, 63 - lg);
+    c->scale = 2 * c->L - 1;
+
+    UT_TRY(dev_alloc(c, (void **)&c->d_live, (size_t)c->colPitchW * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_live0, (size_t)c->colPitchW * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_gain_cnt, S * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_gain0_cnt, S * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_var_count, S * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_mask, S));
+    UT_TRY(dev_alloc(c, (void **)&c->d_weights, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_out_idx, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_out_new, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_out_score, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_dbg_score, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_bar, 64));
+    UT_TRY(dev_alloc(c, (void **)&c->d_partials, sizeof(ArgPartial) * 2048));
+    UT_CUDA(cudaMemsetAsync(c->d_gain0_cnt, 0, S * 4, c->stream));
+    UT_CUDA(cudaMemsetAsync(c->d_var_count, 0, S * 4, c->stream));
+    if (af) {
+        UT_TRY(dev_alloc(c, (void **)&c->d_gain_lo, S * 8));
+        UT_TRY(dev_alloc(c, (void **)&c->d_gain_hi, S * 8));
+        UT_TRY(dev_alloc(c, (void **)&c->d_gain0_lo, S * 8));
+        UT_TRY(dev_alloc(c, (void **)&c->d_gain0_hi, S * 8));
+        UT_TRY(dev_alloc(c, (void **)&c->d_q_lo, (size_t)v * 8));
+        UT_TRY(dev_alloc(c, (void **)&c->d_q_hi, (size_t)v * 8));
+        UT_CUDA(cudaMemsetAsync(c->d_gain0_lo, 0, S * 8, c->stream));
+        UT_CUDA(cudaMemsetAsync(c->d_gain0_hi, 0, S * 8, c->stream));
+    }
+    // sample-major copy when it fits (keeps ~2 GiB of head-room)
+    if (!(c->flags & UTMOS_F_NO_TRANSPOSE) && v > 0) {
+        const size_t bytes = (size_t)S32 * (size_t)c->colPitchW * 4;
+        size_t free_b = 0, total_b = 0;
+        UT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t reserve = 2ull << 30;
+        if (free_b > bytes + reserve) {
+            UT_TRY(dev_alloc(c, (void **)&c->d_cols, bytes));
+        } else if (c->flags & UTMOS_F_FORCE_TRANSPOSE) {
+            set_error("finalize: sample-major copy does not fit in device memory");
+            return UTMOS_E_NOMEM;
+        }
+    }
+    if (c->d_cols) {
+        t_begin(c, T_TRANSPOSE, c->stream);
+        UT_TRY(launch_transpose(c->stream, c->d_rows, v, c->pitchW, (int)c->S, c->d_cols, c->colPitchW, &c->n_launch));
+        t_end(c, c->stream);
+    }
+    t_begin(c, T_GAIN, c->stream);
+    if (af) UT_TRY(launch_fixed_af(c->stream, c->d_af, v, c->af_mode, c->L, c->scale, c->d_q_lo, c->d_q_hi, c->d_state,
+                                   &c->n_launch));
+    UT_TRY(launch_live_init(c->stream, c->d_live0, c->colPitchW, v, c->d_q_lo, c->d_q_hi, af ? 1 : 0, &c->n_launch));
+    {
+        const SelParams p = make_params(c, true);
+        UT_TRY(launch_gain_init(c->stream, p, c->d_var_count, &c->n_launch));
+    }
+    t_end(c, c->stream);
+    UT_TRY(sync_all(c));
+    SelState st;
+    UT_CUDA(cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st.af_invalid) {
+        set_error("finalize: " + std::to_string(st.af_invalid) +
+                  " informative rows have an allele frequency that is NaN, negative or > 1");
+        return UTMOS_E_DATA;
+    }
+    c->af_inexact = st.af_inexact;
+    if (var_count_out) {
+        std::vector<unsigned int> tmp(S);
+        UT_CUDA(cudaMemcpy(tmp.data(), c->d_var_count, S * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; ++i) var_count_out[i] = tmp[i];
+    }
+    if (num_vars_out) *num_vars_out = v;
+    if (!(c->flags & UTMOS_F_STEP_KERNELS)) UT_TRY(persistent_grid(c->device, &c->grid, &c->block));
+    c->finalized = true;
+    return UTMOS_OK;
+}
+
+int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
+{
+    if (!c || !mask) { set_error("select_begin: null argument"); return UTMOS_E_ARG; }
+    if (!c->finalized) { set_error("select_begin before finalize"); return UTMOS_E_ARG; }
+    const size_t S = (size_t)c->S;
+    for (size_t i = 0; i < S; ++i)
+        if (mask[i] > 2) { set_error("select_begin: mask values must be 0, 1 or 2"); return UTMOS_E_ARG; }
+    if (weights)
+        for (size_t i = 0; i < S; ++i)
+            if (!isfinite(weights[i])) { set_error("select_begin: weights must be finite"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    UT_CUDA(cudaMemcpyAsync(c->d_mask, mask, S, cudaMemcpyHostToDevice, c->stream));
+    const bool had_weights = c->has_weights;
+    c->has_weights = weights != nullptr;
+    if (weights) UT_CUDA(cudaMemcpyAsync(c->d_weights, weights, S * 8, cudaMemcpyHostToDevice, c->stream));
+    UT_CUDA(cudaMemcpyAsync(c->d_live, c->d_live0, (size_t)c->colPitchW * 4, cudaMemcpyDeviceToDevice, c->stream));
+    UT_CUDA(cudaMemcpyAsync(c->d_gain_cnt, c->d_gain0_cnt, S * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->af_mode != UTMOS_AF_NONE) {
+        UT_CUDA(cudaMemcpyAsync(c->d_gain_lo, c->d_gain0_lo, S * 8, cudaMemcpyDeviceToDevice, c->stream));
+        UT_CUDA(cudaMemcpyAsync(c->d_gain_hi, c->d_gain0_hi, S * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    SelState st;
+    memset(&st, 0, sizeof(st));
+    st.winner = -1;
+    UT_CUDA(cudaMemcpyAsync(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    UT_CUDA(cudaStreamSynchronize(c->stream));      // host buffers (mask, weights, st) may go away
+    if ((c->flags & UTMOS_F_STEP_KERNELS) && (!c->graph_exec || had_weights != c->has_weights)) UT_TRY(build_graph(c));
+    c->selecting = true;
+    return UTMOS_OK;
+}
+
+int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_t *new_out, double *score_out,
+                       int64_t *n_out, int *stop_out)
+{
+    if (!c || !n_out || !stop_out) { set_error("select_steps: null argument"); return UTMOS_E_ARG; }
+    if (!c->selecting) { set_error("select_steps before select_begin"); return UTMOS_E_ARG; }
+    *n_out = 0;
+    *stop_out = UTMOS_STOP_NONE;
+    UT_CUDA(cudaSetDevice(c->device));
+    SelState st;
+    UT_CUDA(cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    const long long start = st.step;
+    if (st.stop != 0) { *stop_out = st.stop; return UTMOS_OK; }
+    if (max_steps <= 0) return UTMOS_OK;
+    if ((!idx_out || !new_out)) { set_error("select_steps: null output"); return UTMOS_E_ARG; }
+    const long long limit = std::min<long long>(c->S, start + max_steps);
+    if (limit <= start) {
+        // every sample is already used: the reference's next argmax sees only zeros (select.py:43,51)
+        st.stop = UTMOS_STOP_ZERO;
+        UT_CUDA(cudaMemcpy(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+        *stop_out = UTMOS_STOP_ZERO;
+        return UTMOS_OK;
+    }
+    st.limit = limit;
+    UT_CUDA(cudaMemcpy(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+    const SelParams p = make_params(c, false);
+    t_begin(c, T_SELECT, c->stream);
+    if (c->flags & UTMOS_F_STEP_KERNELS) {
+        while (true) {
+            UT_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
+            c->n_launch += 2 * kGraphSteps;
+            UT_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+            UT_CUDA(cudaStreamSynchronize(c->stream));
+            if (st.stop != 0 || st.step >= limit) break;
+        }
+    } else {
+        UT_TRY(launch_persistent(c->stream, p, c->grid, c->block, c->d_bar, c->d_partials, &c->n_launch));
+        c->persistent_used = true;
+    }
+    t_end(c, c->stream);
+    UT_TRY(sync_all(c));
+    UT_CUDA(cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st.abort_flag) {
+        set_error("select_steps: device watchdog tripped (grid barrier timeout)");
+        return UTMOS_E_DEVICE;
+    }
+    const long long n = st.step - start;
+    if (n > 0) {
+        UT_CUDA(cudaMemcpy(idx_out, c->d_out_idx + start, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        UT_CUDA(cudaMemcpy(new_out, c->d_out_new + start, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        if (score_out) UT_CUDA(cudaMemcpy(score_out, c->d_out_score + start, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    }
+    *n_out = n;
+    *stop_out = st.stop;
+    return UTMOS_OK;
+}
+
+int utmos_debug_gains(utmos_ctx *c, int64_t *count_out, double *score_out)
+{
+    if (!c || !c->selecting) { set_error("debug_gains: no selection in progress"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    const size_t S = (size_t)c->S;
+    const SelParams p = make_params(c, false);
+    if (count_out) {
+        std::vector<unsigned int> tmp(S);
+        UT_CUDA(cudaMemcpy(tmp.data(), c->d_gain_cnt, S * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < S; ++i) count_out[i] = tmp[i];
+    }
+    if (score_out) {
+        UT_TRY(launch_debug_scores(c->stream, p, c->d_dbg_score, &c->n_launch));
+        UT_CUDA(cudaStreamSynchronize(c->stream));
+        UT_CUDA(cudaMemcpy(score_out, c->d_dbg_score, S * 8, cudaMemcpyDeviceToHost));
+    }
+    return UTMOS_OK;
+}
+
+int utmos_info(utmos_ctx *c, int64_t *info, int n)
+{
+    if (!c || !info) { set_error("info: null argument"); return UTMOS_E_ARG; }
+    const int64_t vals[8] = {c->V, (int64_t)c->pitchW * 4, c->d_cols ? 1 : 0, (int64_t)c->dev_bytes, c->scale,
+                             (int64_t)c->af_inexact, c->n_launch, c->persistent_used ? 1 : 0};
+    for (int i = 0; i < n && i < 8; ++i) info[i] = vals[i];
+    return UTMOS_OK;
+}
+
+int utmos_timings(utmos_ctx *c, double *ms, int n, int reset)
+{
+    if (!c) { set_error("timings: null context"); return UTMOS_E_ARG; }
+    for (int i = 0; i < n && i < T_COUNT; ++i)
+        if (ms) ms[i] = c->ms[i];
+    if (reset) for (int i = 0; i < T_COUNT; ++i) c->ms[i] = 0.0;
+    return UTMOS_OK;
+}
+
+int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_samples, int64_t ploidy,
+                     uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
+                     uint8_t *singleton_out)
+{
+    if (n_vars < 0 || n_samples <= 0 || ploidy <= 0 || ploidy > 8) { set_error("convert_gt: bad shape"); return UTMOS_E_ARG; }
+    if (n_vars > 0 && (!gt || !packed_out || !af_out)) { set_error("convert_gt: null buffer"); return UTMOS_E_ARG; }
+    int n = 0;
+    utmos_device_count(&n);
+    if (n <= 0) { set_error("no CUDA device visible: utmos_b200 has no CPU fallback"); return UTMOS_E_NOGPU; }
+    if (device < 0 || device >= n) { set_error("convert_gt: device index out of range"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(device));
+    const long long pitch = (n_samples + 7) / 8;
+    const size_t row_in = (size_t)n_samples * (size_t)ploidy;
+    const long long chunk = std::max<long long>(1, std::min<long long>(n_vars, (long long)((256ull << 20) / row_in)));
+    int8_t *d_gt = nullptr;
+    uint8_t *d_packed = nullptr, *d_single = nullptr;
+    double *d_af = nullptr;
+    unsigned long long *d_hh = nullptr;
+    cudaStream_t stream = nullptr;
+    int rc = UTMOS_OK, launches = 0;
+    unsigned long long hh[2] = {0, 0};
+    do {
+        if (n_vars == 0) break;
+#define CV(call) if ((call) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), #call, __FILE__, __LINE__); break; }
+        CV(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CV(cudaMalloc(&d_gt, (size_t)chunk * row_in));
+        CV(cudaMalloc(&d_packed, (size_t)chunk * (size_t)pitch));
+        CV(cudaMalloc(&d_single, (size_t)chunk));
+        CV(cudaMalloc(&d_af, (size_t)chunk * 8));
+        CV(cudaMalloc(&d_hh, 16));
+        CV(cudaMemsetAsync(d_hh, 0, 16, stream));
+        for (long long r0 = 0; r0 < n_vars && rc == UTMOS_OK; r0 += chunk) {
+            const long long m = std::min(chunk, n_vars - r0);
+            CV(cudaMemcpyAsync(d_gt, gt + (size_t)r0 * row_in, (size_t)m * row_in, cudaMemcpyHostToDevice, stream));
+            rc = launch_convert_gt(stream, d_gt, m, (int)n_samples, (int)ploidy, d_packed, pitch, d_af, d_hh, d_single,
+                                   &launches);
+            if (rc != UTMOS_OK) break;
+            CV(cudaMemcpyAsync(packed_out + (size_t)r0 * (size_t)pitch, d_packed, (size_t)m * (size_t)pitch,
+                               cudaMemcpyDeviceToHost, stream));
+            CV(cudaMemcpyAsync(af_out + r0, d_af, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
+            if (singleton_out) CV(cudaMemcpyAsync(singleton_out + r0, d_single, (size_t)m, cudaMemcpyDeviceToHost, stream));
+            CV(cudaStreamSynchronize(stream));
+        }
+        if (rc != UTMOS_OK) break;
+        CV(cudaMemcpy(hh, d_hh, 16, cudaMemcpyDeviceToHost));
+#undef CV
+    } while (0);
+    if (d_gt) cudaFree(d_gt);
+    if (d_packed) cudaFree(d_packed);
+    if (d_single) cudaFree(d_single);
+    if (d_af) cudaFree(d_af);
+    if (d_hh) cudaFree(d_hh);
+    if (stream) cudaStreamDestroy(stream);
+    if (rc != UTMOS_OK) return rc;
+    if (num_het_out) *num_het_out = (int64_t)hh[0];
+    if (num_hom_out) *num_hom_out = (int64_t)hh[1];
+    return UTMOS_OK;
+}
+
+}  // extern "C"

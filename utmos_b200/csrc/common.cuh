@@ -1,0 +1,180 @@
+// common.cuh -- shared device helpers and host-side declarations for libutmos_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "utmos_b200.h"
+
+namespace utmos {
+
+// ------------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ------------------------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line);
+
+#define UT_CUDA(call)                                                         \
+    do {                                                                      \
+        cudaError_t ut_err__ = (call);                                        \
+        if (ut_err__ != cudaSuccess) return ::utmos::cuda_fail(ut_err__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define UT_TRY(call)                     \
+    do {                                 \
+        int ut_rc__ = (call);            \
+        if (ut_rc__ != UTMOS_OK) return ut_rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device state shared by the selection kernels
+// ------------------------------------------------------------------------------------------------
+struct SelState {
+    long long step;        // report rows emitted so far in this selection
+    long long limit;       // step budget of the current utmos_select_steps call (absolute)
+    long long tot;         // tot_captured (utmos/select.py:99)
+    int stop;              // UTMOS_STOP_*
+    int winner;            // sample picked by the last argmax (step kernels), -1 = none
+    unsigned int abort_flag;   // set by the grid-barrier watchdog
+    unsigned int af_inexact;   // AF values with bits below 2^-scale (informative rows only)
+    unsigned int af_invalid;   // AF NaN / negative / > 1 on an informative row
+    unsigned int pad;
+};
+
+struct ArgPartial {        // one per CTA of the persistent kernel
+    double score;
+    int idx;
+    unsigned int cnt;
+};
+
+struct SelParams {
+    const uint32_t *rows;              // variant-major bit matrix [V][pitchW], sample s = word s>>5, bit s&31
+    const uint32_t *cols;              // sample-major copy [S32][colPitchW], row r = word r>>5, bit r&31 (may be null)
+    uint32_t *live;                    // [colPitchW] bit r set = row r not yet covered (and scoring)
+    unsigned int *gain_cnt;            // [S] rows still uncovered that carry sample s  (new_count if picked now)
+    unsigned long long *gain_lo;       // [S] AF flavours: sum of low limbs of AF*2^scale over those rows
+    unsigned long long *gain_hi;       // [S] ... high limbs
+    const unsigned long long *q_lo;    // [V] per-row fixed-point AF, low limb (L bits)
+    const unsigned long long *q_hi;    // [V] high limb
+    uint8_t *mask;                     // [S] working copy of sample_mask
+    const double *weights;             // [S] or null
+    long long *out_idx;                // [S] report rows
+    long long *out_new;
+    double *out_score;
+    SelState *st;
+    long long V;                       // informative rows == num_vars
+    long long colPitchW;               // words per sample-major row (multiple of 8)
+    int S;
+    int pitchW;                        // words per variant-major row (multiple of 4)
+    int nW;                            // ceil(S/32)
+    int L;                             // limb bits
+    int scale;                         // fixed-point scale: value = AF * 2^scale
+    int af;                            // 0 count mode, 1 AF flavours
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// 128-bit streaming load that does not allocate in L1 (data is touched once)
+__device__ __forceinline__ uint4 ld_stream_u128(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// .jl bytes are MSB-first (np.packbits); the device layout is LSB-first 32-bit words.
+// le = little-endian load of 4 consecutive bytes b0..b3; result bit i <-> sample 32w+i.
+__device__ __forceinline__ uint32_t msb_bytes_to_word(uint32_t le) { return __brev(__byte_perm(le, 0, 0x0123)); }
+__device__ __forceinline__ uint32_t word_to_msb_bytes(uint32_t w) { return __byte_perm(__brev(w), 0, 0x0123); }
+
+// value = hi * 2^L + lo as an unsigned 128-bit integer, rounded ONCE to the nearest double (ties to even)
+// and scaled by 2^-scale.  Bit-for-bit the same function as u128_to_double_scaled in oracle/greedy_oracle.c.
+__device__ __forceinline__ double fixed_to_double(unsigned long long lo, unsigned long long hi, int L, int scale)
+{
+    unsigned long long x_lo = lo + (hi << L);
+    unsigned long long x_hi = (hi >> (64 - L)) + (x_lo < lo ? 1ull : 0ull);
+    if ((x_lo | x_hi) == 0ull) return 0.0;
+    const int msb = x_hi ? 127 - __clzll((long long)x_hi) : 63 - __clzll((long long)x_lo);
+    if (msb <= 52) return scalbn((double)x_lo, -scale);
+    const int shift = msb - 52;                  // 1..75 low bits are dropped
+    unsigned long long mant, rem_hi, rem_lo, half_hi, half_lo;
+    if (shift < 64) {
+        mant = (x_lo >> shift) | (x_hi ? (x_hi << (64 - shift)) : 0ull);
+        rem_lo = x_lo & ((1ull << shift) - 1ull);
+        rem_hi = 0ull;
+        half_lo = 1ull << (shift - 1);
+        half_hi = 0ull;
+    } else {
+        const int s2 = shift - 64;
+        mant = x_hi >> s2;
+        rem_lo = x_lo;
+        rem_hi = s2 ? (x_hi & ((1ull << s2) - 1ull)) : 0ull;
+        if (s2 == 0) { half_hi = 0ull; half_lo = 1ull << 63; }
+        else { half_hi = 1ull << (s2 - 1); half_lo = 0ull; }
+    }
+    const bool above = rem_hi > half_hi || (rem_hi == half_hi && rem_lo > half_lo);
+    const bool tie = rem_hi == half_hi && rem_lo == half_lo;
+    if (above || (tie && (mant & 1ull))) mant += 1ull;
+    return scalbn((double)mant, shift - scale);
+}
+
+// np.argmax order: larger score wins, equal scores -> lower index (utmos/select.py:48)
+__device__ __forceinline__ bool arg_better(double sa, int ia, double sb, int ib)
+{
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// host launchers implemented in the .cu files
+// ------------------------------------------------------------------------------------------------
+enum RawKind { RAW_PACKED_MSB = 0, RAW_DENSE_U8 = 1, RAW_DENSE_F32 = 2 };
+
+// ingest.cu : raw chunk (device) -> informative rows appended to the variant-major matrix
+struct IngestScratch {
+    uint8_t *flags = nullptr;          // [chunk rows]
+    unsigned int *block_counts = nullptr;
+    unsigned int *block_offsets = nullptr;
+    long long cap_rows = 0;
+};
+int ingest_scratch_reserve(IngestScratch &sc, long long rows);
+void ingest_scratch_free(IngestScratch &sc);
+int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *raw, long long n_rows,
+                  long long pitch_in, const double *af_in, int S, int pitchW, uint32_t *rows_out, double *af_out,
+                  long long *d_nrows, int *n_launch);
+
+// select.cu
+int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int pitchW, int S, uint32_t *cols,
+                     long long colPitchW, int *n_launch);
+int launch_fixed_af(cudaStream_t stream, const double *af, long long V, int af_mode, int L, int scale,
+                    unsigned long long *q_lo, unsigned long long *q_hi, SelState *st, int *n_launch);
+int launch_live_init(cudaStream_t stream, uint32_t *live, long long colPitchW, long long V,
+                     const unsigned long long *q_lo, const unsigned long long *q_hi, int af, int *n_launch);
+int launch_gain_init(cudaStream_t stream, const SelParams &p, unsigned int *var_count, int *n_launch);
+int launch_step_pair(cudaStream_t stream, const SelParams &p, int n_sms, int *n_launch);
+int persistent_grid(int device, int *grid_out, int *block_out);
+int launch_persistent(cudaStream_t stream, const SelParams &p, int grid, int block, unsigned int *bar_counter,
+                      ArgPartial *partials, int *n_launch);
+int launch_debug_scores(cudaStream_t stream, const SelParams &p, double *score_out, int *n_launch);
+
+// convert.cu
+int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S, int ploidy, uint8_t *packed,
+                      long long pitch_out, double *af, unsigned long long *het_hom, uint8_t *singleton,
+                      int *n_launch);
+
+}  // namespace utmos

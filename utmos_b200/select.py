@@ -1,0 +1,299 @@
+"""
+Select fewest samples with maximum number of variants
+
+Host-side mirror of utmos/select.py: same CLI, same ``load_files`` / ``run_selection`` / ``select_main``
+entry points, same report.  What differs is where the numbers are made: ``load_files`` streams the packed
+``.jl`` rows / hdf5 chunks into HBM (``_native.DeviceMatrix``) instead of building a dense NumPy matrix, and
+``run_selection`` iterates the CUDA greedy loop (csrc/select.cu) instead of ``greedy_select`` /
+``calculate_scores`` (utmos/select.py:24-137).  There is no CPU path.
+"""
+import argparse
+import json
+import logging
+import os
+import sys
+
+import joblib
+import numpy as np
+import pandas as pd
+
+from utmos_b200 import _native, h5lite
+from utmos_b200.convert import read_vcf
+from utmos_b200.logutil import setup_logging
+
+MAXMEM = 2  # in GB; accepted for CLI compatibility (utmos/select.py:18) -- the matrix lives in HBM
+STEP_BATCH = 4096  # report rows fetched per C-ABI call (rows are still written and flushed one by one)
+
+
+####################
+# Setup/Management #
+####################
+def resolve_select_count(select_count, num_samples):
+    """utmos/select.py:157-159"""
+    if select_count < 0:
+        return num_samples
+    return max(1, int(num_samples * select_count) if select_count < 1 else int(select_count))
+
+
+def run_selection(data, select_count=0.02, subset=None, exclude=None, weights=None):
+    """
+    Setup the selection calculation and iterate it (utmos/select.py:147-195 + :69-112)
+    if select_count [0,1], select that percent of samples
+    if select_count >= 1, select that number of samples
+
+    Generator of [sample, var_count, new_count, tot_captured, pct_captured].
+    """
+    matrix = data["data"]
+    num_vars, num_samples = matrix.shape
+    logging.info("Sample Count %d", num_samples)
+    logging.info("Variant Count %d", num_vars)
+
+    select_count = resolve_select_count(select_count, num_samples)
+    logging.info("Selecting %d samples", select_count)
+
+    vcf_samples = np.asarray(data["samples"]).astype(str)
+
+    # 1 = can use, 0 = mask, 2 = exclude   (utmos/select.py:168-179)
+    sample_mask = np.ones(num_samples, dtype="uint8")
+    if subset:
+        sample_mask = np.where(np.isin(vcf_samples, subset), 1, 2)
+        logging.info("Subsetting to %d samples", len(subset))
+    if exclude:
+        sample_mask = np.where(np.isin(vcf_samples, exclude), 2, sample_mask)
+        logging.info("Excluding %d samples", len(exclude))
+    if subset and exclude:
+        remain = len(sample_mask) - (sample_mask == 1).sum()
+        logging.info("Ending with %d samples", remain)
+
+    sample_weights = None
+    if weights is not None:                                   # utmos/select.py:181-187
+        logging.info("Setting %d weights", len(weights))
+        column = weights["weight"] if hasattr(weights, "columns") else weights
+        sample_weights = np.ones(num_samples)
+        for pos, i in enumerate(vcf_samples):
+            if i in column.index:
+                sample_weights[pos] = column.loc[i]
+
+    total_variant_count = np.asarray(data["var_count"][:])
+    matrix.begin(sample_mask.astype(np.uint8), sample_weights)
+    return _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_vars)
+
+
+def _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_vars):
+    """Report rows of utmos/select.py:91-112, fed by batches of GPU steps."""
+    tot_captured = 0
+    emitted = 0
+    while emitted < select_count:
+        idx, new, _score, stop = matrix.steps(min(STEP_BATCH, select_count - emitted))
+        for use_sample, new_variant_count in zip(idx, new):
+            tot_captured += new_variant_count               # np.int64, like counts[use_sample]
+            emitted += 1
+            yield [
+                vcf_samples[use_sample],
+                int(total_variant_count[use_sample]),
+                int(new_variant_count),
+                int(tot_captured),
+                round(tot_captured / num_vars, 4)
+            ]
+        if stop == _native.STOP_ZERO:
+            # Backwards compatibility for data without max-alt-af convert
+            logging.warning("Ran out of new variants (multi-allelics)")
+            return
+        if stop == _native.STOP_ALL:
+            logging.warning("Ran out of new variants")
+            return
+        if len(idx) == 0:
+            return
+
+
+class LoadedData(dict):
+    """What load_files returns: mapping with 'samples', 'data' (DeviceMatrix) and 'var_count'."""
+
+    def close(self):
+        if "data" in self and hasattr(self["data"], "close"):
+            self["data"].close()
+
+
+def _load_hdf5(path, device, flags):
+    """Stream an existing utmos hdf5 (utmos/select.py:250-251) chunk by chunk into HBM."""
+    with h5lite.H5File(path) as h5:
+        dset = h5["data"]
+        num_rows, num_samples = dset.shape
+        is_float = dset.dtype != np.dtype(bool)
+        if is_float and dset.dtype != np.float32:
+            raise h5lite.H5FormatError(f"unexpected data dtype {dset.dtype}")
+        af_mode = _native.AF_F32 if is_float else _native.AF_NONE
+        matrix = _native.DeviceMatrix(num_samples, af_mode, rows_hint=num_rows, device=device, flags=flags)
+        for _first, block in dset.iter_chunks():
+            matrix.append_dense(block)
+        samples = h5["samples"].read()
+        stored_var_count = h5["var_count"].read() if "var_count" in h5 else None
+    var_count = matrix.finalize()
+    if stored_var_count is not None and not np.array_equal(stored_var_count, var_count):
+        logging.warning("var_count stored in %s differs from the data; using the stored values", path)
+        var_count = np.asarray(stored_var_count)
+    return LoadedData(samples=samples, data=matrix, var_count=var_count)
+
+
+def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, flags=0):
+    """
+    Load and concatenate multiple files into one HBM-resident matrix (utmos/select.py:241-321).
+    if lowmem is a filename, the concatenated informative rows are also written to that hdf5 file
+    (bool, or float32 GT*AF when calc_af, utmos/select.py:198-238) so it can be reused later;
+    scoring then uses the float32-rounded AF exactly like the reference, which re-reads the file.
+    lowmem == 1 means in_files[0] is such an hdf5 file.
+    """
+    logging.info(f"Loading {len(in_files)} files")
+    if lowmem == 1:
+        return _load_hdf5(in_files[0], device, flags)
+
+    samples = None
+    matrix = None
+    writer = None
+    load_row_count = 0
+    af_mode = _native.AF_NONE
+    if calc_af:
+        af_mode = _native.AF_F32 if lowmem is not None else _native.AF_F64
+    for load_count, i in enumerate(in_files):
+        if i.endswith((".vcf.gz", ".vcf")):
+            dat = read_vcf(i, lowmem is not None, min(max(1, buffer), 4096), device=device)
+        elif i.endswith(".jl"):
+            dat = joblib.load(i)
+        else:
+            logging.error("Unknown filetype %s. Expected `.vcf[.gz]`, `.jl`", i)
+            sys.exit(1)
+
+        if samples is None:
+            samples = np.asarray(dat["samples"]).astype("S")
+            matrix = _native.DeviceMatrix(len(samples), af_mode, rows_hint=dat["GT"].shape[0] * len(in_files),
+                                          device=device, flags=flags)
+            if lowmem is not None:
+                writer = h5lite.H5Writer(lowmem, samples, float_data=calc_af)
+        matrix.append_packed(dat["GT"], dat["AF"] if calc_af else None)
+        if writer is not None:
+            writer.append_packed(dat["GT"], dat["AF"])
+        load_row_count += dat["GT"].shape[0]
+        logging.debug("Loaded %d of %d (%.2f%%) with %d vars", load_count + 1, len(in_files),
+                      (load_count + 1) / len(in_files) * 100, load_row_count)
+
+    var_count = matrix.finalize()
+    logging.debug("Average of %d variants per-sample", np.mean(var_count) if len(var_count) else 0)
+    if writer is not None:
+        writer.close(var_count)
+    return LoadedData(samples=samples, data=matrix, var_count=var_count)
+
+
+###################
+# Input utilities #
+###################
+def parse_sample_lists(argument):
+    """
+    Parse the --exclude/--subset arguments (utmos/select.py:327-340): every item is a file of names when
+    such a file exists, otherwise a comma-separated list
+    """
+    ret = []
+    if not argument:
+        return ret
+    for item in argument:
+        if os.path.exists(item):
+            with open(item, "r") as fh:
+                ret.extend(line.strip() for line in fh)
+        else:
+            ret.extend(item.split(","))
+    return ret
+
+
+def parse_weights(argument):
+    """
+    Parse the weights file (utmos/select.py:343-352): two tab-delimited columns, no header
+    """
+    if not argument:
+        return None
+    data = pd.read_csv(argument, sep="\t", header=None)
+    data.columns = ["sample", "weight"]
+    data.set_index("sample", inplace=True)
+    return data
+
+
+def parse_args(args):
+    """
+    Pull the command line parameters (utmos/select.py:355-418)
+    """
+    parser = argparse.ArgumentParser(prog="select", description=__doc__.strip().split("\n")[0],
+                                     formatter_class=argparse.RawDescriptionHelpFormatter)
+    parser.add_argument("in_files", nargs="*", type=str, help="Input VCF or jl files")
+    parser.add_argument("-c", "--count", type=float, default=0.02,
+                        help="Number of samples to select as a percent if <1 or count if >=1 or -1 for all (%(default)s)")
+    parser.add_argument("-o", "--out", type=str, default="/dev/stdout", help="Output file (stdout)")
+    parser.add_argument("--debug", action="store_true", help="Verbose logging")
+
+    scoreg = parser.add_argument_group("Scoring Arguments")
+    scoreg.add_argument("--af", action="store_true", help="Weigh variants by allele frequency")
+    scoreg.add_argument("--weights", type=str, default=None, help="Tab-delimited file of sample weights")
+    scoreg.add_argument("--subset", type=str, default=None, action="append",
+                        help="Filename with or Comma-separated list of samples to analyze")
+    scoreg.add_argument("--exclude", type=str, default=None, action="append",
+                        help="Filename with or Comma-separated list of samples to exclude selection")
+
+    mperfg = parser.add_argument_group("Memory Arguments")
+    mperfg.add_argument("--lowmem", type=str, default=None,
+                        help="Name of concatenated hdf5 file to create/use (%(default)s)")
+    mperfg.add_argument("--buffer", type=int, default=32768,
+                        help="Number of variants to buffer during concatenation (%(default)s)")
+    mperfg.add_argument("--maxmem", type=int, default=2,
+                        help="Maximum amount of memory in (GB). 0 keeps data in hdf5 (%(default)s)")
+
+    devg = parser.add_argument_group("Device Arguments")
+    devg.add_argument("--device", type=int, default=int(os.environ.get("UTMOS_DEVICE", "0")),
+                      help="CUDA device index (%(default)s)")
+
+    args = parser.parse_args(args)
+    setup_logging(args.debug)
+    # Validate inputs
+    if [_ for _ in args.in_files if _.endswith(".hdf5")] and len(args.in_files) > 1:
+        logging.error("Cannot provide hdf5 with multiple input files")
+        sys.exit(1)
+
+    if len(args.in_files) == 0:
+        if not args.lowmem:
+            logging.error("No input files provided")
+            sys.exit(1)
+        args.in_files = [args.lowmem]
+        args.lowmem = 1
+
+    if len(args.in_files) == 1 and args.in_files[0].endswith(".hdf5") and not args.lowmem:
+        logging.info("Switching on lowmem for hdf5 input")
+        args.lowmem = 1
+
+    logging.info("Params:\n%s", json.dumps(vars(args), indent=4))
+    return args
+
+
+def select_main(cmdargs):
+    """
+    Main (utmos/select.py:421-448)
+    """
+    global MAXMEM  # pylint: disable=global-statement
+    args = parse_args(cmdargs)
+
+    data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device)
+    if data["data"].dtype == bool and args.af:
+        logging.critical("HDF5 file doesn't appear to be created with --af weighted scores, remove --af or recreate hdf5")
+        sys.exit(1)
+    if data["data"].dtype != bool and not args.af:
+        logging.critical("HDF5 file appears to be created with --af weighted scores, add --af or recreate hdf5")
+
+    args.subset = parse_sample_lists(args.subset)
+    args.exclude = parse_sample_lists(args.exclude)
+    args.weights = parse_weights(args.weights)
+
+    MAXMEM = args.maxmem
+    with open(args.out, "w") as fout:
+        fout.write("sample\tvar_count\tnew_count\ttot_captured\tpct_captured\n")
+        m_iter = run_selection(data, args.count, args.subset, args.exclude, args.weights)
+        for result in m_iter:
+            logging.info("Selected %s (%.1f%% of variants)", result[0], result[4] * 100)
+            fout.write("\t".join([str(_) for _ in result]) + "\n")
+            fout.flush()
+    data.close()
+    logging.info("Finished utmos")
