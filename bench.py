@@ -201,6 +201,8 @@ def main():
         dm.begin(mask)
         idx, new, score, stop = dm.steps(n_samples)
         info, tim = dm.info(), dm.timings()
+        tim["step_ns"] = dm.step_times(0, len(idx))
+        tim["counters"] = dm.counters()
         dm.close()
         return idx, new, score, stop, var_count, info, tim
 
@@ -236,13 +238,23 @@ def main():
     e2e_value = world * packed_bytes / 1e9 / (t_e2e / args.steps)
 
     # device-side (CUDA event) time of each phase, averaged over the timed resident steps
-    phases = {k: float(np.mean([o[6][k] for o in outs_res])) for k in outs_res[0][6]}
-    phases_e2e = {k: float(np.mean([o[6][k] for o in outs_e2e])) for k in outs_e2e[0][6]}
+    phases = {k: float(np.mean([o[6][k] for o in outs_res])) for k in outs_res[0][6] if k not in ("step_ns", "counters")}
+    phases_e2e = {k: float(np.mean([o[6][k] for o in outs_e2e])) for k in outs_e2e[0][6] if k not in ("step_ns", "counters")}
+    step_ns = outs_res[-1][6]["step_ns"].astype(np.float64)
+    gaps = np.diff(step_ns) / 1e3                      # us between consecutive picks
+    step_profile = {}
+    if len(gaps) > 200:
+        step_profile = {"first_20_steps_ms": float(gaps[:20].sum() / 1e3), "steps_20_200_ms": float(gaps[20:200].sum() / 1e3),
+                        "steps_200_end_ms": float(gaps[200:].sum() / 1e3),
+                        "tail_us_per_step_median": float(np.median(gaps[200:])),
+                        "tail_us_per_step_p90": float(np.percentile(gaps[200:], 90)),
+                        "max_us": float(gaps.max())}
     peak, peak_kind = peaks()
     n_steps = len(idx)
     sel_bytes = select_bytes(info["num_vars"], info["row_pitch_bytes"], n_samples, n_steps, int(new.sum()))
     achieved = sel_bytes / 1e9 / (phases["select_ms"] / 1e3) if phases["select_ms"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "select_persistent_kernel" if info["persistent"] else "argmax+cover step kernels",
+    roofline = {"bound": "hbm", "kernel": ["argmax_step_kernel+cover_step_kernel", "select_persistent_kernel", "select_cluster_kernel",
+                           "select_tail_kernel (head: select_cluster_kernel + regain_kernel)"][info["flavour"]],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
                 "note": "latency-bound: %d dependent greedy steps, %.2f us per step" %
@@ -299,7 +311,7 @@ def main():
             "gpu_launches": int(info["kernel_launches"]) * args.steps,
             "roofline": roofline, "streaming_kernels": streaming, "phases_ms": phases,
             "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
+            "step_profile": step_profile, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:12]], "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -48,6 +48,8 @@ typedef struct utmos_ctx utmos_ctx;
 #define UTMOS_F_NO_TRANSPOSE 1u      /* never build the sample-major copy (probe the variant-major matrix) */
 #define UTMOS_F_STEP_KERNELS 2u      /* per-step kernel launches (CUDA graph) instead of the persistent kernel */
 #define UTMOS_F_FORCE_TRANSPOSE 4u   /* fail instead of falling back when the sample-major copy does not fit */
+#define UTMOS_F_NO_CLUSTER 8u        /* grid-wide persistent kernel instead of the one-cluster DSMEM kernel */
+#define UTMOS_F_NO_TAIL 16u          /* never switch to the single-CTA list-driven tail kernel */
 
 /* stop reasons reported by utmos_select_steps (utmos/select.py:91, :51-52/:93-96, :110-112) */
 #define UTMOS_STOP_NONE 0            /* max_steps of this call done; selection can continue */
@@ -127,9 +129,22 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
 /* Current per-sample state: gain counts (new_count each sample would get now) and unweighted, unmasked scores. */
 int utmos_debug_gains(utmos_ctx *ctx, int64_t *count_out, double *score_out);
 
+/* %globaltimer nanoseconds at which steps first..first+n-1 of the current selection were picked. */
+int utmos_debug_step_times(utmos_ctx *ctx, int64_t first, int64_t n, int64_t *ns_out);
+
+/* Profiling counters of the selection kernel: out16[0..3] = clock cycles spent (CTA 0, thread 0) in argmax,
+ * barrier 1, cover, barrier 2, summed over steps; out16[4] = kernel launches. */
+int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
+
+/* Tunables.  UTMOS_OPT_REGAIN_ROWS: a pick that newly covers >= value rows triggers one streaming recompute of
+ * all gains from the sample-major copy instead of per-bit subtraction (0 = never, -1 = default max(4096, V/128)). */
+#define UTMOS_OPT_REGAIN_ROWS 1
+int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
+
 /* info[0]=num_vars, [1]=row pitch bytes, [2]=has sample-major copy, [3]=device bytes in use,
  * [4]=fixed-point scale (AF flavours), [5]=AF values not exactly representable (count), [6]=kernels launched,
- * [7]=persistent kernel used (0/1) */
+ * [7]=selection kernel flavour used: 0 step kernels, 1 grid-wide persistent, 2 one-cluster DSMEM,
+ *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2) */
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:

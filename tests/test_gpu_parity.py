@@ -16,8 +16,12 @@ from utmos_b200 import convert as ucvt
 pytestmark = pytest.mark.gpu
 
 MODES = {
-    "persistent": 0,
-    "persistent_notranspose": _native.F_NO_TRANSPOSE,
+    "tail": 0,
+    "tail_persistent_head": _native.F_NO_CLUSTER,
+    "cluster": _native.F_NO_TAIL,
+    "cluster_notranspose": _native.F_NO_TRANSPOSE,
+    "persistent": _native.F_NO_CLUSTER | _native.F_NO_TAIL,
+    "persistent_notranspose": _native.F_NO_CLUSTER | _native.F_NO_TRANSPOSE,
     "stepkernels": _native.F_STEP_KERNELS,
     "stepkernels_notranspose": _native.F_STEP_KERNELS | _native.F_NO_TRANSPOSE,
 }
@@ -191,6 +195,27 @@ def test_gains_after_k_steps_match_oracle_score_vector(flags):
         dm.close()
 
 
+@pytest.mark.parametrize("use_af", [False, True], ids=["count", "af"])
+@pytest.mark.parametrize("thr", [1, 20, 0], ids=["regain_always", "regain_some", "regain_never"])
+def test_regain_threshold_does_not_change_results(use_af, thr, flags):
+    """Recomputing all gains from the sample-major copy and subtracting retired rows are interchangeable."""
+    gold = H.golden_json("full_order_af.json" if use_af else "full_order_count.json")
+    parts = H.load_jl_parts(gold["files"])
+    n = 2504
+    dm = _native.DeviceMatrix(n, _native.AF_F64 if use_af else _native.AF_NONE, flags=flags)
+    for part in parts:
+        dm.append_packed(part["GT"], part["AF"])
+    dm.finalize()
+    dm.set_regain_rows(thr)
+    dm.begin(np.ones(n, np.uint8))
+    idx, new, score, _ = dm.steps(300)
+    names = np.asarray(parts[0]["samples"]).astype(str)
+    assert [names[i] for i in idx] == [g[0] for g in gold["rows"][:300]]
+    assert [int(x) for x in new] == [g[2] for g in gold["rows"][:300]]
+    np.testing.assert_allclose(score, gold["argmax_scores"][:300], rtol=1e-9)
+    dm.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # tier 3: edge cases
 # ------------------------------------------------------------------------------------------------
@@ -324,7 +349,7 @@ def test_full_shape_properties_and_mode_agreement():
         results[name] = (idx, new, score, stop, vc, dm.num_vars)
         dm.close()
     coh.close()
-    idx, new, score, stop, vc, nv = results["persistent"]
+    idx, new, score, stop, vc, nv = results["tail"]
     assert nv == n_vars                                        # every synthetic row is informative
     assert len(np.unique(idx)) == len(idx)                     # a sample is picked once
     assert np.all(np.diff(new) <= 0)                           # coverage gains are non-increasing (submodular)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libutmos_b200.so")
 
 AF_NONE, AF_F64, AF_F32 = 0, 1, 2
-F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE = 1, 2, 4
+F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL = 1, 2, 4, 8, 16
 STOP_NONE, STOP_ZERO, STOP_ALL = 0, 1, 2
 E_NOGPU = -3
 
@@ -20,7 +20,7 @@ E_NOGPU = -3
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_finalize", "utmos_select_begin",
-           "utmos_select_steps", "utmos_convert_gt", "utmos_debug_gains", "utmos_info", "utmos_timings",
+           "utmos_select_steps", "utmos_convert_gt", "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
 
@@ -65,6 +65,9 @@ def lib():
         "utmos_convert_gt": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p]),
         "utmos_debug_gains": (i32, [p, p, p]),
         "utmos_info": (i32, [p, p, i32]),
+        "utmos_debug_step_times": (i32, [p, i64, i64, p]),
+        "utmos_set_option": (i32, [p, i32, i64]),
+        "utmos_debug_counters": (i32, [p, p]),
         "utmos_timings": (i32, [p, p, i32, i32]),
         "utmos_lzf_decompress": (i64, [p, i64, p, i64]),
         "utmos_lzf_compress": (i64, [p, i64, p, i64]),
@@ -210,11 +213,26 @@ class DeviceMatrix:
         check(lib().utmos_debug_gains(self._ctx, _ptr(cnt), _ptr(score)))
         return cnt, score
 
+    def step_times(self, first, n):
+        """%globaltimer ns of the picks first..first+n-1 (profiling aid)."""
+        out = np.zeros(n, dtype=np.int64)
+        check(lib().utmos_debug_step_times(self._ctx, first, n, _ptr(out)))
+        return out
+
+    def counters(self):
+        out = np.zeros(16, dtype=np.int64)
+        check(lib().utmos_debug_counters(self._ctx, _ptr(out)))
+        return out
+
+    def set_regain_rows(self, rows):
+        """Override the recompute-vs-subtract threshold (0 never recompute, -1 default)."""
+        check(lib().utmos_set_option(self._ctx, 1, int(rows)))
+
     def info(self):
         arr = np.zeros(8, dtype=np.int64)
         check(lib().utmos_info(self._ctx, _ptr(arr), 8))
         keys = ["num_vars", "row_pitch_bytes", "has_sample_major", "device_bytes", "fixed_scale", "af_inexact",
-                "kernel_launches", "persistent"]
+                "kernel_launches", "flavour"]
         return dict(zip(keys, (int(x) for x in arr)))
 
     def timings(self, reset=False):

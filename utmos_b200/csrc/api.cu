@@ -73,6 +73,7 @@ struct utmos_ctx {
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
     bool stage_used[2] = {false, false};
     int stage_next = 0;
+    bool owns_pinned_cache = false;
 
     bool finalized = false;
     long long V = 0, colPitchW = 0;
@@ -86,13 +87,28 @@ struct utmos_ctx {
     bool has_weights = false;
     long long *d_out_idx = nullptr, *d_out_new = nullptr;
     double *d_out_score = nullptr, *d_dbg_score = nullptr;
+    long long *d_out_time = nullptr;
+    long long *d_dbg = nullptr;
+    uint4 *d_lists[2] = {nullptr, nullptr};            // edge lists, double buffered for re-compaction
+    unsigned int *d_list_off[2] = {nullptr, nullptr}, *d_list_len[2] = {nullptr, nullptr}, *d_cursor = nullptr, *d_pool_cursor = nullptr;
+    unsigned short *d_pool = nullptr;
+    size_t pool_cap = 0;
+    size_t lists_cap[2] = {0, 0};      // uint4 units allocated
+    int lists_cur = 0;
+    unsigned long long lists_total = 0;   // entries in the current lists (live bits when they were built)
+    bool lists_valid = false;
+    unsigned int tail_rows = 768;         // hand over to the single-CTA tail once picks cover fewer rows than this
+    unsigned long long tail_budget = 0;   // handed to the head kernels while the tail flavour waits for sparsity
+    unsigned long long total_bits = 0;    // set bits of the scoring rows at step 0
+    long long regain_rows = -1;        // -1 = default heuristic
     SelState *d_state = nullptr;
     unsigned int *d_bar = nullptr;
     ArgPartial *d_partials = nullptr;
     int grid = 0, block = 0;
     bool selecting = false;
     cudaGraphExec_t graph_exec = nullptr;
-    bool persistent_used = false;
+    int flavour_used = 0;
+    int cluster = 0;
     unsigned int af_inexact = 0;
 
     int n_launch = 0;
@@ -103,10 +119,14 @@ struct utmos_ctx {
 
 namespace {
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold
+// lifted, so a process that runs many selections re-uses its buffers instead of paying cudaMalloc/cudaFree
+// for hundreds of MB each time.  Allocations are ordered on c->stream; callers that hand a fresh buffer to
+// the copy stream synchronise c->stream first (ensure_stage).
 int dev_alloc(utmos_ctx *c, void **p, size_t bytes)
 {
     if (bytes == 0) bytes = 16;
-    UT_CUDA(cudaMalloc(p, bytes));
+    UT_CUDA(cudaMallocAsync(p, bytes, c->stream));
     c->dev_bytes += bytes;
     return UTMOS_OK;
 }
@@ -115,11 +135,21 @@ template <typename T>
 void dev_free(utmos_ctx *c, T *&p, size_t bytes)
 {
     if (p) {
-        cudaFree(p);
+        cudaFreeAsync(p, c->stream);
         c->dev_bytes -= std::min(c->dev_bytes, bytes ? bytes : (size_t)16);
         p = nullptr;
     }
 }
+
+// pinned staging buffers are expensive to create (page locking): keep two per process and lend them out
+struct PinnedCache {
+    void *buf[2] = {nullptr, nullptr};
+    bool busy = false;
+};
+PinnedCache g_pinned;
+
+int pinned_acquire(utmos_ctx *c);
+void pinned_release(utmos_ctx *c);
 
 void t_begin(utmos_ctx *c, int cat, cudaStream_t s)
 {
@@ -177,16 +207,46 @@ int grow_rows(utmos_ctx *c, long long need)
     return UTMOS_OK;
 }
 
-int ensure_stage(utmos_ctx *c, long long af_rows)
+int pinned_acquire(utmos_ctx *c)
 {
+    if (c->h_stage[0]) return UTMOS_OK;
+    if (!g_pinned.busy) {
+        for (int i = 0; i < 2; ++i)
+            if (!g_pinned.buf[i]) UT_CUDA(cudaMallocHost(&g_pinned.buf[i], kStageBytes));
+        g_pinned.busy = true;
+        c->owns_pinned_cache = true;
+        c->h_stage[0] = g_pinned.buf[0];
+        c->h_stage[1] = g_pinned.buf[1];
+    } else {
+        for (int i = 0; i < 2; ++i) UT_CUDA(cudaMallocHost(&c->h_stage[i], kStageBytes));
+    }
+    return UTMOS_OK;
+}
+
+void pinned_release(utmos_ctx *c)
+{
+    if (c->owns_pinned_cache) {
+        g_pinned.busy = false;
+        c->owns_pinned_cache = false;
+    } else {
+        for (int i = 0; i < 2; ++i)
+            if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    }
+    c->h_stage[0] = c->h_stage[1] = nullptr;
+}
+
+int ensure_stage(utmos_ctx *c, long long af_rows, bool need_host)
+{
+    bool fresh = false;
     for (int i = 0; i < 2; ++i) {
         if (!c->d_stage[i]) {
             UT_TRY(dev_alloc(c, &c->d_stage[i], kStageBytes));
-            UT_CUDA(cudaMallocHost(&c->h_stage[i], kStageBytes));
             UT_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
             UT_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+            fresh = true;
         }
     }
+    if (need_host) UT_TRY(pinned_acquire(c));
     if (af_rows > c->af_stage_rows) {
         UT_CUDA(cudaStreamSynchronize(c->stream));
         UT_CUDA(cudaStreamSynchronize(c->copy_stream));
@@ -197,7 +257,9 @@ int ensure_stage(utmos_ctx *c, long long af_rows)
             UT_CUDA(cudaMallocHost((void **)&c->h_af_stage[i], (size_t)af_rows * 8));
         }
         c->af_stage_rows = af_rows;
+        fresh = true;
     }
+    if (fresh) UT_CUDA(cudaStreamSynchronize(c->stream));   // pool allocations are ordered on c->stream
     return UTMOS_OK;
 }
 
@@ -220,9 +282,9 @@ int append_host(utmos_ctx *c, int kind, const void *src, long long n_rows, long 
     const long long chunk_rows = std::max(1ll, (long long)(kStageBytes / (size_t)pitch_in));
     if ((size_t)pitch_in > kStageBytes) { set_error("append: one row exceeds the staging buffer"); return UTMOS_E_ARG; }
     const bool need_af_stage = (kind == RAW_PACKED_MSB && want_af) || kind == RAW_DENSE_F32;
-    UT_TRY(ensure_stage(c, need_af_stage ? std::min(chunk_rows, n_rows) : 0));
     const bool src_pinned = is_pinned(src);
     const bool af_pinned = af && is_pinned(af);
+    UT_TRY(ensure_stage(c, need_af_stage ? std::min(chunk_rows, n_rows) : 0, !src_pinned));
     for (long long r0 = 0; r0 < n_rows; r0 += chunk_rows) {
         const long long n = std::min(chunk_rows, n_rows - r0);
         const int b = c->stage_next;
@@ -288,6 +350,19 @@ void free_select_state(utmos_ctx *c)
     dev_free(c, c->d_out_idx, S * 8);
     dev_free(c, c->d_out_new, S * 8);
     dev_free(c, c->d_out_score, S * 8);
+    dev_free(c, c->d_out_time, S * 8);
+    dev_free(c, c->d_dbg, 128);
+    for (int i = 0; i < 2; ++i) {
+        dev_free(c, c->d_lists[i], c->lists_cap[i] * 16);
+        dev_free(c, c->d_list_off[i], S * 4);
+        dev_free(c, c->d_list_len[i], S * 4);
+        c->lists_cap[i] = 0;
+    }
+    dev_free(c, c->d_cursor, S * 4);
+    dev_free(c, c->d_pool_cursor, 16);
+    dev_free(c, c->d_pool, c->pool_cap * 2);
+    c->pool_cap = 0;
+    c->lists_valid = false;
     dev_free(c, c->d_dbg_score, S * 8);
     dev_free(c, c->d_bar, 64);
     dev_free(c, c->d_partials, sizeof(ArgPartial) * 2048);
@@ -310,6 +385,21 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.out_idx = c->d_out_idx;
     p.out_new = c->d_out_new;
     p.out_score = c->d_out_score;
+    p.out_time = c->d_out_time;
+    p.dbg = c->d_dbg;
+    p.lists = c->d_lists[c->lists_cur];
+    p.list_off = c->d_list_off[c->lists_cur];
+    p.list_len = c->d_list_len[c->lists_cur];
+    p.pool = c->d_pool;
+    {
+        // a pick that newly covers this many rows is cheaper to absorb by one streaming recompute of all gains
+        // (S columns, ~V*S/8 bytes) than by one atomic per set bit of those rows
+        long long thr = c->regain_rows >= 0 ? c->regain_rows : std::max(4096ll, c->V / 128);
+        if (!c->d_cols || (c->flags & UTMOS_F_STEP_KERNELS)) thr = 0;
+        p.regain_rows = (unsigned int)std::min(thr, 0xffffffffll);
+    }
+    p.tail_budget = c->tail_budget;
+    p.tail_rows = c->tail_rows;
     p.st = c->d_state;
     p.V = c->V;
     p.colPitchW = c->colPitchW;
@@ -408,10 +498,17 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
             rc = cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__);
             break;
         }
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;                 // never trim: buffers are re-used across selections
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
         if ((rc = dev_alloc(c, (void **)&c->d_nrows, 16)) != UTMOS_OK) break;
-        if (cudaMemset(c->d_nrows, 0, 16) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
+        if (cudaMemsetAsync(c->d_nrows, 0, 16, c->stream) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
         if ((rc = dev_alloc(c, (void **)&c->d_state, sizeof(SelState))) != UTMOS_OK) break;
-        if (cudaMemset(c->d_state, 0, sizeof(SelState)) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
+        if (cudaMemsetAsync(c->d_state, 0, sizeof(SelState), c->stream) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
         if (rows_hint > 0) rc = grow_rows(c, rows_hint);
     } while (0);
     if (rc != UTMOS_OK) { utmos_destroy(c); return rc; }
@@ -427,19 +524,20 @@ int utmos_destroy(utmos_ctx *c)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     t_resolve(c);
     free_select_state(c);
-    ingest_scratch_free(c->scratch);
+    ingest_scratch_free(c->scratch, c->stream);
+    pinned_release(c);
     for (int i = 0; i < 2; ++i) {
-        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
-        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
-        if (c->d_af_stage[i]) cudaFree(c->d_af_stage[i]);
+        if (c->d_stage[i]) cudaFreeAsync(c->d_stage[i], c->stream);
+        if (c->d_af_stage[i]) cudaFreeAsync(c->d_af_stage[i], c->stream);
         if (c->h_af_stage[i]) cudaFreeHost(c->h_af_stage[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
     }
-    if (c->d_rows) cudaFree(c->d_rows);
-    if (c->d_af) cudaFree(c->d_af);
-    if (c->d_nrows) cudaFree(c->d_nrows);
-    if (c->d_state) cudaFree(c->d_state);
+    if (c->d_rows) cudaFreeAsync(c->d_rows, c->stream);
+    if (c->d_af) cudaFreeAsync(c->d_af, c->stream);
+    if (c->d_nrows) cudaFreeAsync(c->d_nrows, c->stream);
+    if (c->d_state) cudaFreeAsync(c->d_state, c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaGetLastError();
@@ -520,6 +618,16 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
     UT_TRY(dev_alloc(c, (void **)&c->d_out_idx, S * 8));
     UT_TRY(dev_alloc(c, (void **)&c->d_out_new, S * 8));
     UT_TRY(dev_alloc(c, (void **)&c->d_out_score, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_out_time, S * 8));
+    UT_TRY(dev_alloc(c, (void **)&c->d_dbg, 128));
+    for (int i = 0; i < 2; ++i) {
+        UT_TRY(dev_alloc(c, (void **)&c->d_list_off[i], S * 4));
+        UT_TRY(dev_alloc(c, (void **)&c->d_list_len[i], S * 4));
+    }
+    UT_TRY(dev_alloc(c, (void **)&c->d_cursor, S * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_pool_cursor, 16));
+    UT_CUDA(cudaMemsetAsync(c->d_dbg, 0, 128, c->stream));
+    UT_CUDA(cudaMemsetAsync(c->d_out_time, 0, S * 8, c->stream));
     UT_TRY(dev_alloc(c, (void **)&c->d_dbg_score, S * 8));
     UT_TRY(dev_alloc(c, (void **)&c->d_bar, 64));
     UT_TRY(dev_alloc(c, (void **)&c->d_partials, sizeof(ArgPartial) * 2048));
@@ -540,6 +648,15 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
         const size_t bytes = (size_t)S32 * (size_t)c->colPitchW * 4;
         size_t free_b = 0, total_b = 0;
         UT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        {
+            cudaMemPool_t pool;
+            unsigned long long reserved = 0, used = 0;
+            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess &&
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+                free_b += (size_t)(reserved - used);
+            cudaGetLastError();
+        }
         const size_t reserve = 2ull << 30;
         if (free_b > bytes + reserve) {
             UT_TRY(dev_alloc(c, (void **)&c->d_cols, bytes));
@@ -607,8 +724,13 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
     memset(&st, 0, sizeof(st));
     st.winner = -1;
     UT_CUDA(cudaMemcpyAsync(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    {
+        const SelParams p0 = make_params(c, false);
+        UT_TRY(launch_sum_gains(c->stream, p0, &c->n_launch));     // st->live_bits = set bits of the scoring rows
+    }
     UT_CUDA(cudaStreamSynchronize(c->stream));      // host buffers (mask, weights, st) may go away
     if ((c->flags & UTMOS_F_STEP_KERNELS) && (!c->graph_exec || had_weights != c->has_weights)) UT_TRY(build_graph(c));
+    c->lists_valid = false;
     c->selecting = true;
     return UTMOS_OK;
 }
@@ -648,8 +770,81 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             if (st.stop != 0 || st.step >= limit) break;
         }
     } else {
-        UT_TRY(launch_persistent(c->stream, p, c->grid, c->block, c->d_bar, c->d_partials, &c->n_launch));
-        c->persistent_used = true;
+        int CL = 0, tail_ok = 0;
+        if (!(c->flags & UTMOS_F_NO_CLUSTER)) UT_TRY(cluster_plan(p, &CL));
+        if (!(c->flags & UTMOS_F_NO_TAIL)) UT_TRY(tail_plan(p, &tail_ok));
+        // Head: greedy steps by the cluster (or grid-wide) kernel; a pick that covers very many rows ends the
+        // launch and the conditional regain kernel recomputes the gains.  While the tail flavour is still
+        // waiting for the live part of the matrix to become sparse, launches are kept short (4 steps) so the
+        // host can switch as soon as the per-sample live-row lists fit the budget.
+        // Tail: one CTA runs all remaining steps from the lists.
+        const unsigned long long list_budget = 1ull << 24;          // entries (16 B each; 32 B for AF flavours)
+        const size_t estride = c->af_mode != UTMOS_AF_NONE ? 2 : 1;
+        c->tail_budget = tail_ok ? list_budget : 0;
+        auto reserve_lists = [&](int which, unsigned long long entries) -> int {
+            const size_t need = (size_t)std::max<unsigned long long>(entries, 1) * estride;
+            if (need > c->lists_cap[which]) {
+                dev_free(c, c->d_lists[which], c->lists_cap[which] * 16);
+                UT_TRY(dev_alloc(c, (void **)&c->d_lists[which], need * 16));
+                c->lists_cap[which] = need;
+            }
+            return UTMOS_OK;
+        };
+        while (true) {
+            SelParams q = make_params(c, false);
+            if (c->lists_valid) {
+                UT_TRY(launch_tail(c->stream, q, c->lists_total, &c->n_launch));
+                UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                c->flavour_used = 3;
+            } else {
+                // a few launches are queued between host checks; once the live part is sparse enough the queued
+                // head kernels return immediately (they test st->live_bits at launch)
+                for (int rep = 0; rep < 4; ++rep) {
+                    if (CL > 0) {
+                        UT_TRY(launch_cluster(c->stream, q, CL, &c->n_launch));
+                        c->flavour_used = 2;
+                        c->cluster = CL;
+                    } else {
+                        UT_TRY(launch_persistent(c->stream, q, c->grid, c->block, c->d_bar, c->d_partials, &c->n_launch));
+                        c->flavour_used = 1;
+                    }
+                    if (!q.regain_rows) break;
+                    UT_TRY(launch_regain(c->stream, q, &c->n_launch));
+                    UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                }
+            }
+            UT_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+            UT_CUDA(cudaStreamSynchronize(c->stream));
+            if (st.stop != 0 || st.step >= limit || st.abort_flag) break;
+            if (tail_ok && !c->lists_valid && st.want_tail && st.live_bits <= list_budget) {
+                // first compaction: edge lists from the bit matrix
+                UT_TRY(reserve_lists(c->lists_cur, st.live_bits));
+                if ((size_t)st.live_bits + 64 > c->pool_cap) {
+                    dev_free(c, c->d_pool, c->pool_cap * 2);
+                    c->pool_cap = (size_t)st.live_bits + 64;
+                    UT_TRY(dev_alloc(c, (void **)&c->d_pool, c->pool_cap * 2));
+                }
+                q = make_params(c, false);
+                UT_TRY(launch_build_lists(c->stream, q, c->d_lists[c->lists_cur], c->d_list_off[c->lists_cur],
+                                          c->d_list_len[c->lists_cur], c->d_cursor, c->d_pool, c->d_pool_cursor,
+                                          &c->n_launch));
+                c->lists_total = st.live_bits;
+                c->lists_valid = true;
+            } else if (c->lists_valid && st.recompact) {
+                // re-compaction: keep the entries whose row is still live
+                const int nxt = c->lists_cur ^ 1;
+                UT_TRY(reserve_lists(nxt, st.live_bits));
+                q = make_params(c, false);
+                UT_TRY(launch_filter_lists(c->stream, q, c->d_lists[c->lists_cur], c->d_list_off[c->lists_cur],
+                                           c->d_list_len[c->lists_cur], c->d_lists[nxt], c->d_list_off[nxt],
+                                           c->d_list_len[nxt], &c->n_launch));
+                c->lists_cur = nxt;
+                c->lists_total = st.live_bits;
+            }
+        }
+        if (st.limit != limit) {
+            st.limit = limit;
+        }
     }
     t_end(c, c->stream);
     UT_TRY(sync_all(c));
@@ -688,11 +883,35 @@ int utmos_debug_gains(utmos_ctx *c, int64_t *count_out, double *score_out)
     return UTMOS_OK;
 }
 
+int utmos_debug_step_times(utmos_ctx *c, int64_t first, int64_t n, int64_t *ns_out)
+{
+    if (!c || !c->selecting || !ns_out || first < 0 || n < 0 || first + n > c->S) { set_error("debug_step_times: bad arguments"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    if (n > 0) UT_CUDA(cudaMemcpy(ns_out, c->d_out_time + first, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return UTMOS_OK;
+}
+
+int utmos_debug_counters(utmos_ctx *c, int64_t *out16)
+{
+    if (!c || !c->finalized || !out16) { set_error("debug_counters: bad arguments"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    UT_CUDA(cudaMemcpy(out16, c->d_dbg, 128, cudaMemcpyDeviceToHost));
+    return UTMOS_OK;
+}
+
+int utmos_set_option(utmos_ctx *c, int option, int64_t value)
+{
+    if (!c) { set_error("set_option: null context"); return UTMOS_E_ARG; }
+    if (option == UTMOS_OPT_REGAIN_ROWS) { c->regain_rows = value; return UTMOS_OK; }
+    set_error("set_option: unknown option");
+    return UTMOS_E_ARG;
+}
+
 int utmos_info(utmos_ctx *c, int64_t *info, int n)
 {
     if (!c || !info) { set_error("info: null argument"); return UTMOS_E_ARG; }
     const int64_t vals[8] = {c->V, (int64_t)c->pitchW * 4, c->d_cols ? 1 : 0, (int64_t)c->dev_bytes, c->scale,
-                             (int64_t)c->af_inexact, c->n_launch, c->persistent_used ? 1 : 0};
+                             (int64_t)c->af_inexact, c->n_launch, c->flavour_used};
     for (int i = 0; i < n && i < 8; ++i) info[i] = vals[i];
     return UTMOS_OK;
 }

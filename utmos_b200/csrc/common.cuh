@@ -40,13 +40,17 @@ struct SelState {
     unsigned int abort_flag;   // set by the grid-barrier watchdog
     unsigned int af_inexact;   // AF values with bits below 2^-scale (informative rows only)
     unsigned int af_invalid;   // AF NaN / negative / > 1 on an informative row
-    unsigned int pad;
+    unsigned int want_tail;    // head kernel returned because the tail kernel should take over
+    unsigned int recompact;    // tail kernel returned because at most half of its list entries are still live
+    unsigned int regain;       // 1 = gains are stale: the pick retired too many rows to subtract, recompute them
+    unsigned long long live_bits;   // sum of all gains = set bits in rows not yet covered (sum_gains_kernel)
 };
 
-struct ArgPartial {        // one per CTA of the persistent kernel
+struct ArgPartial {        // one per CTA of the persistent / cluster kernel
     double score;
     int idx;
     unsigned int cnt;
+    unsigned long long sum;    // sum of the gains this CTA owns (live set bits), for the hand-over to the tail kernel
 };
 
 struct SelParams {
@@ -63,7 +67,13 @@ struct SelParams {
     long long *out_idx;                // [S] report rows
     long long *out_new;
     double *out_score;
+    long long *out_time;               // [S] %globaltimer (ns) when the pick of each step was made
     SelState *st;
+    const uint4 *lists;                // per-sample edge lists (tail kernel), may be null; see tail.cu
+    const unsigned int *list_off;      // [S] first entry of sample s in lists
+    const unsigned int *list_len;      // [S] entries of sample s
+    const unsigned short *pool;        // carrier lists of rows with more than six carriers
+    long long *dbg;                    // [16] profiling counters (clock64 cycles per phase, summed over steps)
     long long V;                       // informative rows == num_vars
     long long colPitchW;               // words per sample-major row (multiple of 8)
     int S;
@@ -72,12 +82,24 @@ struct SelParams {
     int L;                             // limb bits
     int scale;                         // fixed-point scale: value = AF * 2^scale
     int af;                            // 0 count mode, 1 AF flavours
+    unsigned long long tail_budget;    // head kernels hand over to the tail kernel once st->live_bits <= this (0 = never)
+    unsigned int tail_rows;            // ... and the pick at hand newly covers fewer rows than this
+    unsigned int regain_rows;          // picks that newly cover >= this many rows trigger a gain recompute (0 = never)
 };
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ long long global_timer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
 {
@@ -152,8 +174,8 @@ struct IngestScratch {
     unsigned int *block_offsets = nullptr;
     long long cap_rows = 0;
 };
-int ingest_scratch_reserve(IngestScratch &sc, long long rows);
-void ingest_scratch_free(IngestScratch &sc);
+int ingest_scratch_reserve(IngestScratch &sc, long long rows, cudaStream_t stream);
+void ingest_scratch_free(IngestScratch &sc, cudaStream_t stream);
 int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *raw, long long n_rows,
                   long long pitch_in, const double *af_in, int S, int pitchW, uint32_t *rows_out, double *af_out,
                   long long *d_nrows, int *n_launch);
@@ -171,6 +193,18 @@ int persistent_grid(int device, int *grid_out, int *block_out);
 int launch_persistent(cudaStream_t stream, const SelParams &p, int grid, int block, unsigned int *bar_counter,
                       ArgPartial *partials, int *n_launch);
 int launch_debug_scores(cudaStream_t stream, const SelParams &p, double *score_out, int *n_launch);
+int launch_regain(cudaStream_t stream, const SelParams &p, int *n_launch);
+int launch_sum_gains(cudaStream_t stream, const SelParams &p, int *n_launch);
+int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, unsigned int *list_off,
+                       unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,
+                       int *n_launch);
+int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *old_lists, const unsigned int *old_off,
+                        const unsigned int *old_len, uint4 *new_lists, unsigned int *new_off, unsigned int *new_len,
+                        int *n_launch);
+int tail_plan(const SelParams &p, int *ok_out);
+int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, int *n_launch);
+int cluster_plan(const SelParams &p, int *cluster_out);
+int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch);
 
 // convert.cu
 int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S, int ploidy, uint8_t *packed,

@@ -193,23 +193,23 @@ __global__ void bump_rows_kernel(long long *d_nrows, const long long *d_chunk_to
 
 }  // namespace
 
-int ingest_scratch_reserve(IngestScratch &sc, long long rows)
+int ingest_scratch_reserve(IngestScratch &sc, long long rows, cudaStream_t stream)
 {
     if (rows <= sc.cap_rows) return UTMOS_OK;
-    ingest_scratch_free(sc);
+    ingest_scratch_free(sc, stream);
     const long long nb = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
-    UT_CUDA(cudaMalloc(&sc.flags, (size_t)rows));
-    UT_CUDA(cudaMalloc(&sc.block_counts, sizeof(unsigned int) * (size_t)nb));
-    UT_CUDA(cudaMalloc(&sc.block_offsets, sizeof(unsigned int) * (size_t)nb));
+    UT_CUDA(cudaMallocAsync(&sc.flags, (size_t)rows, stream));
+    UT_CUDA(cudaMallocAsync(&sc.block_counts, sizeof(unsigned int) * (size_t)nb, stream));
+    UT_CUDA(cudaMallocAsync(&sc.block_offsets, sizeof(unsigned int) * (size_t)nb, stream));
     sc.cap_rows = rows;
     return UTMOS_OK;
 }
 
-void ingest_scratch_free(IngestScratch &sc)
+void ingest_scratch_free(IngestScratch &sc, cudaStream_t stream)
 {
-    if (sc.flags) cudaFree(sc.flags);
-    if (sc.block_counts) cudaFree(sc.block_counts);
-    if (sc.block_offsets) cudaFree(sc.block_offsets);
+    if (sc.flags) cudaFreeAsync(sc.flags, stream);
+    if (sc.block_counts) cudaFreeAsync(sc.block_counts, stream);
+    if (sc.block_offsets) cudaFreeAsync(sc.block_offsets, stream);
     sc = IngestScratch();
 }
 
@@ -238,7 +238,7 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
                   long long *d_nrows, int *n_launch)
 {
     if (n_rows <= 0) return UTMOS_OK;
-    UT_TRY(ingest_scratch_reserve(sc, n_rows));
+    UT_TRY(ingest_scratch_reserve(sc, n_rows, stream));
     *n_launch += 4;
     long long *d_total = d_nrows + 1;
     switch (kind) {

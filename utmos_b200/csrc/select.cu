@@ -158,6 +158,58 @@ __global__ void __launch_bounds__(256) colpop_kernel(const uint32_t *__restrict_
     }
 }
 
+
+// Gain recompute ("regain"): when a pick newly covers very many rows, subtracting them bit by bit costs one
+// atomic per set bit (tens of millions for the first picks, which carry the common variants).  Recomputing
+// every gain from the sample-major copy is one streaming pass (popcount of col & live) whatever the rows hold.
+// Runs only when the selection kernel left st->regain set.
+__global__ void __launch_bounds__(256) regain_kernel(SelParams p)
+{
+    if (p.st->regain == 0) return;
+    const int s = blockIdx.x;
+    if (s >= p.S) return;
+    const uint4 *col = reinterpret_cast<const uint4 *>(p.cols + (long long)s * p.colPitchW);
+    const uint4 *lv = reinterpret_cast<const uint4 *>(p.live);
+    const long long n4 = p.colPitchW / 4;
+    unsigned int alive = 0;
+    unsigned long long lo = 0, hi = 0;
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+        const uint4 c = ld_stream_u128(col + i);
+        const uint4 l = __ldcg(lv + i);
+        uint32_t w[4] = {c.x & l.x, c.y & l.y, c.z & l.z, c.w & l.w};
+        alive += __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+        if (p.af) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t x = w[u];
+                while (x) {
+                    const long long r = (i * 4 + u) * 32 + (__ffs(x) - 1);
+                    x &= x - 1;
+                    lo += __ldg(p.q_lo + r);
+                    hi += __ldg(p.q_hi + r);
+                }
+            }
+        }
+    }
+    __shared__ unsigned int s_alive[8];
+    __shared__ unsigned long long s_lo[8], s_hi[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        alive += __shfl_xor_sync(0xffffffffu, alive, o);
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_alive[threadIdx.x >> 5] = alive; s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int a = 0;
+        unsigned long long l = 0, h = 0;
+        for (int i = 0; i < 8; ++i) { a += s_alive[i]; l += s_lo[i]; h += s_hi[i]; }
+        p.gain_cnt[s] = a;
+        if (p.af) { p.gain_lo[s] = l; p.gain_hi[s] = h; }
+    }
+}
+
 // K3 (variant-major source): one warp per row, one reduction per set bit.
 //   WHAT bit 0: var_count over all rows, bit 1: gain_cnt over live rows, bit 2: AF limbs over live rows
 __global__ void __launch_bounds__(256) row_gain_kernel(SelParams p, unsigned int *var_count, int what)
@@ -271,7 +323,7 @@ __device__ __forceinline__ void retire_row(const SelParams &p, long long r, int 
 }
 
 // one warp handles 32 consecutive words (1024 rows) of the live mask for winner b
-__device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long chunk, int lane)
+__device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long chunk, int lane, bool retire = true)
 {
     const long long w = chunk * 32 + lane;
     uint32_t lv = 0, nw = 0;
@@ -290,6 +342,7 @@ __device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long
         }
     }
     if (nw) __stcg(p.live + w, lv ^ nw);
+    if (!retire) return;                              // gains will be recomputed by regain_kernel
     unsigned int pending = __ballot_sync(0xffffffffu, nw != 0);
     while (pending) {
         const int src = __ffs(pending) - 1;
@@ -327,6 +380,7 @@ __global__ void __launch_bounds__(1024) argmax_step_kernel(SelParams p)
             p.out_idx[i] = b.idx;
             p.out_new[i] = b.cnt;
             p.out_score[i] = b.score;
+            p.out_time[i] = global_timer_ns();
             st->step = i + 1;
             st->tot += b.cnt;
             p.mask[b.idx] = 0;                            // utmos/select.py:100
@@ -393,6 +447,9 @@ __global__ void __launch_bounds__(1024, 1) select_persistent_kernel(SelParams p,
     long long step = st->step, tot = st->tot;
     const long long limit = st->limit;
     int stop = st->stop;
+    int regain = 0;
+    int want_tail = 0;
+    __shared__ unsigned long long s_sumw[32];
     const int per = (p.S + (int)nblocks - 1) / (int)nblocks;
     const int my_begin = min(p.S, (int)blockIdx.x * per), my_end = min(p.S, my_begin + per);
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -401,31 +458,54 @@ __global__ void __launch_bounds__(1024, 1) select_persistent_kernel(SelParams p,
     __syncthreads();
 
     while (stop == 0 && step < limit) {
-        // ---- phase A: partial argmax over this CTA's slice of the samples
+        // ---- phase A: partial argmax over this CTA's slice of the samples (+ sum of its gains)
+        {
+            unsigned long long acc = 0;
+            if (p.tail_budget)
+                for (int s = my_begin + (int)threadIdx.x; s < my_end; s += (int)blockDim.x) acc += __ldcg(p.gain_cnt + s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_sumw[threadIdx.x >> 5] = acc;
+        }
         Best b = block_best(scan_best(p, my_begin, my_end), s_red);
         if (threadIdx.x == 0) {
             ArgPartial a;
             a.score = b.score; a.idx = b.idx; a.cnt = b.cnt;
+            a.sum = 0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a.sum += s_sumw[i];
             partials[blockIdx.x] = a;
         }
         if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
         Best t{-1.0e308, 0x7fffffff, 0u};
+        unsigned long long live_now = 0;
         for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) {
             Best o;
             o.score = __ldcg(&partials[i].score);
             o.idx = __ldcg(&partials[i].idx);
             o.cnt = __ldcg(&partials[i].cnt);
+            live_now += __ldcg(&partials[i].sum);
             t = best_of(t, o);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) live_now += __shfl_xor_sync(0xffffffffu, live_now, o);
+        __syncthreads();
+        if (lane == 0) s_sumw[threadIdx.x >> 5] = live_now;
         b = block_best(t, s_red);
+        live_now = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) live_now += s_sumw[i];
         if (p.S == 0 || b.score == 0.0) {                  // utmos/select.py:51-52
             stop = UTMOS_STOP_ZERO;
+            break;
+        }
+        if (p.tail_budget && live_now <= p.tail_budget && b.cnt < p.tail_rows) {
+            want_tail = 1;                                 // sparse and small: the single-CTA tail kernel is faster
             break;
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             p.out_idx[step] = b.idx;
             p.out_new[step] = b.cnt;
             p.out_score[step] = b.score;
+            p.out_time[step] = global_timer_ns();
             p.mask[b.idx] = 0;                             // utmos/select.py:100
         }
         step += 1;
@@ -434,17 +514,324 @@ __global__ void __launch_bounds__(1024, 1) select_persistent_kernel(SelParams p,
             stop = UTMOS_STOP_ALL;
             break;
         }
-        // ---- phase B: clear the newly covered rows, subtract them from every gain
-        for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(p, b.idx, c, lane);
+        // ---- phase B: clear the newly covered rows, subtract them from every gain (or leave that to regain)
+        regain = p.cols && p.regain_rows && b.cnt >= p.regain_rows;
+        for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(p, b.idx, c, lane, !regain);
         if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (regain) break;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->step = step;
         st->tot = tot;
         st->stop = stop;
         st->winner = -1;
+        st->regain = regain;
+        st->want_tail = want_tail;
     }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// cluster flavour (default when the state fits): ONE thread-block cluster of up to 16 CTAs runs the whole
+// selection.  The step loop is latency bound (two dependent synchronisations per greedy step), so the
+// grid-wide barrier through L2 is replaced by the hardware cluster barrier, and everything the loop
+// touches every step lives in distributed shared memory:
+//     gains, mask and weights of sample s  -> CTA s / per          (argmax never leaves the SM)
+//     live-mask words                       -> CTA w / liveW        (probe = smem AND global column word)
+// Decrements are fire-and-forget atomics on the owner CTA's shared memory (DSMEM).  Global memory
+// traffic per step is the winner's column slice (one pass) plus the newly covered rows (each once).
+// While a step runs, every CTA prefetches its slice of the runner-up's column into L2.
+// ------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+struct ClusterCfg {
+    int per;            // samples per CTA (multiple of 32)
+    int liveW;          // live-mask words per CTA (multiple of 32)
+    int off_lo, off_hi, off_w, off_mask, off_live, off_part;   // byte offsets into dynamic smem (cnt at 0)
+    int lanes_per_row;  // power of two: lanes that share one row when retiring
+};
+
+
+__device__ __forceinline__ void retire_row_dsmem(const SelParams &p, const ClusterCfg &cfg, cg::cluster_group &cluster,
+                                                 unsigned int *s_cnt, unsigned long long *s_lo,
+                                                 unsigned long long *s_hi, long long r, int lane)
+{
+    const uint32_t *row = p.rows + r * p.pitchW;
+    const int wpc = cfg.per >> 5;                 // words per owner CTA
+    unsigned long long nl = 0, nh = 0;
+    if (p.af) { nl = 0ull - p.q_lo[r]; nh = 0ull - p.q_hi[r]; }
+    for (int k0 = 0; k0 < p.nW; k0 += 128) {
+        uint32_t x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 32 + lane;
+            x[u] = k < p.nW ? __ldg(row + k) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t w = x[u];
+            if (!w) continue;
+            const int k = k0 + u * 32 + lane;
+            const int owner = k / wpc;
+            const int base = (k - owner * wpc) << 5;
+            unsigned int *rc = cluster.map_shared_rank(s_cnt, owner) + base;
+            unsigned long long *rl = nullptr, *rh = nullptr;
+            if (p.af) { rl = cluster.map_shared_rank(s_lo, owner) + base; rh = cluster.map_shared_rank(s_hi, owner) + base; }
+            while (w) {
+                const int j = __ffs(w) - 1;
+                w &= w - 1;
+                atomicAdd(rc + j, 0xffffffffu);
+                if (p.af) { atomicAdd(rl + j, nl); atomicAdd(rh + j, nh); }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, ClusterCfg cfg)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ Best s_red[32];
+    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(smem);
+    unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(smem + cfg.off_lo);
+    unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(smem + cfg.off_hi);
+    double *s_w = reinterpret_cast<double *>(smem + cfg.off_w);
+    uint8_t *s_mask = smem + cfg.off_mask;
+    uint32_t *s_live = reinterpret_cast<uint32_t *>(smem + cfg.off_live);
+    ArgPartial *s_part = reinterpret_cast<ArgPartial *>(smem + cfg.off_part);
+
+    const int rank = (int)cluster.block_rank();
+    const int CL = (int)cluster.num_blocks();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int s0 = rank * cfg.per;
+    const int n_mine = max(0, min(cfg.per, p.S - s0));
+    const long long w0 = (long long)rank * cfg.liveW;
+    const bool has_w = p.weights != nullptr;
+    SelState *st = p.st;
+
+    // ---- load this CTA's slice of the state into shared memory
+    for (int i = tid; i < cfg.per; i += blockDim.x) {
+        const bool ok = i < n_mine;
+        s_cnt[i] = ok ? p.gain_cnt[s0 + i] : 0u;
+        s_mask[i] = ok ? p.mask[s0 + i] : (uint8_t)2;
+        if (p.af) { s_lo[i] = ok ? p.gain_lo[s0 + i] : 0ull; s_hi[i] = ok ? p.gain_hi[s0 + i] : 0ull; }
+        if (has_w) s_w[i] = ok ? p.weights[s0 + i] : 0.0;
+    }
+    for (int i = tid; i < cfg.liveW; i += blockDim.x) s_live[i] = w0 + i < p.colPitchW ? p.live[w0 + i] : 0u;
+    long long step = st->step, tot = st->tot;
+    const long long limit = st->limit;
+    int stop = st->stop;
+    int regain = 0, want_tail = 0;
+    const int nchunks = cfg.liveW >> 5;
+    __shared__ unsigned long long s_sumw[32];
+    __shared__ unsigned int s_wq[32][64];               // per-warp queue of rows to retire
+    cluster.sync();
+
+    long long t_a = 0, t_s1 = 0, t_b = 0, t_s2 = 0, t_mark = clock64();
+#define UT_TICK(acc) do { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } while (0)
+    while (stop == 0 && step < limit) {
+        // ---- phase A: argmax over the samples this CTA owns (shared memory only)
+        Best b{-1.0e308, 0x7fffffff, 0u};
+        unsigned long long acc = 0;
+        for (int i = tid; i < n_mine; i += blockDim.x) {
+            const unsigned int c = s_cnt[i];
+            acc += c;
+            double g = 0.0;
+            if (s_mask[i] == 1) {
+                g = p.af ? fixed_to_double(s_lo[i], s_hi[i], p.L, p.scale) : (double)c;
+                if (has_w) g *= s_w[i];
+            }
+            if (arg_better(g, s0 + i, b.score, b.idx)) { b.score = g; b.idx = s0 + i; b.cnt = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_sumw[warp] = acc;
+        b = block_best(b, s_red);
+        if (tid < CL) {                                   // publish the partial in every CTA of the cluster
+            ArgPartial *remote = cluster.map_shared_rank(s_part, tid);
+            ArgPartial a;
+            a.score = b.score; a.idx = b.idx; a.cnt = b.cnt;
+            a.sum = 0;
+            for (int i = 0; i < nwarp; ++i) a.sum += s_sumw[i];
+            remote[rank] = a;
+        }
+        UT_TICK(t_a);
+        cluster.sync();
+        UT_TICK(t_s1);
+        // every warp reduces the CL partials redundantly (no further CTA-wide sync needed)
+        Best t{-1.0e308, 0x7fffffff, 0u};
+        unsigned long long live_now = 0;
+        if (lane < CL) { t.score = s_part[lane].score; t.idx = s_part[lane].idx; t.cnt = s_part[lane].cnt; live_now = s_part[lane].sum; }
+        const Best mine = t;
+        b = warp_best(t);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) live_now += __shfl_xor_sync(0xffffffffu, live_now, o);
+        if (p.S == 0 || b.score == 0.0) {                 // utmos/select.py:51-52
+            stop = UTMOS_STOP_ZERO;
+            break;
+        }
+        if (p.tail_budget && live_now <= p.tail_budget && b.cnt < p.tail_rows) {
+            want_tail = 1;                                // sparse and small: the single-CTA tail kernel is faster
+            break;
+        }
+        // runner-up among the other CTAs' local winners: a likely next pick -> prefetch its column slice
+        Best t2 = (lane < CL && mine.idx != b.idx) ? mine : Best{-1.0e308, 0x7fffffff, 0u};
+        t2 = warp_best(t2);
+        const int owner = b.idx / cfg.per;
+        if (tid == 0) {
+            if (rank == 0) {
+                p.out_idx[step] = b.idx;
+                p.out_new[step] = b.cnt;
+                p.out_score[step] = b.score;
+                p.out_time[step] = global_timer_ns();
+            }
+            if (rank == owner) s_mask[b.idx - s0] = 0;    // utmos/select.py:100
+        }
+        step += 1;
+        tot += b.cnt;
+        if (tot >= p.V) {                                 // utmos/select.py:110-112
+            stop = UTMOS_STOP_ALL;
+            break;
+        }
+        // ---- phase B: clear newly covered rows from this CTA's live words, retire them everywhere
+        regain = p.cols && p.regain_rows && b.cnt >= p.regain_rows;   // too many rows: recompute instead
+        if (!regain && p.cols && t2.idx != 0x7fffffff && t2.score > 0.0) {
+            const uint32_t *c2 = p.cols + (long long)t2.idx * p.colPitchW + w0;
+            for (int i = tid * 32; i < cfg.liveW && w0 + i < p.colPitchW; i += blockDim.x * 32) prefetch_l2(c2 + i);
+        }
+        for (int c = warp; c < nchunks; c += nwarp) {
+            const int wl = c * 32 + lane;
+            const long long w = w0 + wl;
+            const uint32_t lv = s_live[wl];
+            uint32_t nw = 0;
+            if (p.cols) {
+                if (w < p.colPitchW) nw = lv & __ldg(p.cols + (long long)b.idx * p.colPitchW + w);
+            } else if (lv) {
+                const int bw = b.idx >> 5, bb = b.idx & 31;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    if ((lv >> j) & 1u) {
+                        const uint32_t x = __ldg(p.rows + (w * 32 + j) * p.pitchW + bw);
+                        nw |= ((x >> bb) & 1u) << j;
+                    }
+                }
+            }
+            if (nw) s_live[wl] = lv ^ nw;
+            if (regain) continue;                         // warp-uniform
+            if (nw) {
+                uint32_t m = nw;                          // warm L2 with the rows this lane found
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const char *rp = reinterpret_cast<const char *>(p.rows + (w * 32 + j) * p.pitchW);
+                    const int lines = min(8, (p.pitchW * 4 + 127) >> 7);
+                    for (int l = 0; l < lines; ++l) prefetch_l2(rp + l * 128);
+                }
+            }
+            // queue this warp's newly covered rows, then retire them G lanes per row with every 128-bit load of
+            // up to 32/G rows in flight before the first use
+            int mine_n = __popc(nw), incl = mine_n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += tt;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            if (total <= 64) {
+                int pos = incl - mine_n;
+                uint32_t m = nw;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    s_wq[warp][pos++] = (unsigned int)((w << 5) + j);
+                }
+                __syncwarp();
+                const int G = cfg.lanes_per_row, sub = lane & (G - 1), slot = lane / G, rpw = 32 / G;
+                const int n4 = p.pitchW >> 2, wpc = cfg.per >> 5;
+                for (int q0 = 0; q0 < total; q0 += rpw) {
+                    const int q = q0 + slot;
+                    const bool have = q < total;
+                    const long long r = have ? (long long)s_wq[warp][q] : 0ll;
+                    const uint4 *row4 = reinterpret_cast<const uint4 *>(p.rows + r * p.pitchW);
+                    unsigned long long nl = 0, nh = 0;
+                    if (p.af && have) { nl = 0ull - p.q_lo[r]; nh = 0ull - p.q_hi[r]; }
+                    for (int t0 = 0; t0 * G < n4; t0 += 4) {
+                        uint4 x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = (t0 + u) * G + sub;
+                            x[u] = (have && j < n4) ? __ldg(row4 + j) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = (t0 + u) * G + sub;
+                            const uint32_t w4[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                uint32_t ww = w4[e];
+                                if (!ww) continue;
+                                const int k = j * 4 + e;
+                                const int owner = k / wpc;
+                                const int sb = (k - owner * wpc) << 5;
+                                unsigned int *rc = cluster.map_shared_rank(s_cnt, owner) + sb;
+                                unsigned long long *rl = nullptr, *rh = nullptr;
+                                if (p.af) { rl = cluster.map_shared_rank(s_lo, owner) + sb; rh = cluster.map_shared_rank(s_hi, owner) + sb; }
+                                while (ww) {
+                                    const int jj = __ffs(ww) - 1;
+                                    ww &= ww - 1;
+                                    atomicAdd(rc + jj, 0xffffffffu);
+                                    if (p.af) { atomicAdd(rl + jj, nl); atomicAdd(rh + jj, nh); }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            } else {
+                unsigned int pending = __ballot_sync(0xffffffffu, nw != 0);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    uint32_t m = __shfl_sync(0xffffffffu, nw, src);
+                    const long long rbase = (w0 + c * 32 + src) * 32;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        retire_row_dsmem(p, cfg, cluster, s_cnt, s_lo, s_hi, rbase + j, lane);
+                    }
+                }
+            }
+        }
+        UT_TICK(t_b);
+        cluster.sync();
+        UT_TICK(t_s2);
+        if (regain) break;
+    }
+#undef UT_TICK
+    if (rank == 0 && tid == 0 && p.dbg) {
+        p.dbg[0] += t_a; p.dbg[1] += t_s1; p.dbg[2] += t_b; p.dbg[3] += t_s2; p.dbg[4] += 1;
+    }
+
+    // ---- write the state back so the selection can be resumed / inspected
+    cluster.sync();
+    for (int i = tid; i < n_mine; i += blockDim.x) {
+        p.gain_cnt[s0 + i] = s_cnt[i];
+        p.mask[s0 + i] = s_mask[i];
+        if (p.af) { p.gain_lo[s0 + i] = s_lo[i]; p.gain_hi[s0 + i] = s_hi[i]; }
+    }
+    for (int i = tid; i < cfg.liveW; i += blockDim.x)
+        if (w0 + i < p.colPitchW) p.live[w0 + i] = s_live[i];
+    if (rank == 0 && tid == 0) {
+        st->step = step;
+        st->tot = tot;
+        st->stop = stop;
+        st->winner = -1;
+        st->regain = regain;
+        st->want_tail = want_tail;
+    }
+}
+
 
 __global__ void debug_scores_kernel(SelParams p, double *score_out)
 {
@@ -554,6 +941,95 @@ int launch_persistent(cudaStream_t stream, const SelParams &p, int grid, int blo
     *n_launch += 1;
     return UTMOS_OK;
 }
+
+
+// Cluster flavour: returns UTMOS_OK and *cluster_out = 0 when the state does not fit / clusters are unavailable.
+static int cluster_layout(const SelParams &p, int CL, ClusterCfg *cfg, size_t *smem_bytes)
+{
+    const int per = ((p.S + CL - 1) / CL + 31) / 32 * 32;
+    const long long liveW = ((p.colPitchW + CL - 1) / CL + 31) / 32 * 32;
+    if (liveW > (1 << 20)) return 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int)o; };
+    take((size_t)per * 4);                                  // cnt at offset 0
+    cfg->off_lo = take(p.af ? (size_t)per * 8 : 0);
+    cfg->off_hi = take(p.af ? (size_t)per * 8 : 0);
+    cfg->off_w = take(p.weights ? (size_t)per * 8 : 0);
+    cfg->off_mask = take((size_t)per);
+    cfg->off_live = take((size_t)liveW * 4);
+    cfg->off_part = take(sizeof(ArgPartial) * 16);
+    int G = 1;
+    while (G < 32 && (p.pitchW / 4 + G - 1) / G > 8) G <<= 1;
+    cfg->lanes_per_row = G;
+    cfg->per = per;
+    cfg->liveW = (int)liveW;
+    *smem_bytes = off;
+    return 1;
+}
+
+int cluster_plan(const SelParams &p, int *cluster_out)
+{
+    *cluster_out = 0;
+    static int configured = 0;
+    if (!configured) {
+        UT_CUDA(cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = 1;
+    }
+    const int tries[2] = {16, 8};
+    for (int t = 0; t < 2; ++t) {
+        const int CL = tries[t];
+        ClusterCfg cfg;
+        size_t smem = 0;
+        if (!cluster_layout(p, CL, &cfg, &smem)) continue;
+        if (smem > 227 * 1024 - 1024) continue;
+        if (cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(CL);
+        lc.blockDim = dim3(1024);
+        lc.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, select_cluster_kernel, &lc) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (n >= 1) { *cluster_out = CL; return UTMOS_OK; }
+    }
+    return UTMOS_OK;
+}
+
+int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch)
+{
+    ClusterCfg cfg;
+    size_t smem = 0;
+    if (!cluster_layout(p, CL, &cfg, &smem)) { set_error("cluster layout failed"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(CL);
+    lc.blockDim = dim3(1024);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    UT_CUDA(cudaLaunchKernelEx(&lc, select_cluster_kernel, p, cfg));
+    *n_launch += 1;
+    return UTMOS_OK;
+}
+
+int launch_regain(cudaStream_t stream, const SelParams &p, int *n_launch)
+{
+    if (!p.cols || p.S <= 0) return UTMOS_OK;
+    regain_kernel<<<p.S, 256, 0, stream>>>(p);
+    *n_launch += 1;
+    UT_CUDA(cudaGetLastError());
+    return UTMOS_OK;
+}
+
 
 int launch_debug_scores(cudaStream_t stream, const SelParams &p, double *score_out, int *n_launch)
 {
