@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--vars", type=int, default=N_VARS, help="rows per rank (default: the 1kGP chr22 count)")
     ap.add_argument("--flags", type=int, default=0, help="utmos_create flags (kernel flavour)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--step-times", action="store_true", help="record per-pick timestamps (profiling; slows the loop)")
+    ap.add_argument("--tail-rows", type=int, default=-1, help="override the tail hand-over threshold")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,18 +194,30 @@ def main():
     mask = np.ones(n_samples, dtype=np.uint8)
 
     def one_selection(resident):
+        t = [time.perf_counter()]
         dm = _native.DeviceMatrix(n_samples, _native.AF_NONE, rows_hint=n_vars, device=device, flags=args.flags)
+        t.append(time.perf_counter())
         if resident:
             dm.append_packed_device(cohort.rows.ptr, n_vars, pitch, 0)
         else:
             dm.append_packed(host_rows, None)
+        t.append(time.perf_counter())
         var_count = dm.finalize()
+        t.append(time.perf_counter())
+        if args.step_times:
+            dm.set_option(2, 1)
+        if args.tail_rows >= 0:
+            dm.set_option(3, args.tail_rows)
         dm.begin(mask)
+        t.append(time.perf_counter())
         idx, new, score, stop = dm.steps(n_samples)
+        t.append(time.perf_counter())
         info, tim = dm.info(), dm.timings()
         tim["step_ns"] = dm.step_times(0, len(idx))
         tim["counters"] = dm.counters()
         dm.close()
+        t.append(time.perf_counter())
+        tim["host_ms"] = [round((b - a) * 1e3, 3) for a, b in zip(t[:-1], t[1:])]
         return idx, new, score, stop, var_count, info, tim
 
     def timed(resident):
@@ -238,12 +252,12 @@ def main():
     e2e_value = world * packed_bytes / 1e9 / (t_e2e / args.steps)
 
     # device-side (CUDA event) time of each phase, averaged over the timed resident steps
-    phases = {k: float(np.mean([o[6][k] for o in outs_res])) for k in outs_res[0][6] if k not in ("step_ns", "counters")}
-    phases_e2e = {k: float(np.mean([o[6][k] for o in outs_e2e])) for k in outs_e2e[0][6] if k not in ("step_ns", "counters")}
+    phases = {k: float(np.mean([o[6][k] for o in outs_res])) for k in outs_res[0][6] if k not in ("step_ns", "counters", "host_ms")}
+    phases_e2e = {k: float(np.mean([o[6][k] for o in outs_e2e])) for k in outs_e2e[0][6] if k not in ("step_ns", "counters", "host_ms")}
     step_ns = outs_res[-1][6]["step_ns"].astype(np.float64)
     gaps = np.diff(step_ns) / 1e3                      # us between consecutive picks
     step_profile = {}
-    if len(gaps) > 200:
+    if args.step_times and len(gaps) > 200:
         step_profile = {"first_20_steps_ms": float(gaps[:20].sum() / 1e3), "steps_20_200_ms": float(gaps[20:200].sum() / 1e3),
                         "steps_200_end_ms": float(gaps[200:].sum() / 1e3),
                         "tail_us_per_step_median": float(np.median(gaps[200:])),
@@ -311,7 +325,7 @@ def main():
             "gpu_launches": int(info["kernel_launches"]) * args.steps,
             "roofline": roofline, "streaming_kernels": streaming, "phases_ms": phases,
             "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "step_profile": step_profile, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:12]], "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
+            "step_profile": step_profile, "host_ms_create_append_finalize_begin_steps_close": {"resident": np.mean([o[6]["host_ms"] for o in outs_res], axis=0).round(3).tolist(), "e2e": np.mean([o[6]["host_ms"] for o in outs_e2e], axis=0).round(3).tolist()}, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:12]], "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

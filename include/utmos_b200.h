@@ -50,6 +50,7 @@ typedef struct utmos_ctx utmos_ctx;
 #define UTMOS_F_FORCE_TRANSPOSE 4u   /* fail instead of falling back when the sample-major copy does not fit */
 #define UTMOS_F_NO_CLUSTER 8u        /* grid-wide persistent kernel instead of the one-cluster DSMEM kernel */
 #define UTMOS_F_NO_TAIL 16u          /* never switch to the single-CTA list-driven tail kernel */
+#define UTMOS_F_DSMEM_GAINS 32u      /* cluster kernel keeps the gains in distributed shared memory (default: L2 atomics) */
 
 /* stop reasons reported by utmos_select_steps (utmos/select.py:91, :51-52/:93-96, :110-112) */
 #define UTMOS_STOP_NONE 0            /* max_steps of this call done; selection can continue */
@@ -139,6 +140,8 @@ int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
 /* Tunables.  UTMOS_OPT_REGAIN_ROWS: a pick that newly covers >= value rows triggers one streaming recompute of
  * all gains from the sample-major copy instead of per-bit subtraction (0 = never, -1 = default max(4096, V/128)). */
 #define UTMOS_OPT_REGAIN_ROWS 1
+#define UTMOS_OPT_STEP_TIMES 2        /* 1: record %globaltimer per pick for utmos_debug_step_times (adds latency) */
+#define UTMOS_OPT_TAIL_ROWS 3         /* hand over to the single-CTA tail kernel once a pick covers fewer rows (default 1536) */
 int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
 
 /* info[0]=num_vars, [1]=row pitch bytes, [2]=has sample-major copy, [3]=device bytes in use,

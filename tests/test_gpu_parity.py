@@ -19,6 +19,7 @@ MODES = {
     "tail": 0,
     "tail_persistent_head": _native.F_NO_CLUSTER,
     "cluster": _native.F_NO_TAIL,
+    "cluster_dsmem": _native.F_NO_TAIL | _native.F_DSMEM_GAINS,
     "cluster_notranspose": _native.F_NO_TRANSPOSE,
     "persistent": _native.F_NO_CLUSTER | _native.F_NO_TAIL,
     "persistent_notranspose": _native.F_NO_CLUSTER | _native.F_NO_TRANSPOSE,

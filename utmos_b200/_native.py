@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libutmos_b200.so")
 
 AF_NONE, AF_F64, AF_F32 = 0, 1, 2
-F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL = 1, 2, 4, 8, 16
+F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL, F_DSMEM_GAINS = 1, 2, 4, 8, 16, 32
 STOP_NONE, STOP_ZERO, STOP_ALL = 0, 1, 2
 E_NOGPU = -3
 
@@ -223,6 +223,10 @@ class DeviceMatrix:
         out = np.zeros(16, dtype=np.int64)
         check(lib().utmos_debug_counters(self._ctx, _ptr(out)))
         return out
+
+    def set_option(self, option, value):
+        """utmos_set_option: 1 regain rows, 2 per-step timestamps, 3 tail hand-over rows."""
+        check(lib().utmos_set_option(self._ctx, int(option), int(value)))
 
     def set_regain_rows(self, rows):
         """Override the recompute-vs-subtract threshold (0 never recompute, -1 default)."""

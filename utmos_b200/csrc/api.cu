@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "common.cuh"
 
@@ -34,6 +35,21 @@ int cuda_fail(cudaError_t err, const char *what, const char *file, int line)
 }
 
 namespace {
+// UTMOS_B200_TRACE=1: host-side wall time of the API sub-steps on stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char *what;
+    explicit Trace(const char *w) : on(getenv("UTMOS_B200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    void lap(const char *label)
+    {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[utmos_b200 trace] %s: %s %.3f ms\n", what, label,
+                std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 constexpr size_t kStageBytes = 64ull << 20;      // per staging buffer (two pinned host + two device)
 constexpr int kGraphSteps = 32;                  // step pairs per CUDA graph replay
 enum { T_H2D = 0, T_INGEST = 1, T_TRANSPOSE = 2, T_GAIN = 3, T_SELECT = 4, T_COUNT = 5 };
@@ -97,7 +113,8 @@ struct utmos_ctx {
     int lists_cur = 0;
     unsigned long long lists_total = 0;   // entries in the current lists (live bits when they were built)
     bool lists_valid = false;
-    unsigned int tail_rows = 768;         // hand over to the single-CTA tail once picks cover fewer rows than this
+    int dbg_time = 0;
+    unsigned int tail_rows = 1536;        // hand over to the single-CTA tail once picks cover fewer rows than this
     unsigned long long tail_budget = 0;   // handed to the head kernels while the tail flavour waits for sparsity
     unsigned long long total_bits = 0;    // set bits of the scoring rows at step 0
     long long regain_rows = -1;        // -1 = default heuristic
@@ -140,6 +157,23 @@ void dev_free(utmos_ctx *c, T *&p, size_t bytes)
         p = nullptr;
     }
 }
+
+// Big blocks (bit matrices, edge lists, staging) come from cudaMalloc and are parked in a small process-wide
+// cache when a context lets go of them: cudaMalloc / cudaFree of hundreds of MB cost milliseconds and cudaFree
+// synchronises the device, which a service that runs selection after selection must not pay every time.
+struct BigBlock {
+    void *ptr;
+    size_t bytes;
+    int device;
+};
+std::vector<BigBlock> g_big_cache;
+constexpr size_t kBigMin = 8ull << 20;
+constexpr size_t kBigCacheMax = 24;
+
+int big_alloc(utmos_ctx *c, void **p, size_t bytes);
+void big_free_raw(int device, void *ptr, size_t bytes);
+template <typename T>
+void big_free(utmos_ctx *c, T *&p, size_t bytes);
 
 // pinned staging buffers are expensive to create (page locking): keep two per process and lend them out
 struct PinnedCache {
@@ -191,20 +225,70 @@ int grow_rows(utmos_ctx *c, long long need)
     uint32_t *nr = nullptr;
     double *na = nullptr;
     const size_t row_bytes = (size_t)c->pitchW * 4;
-    UT_TRY(dev_alloc(c, (void **)&nr, (size_t)cap * row_bytes));
+    UT_TRY(big_alloc(c, (void **)&nr, (size_t)cap * row_bytes));
     if (c->af_mode != UTMOS_AF_NONE) UT_TRY(dev_alloc(c, (void **)&na, (size_t)cap * 8));
     if (c->d_rows) {
         // rows already ingested are copied over stream-ordered behind the ingest kernels
         UT_CUDA(cudaMemcpyAsync(nr, c->d_rows, (size_t)c->rows_upper * row_bytes, cudaMemcpyDeviceToDevice, c->stream));
         if (na) UT_CUDA(cudaMemcpyAsync(na, c->d_af, (size_t)c->rows_upper * 8, cudaMemcpyDeviceToDevice, c->stream));
         UT_CUDA(cudaStreamSynchronize(c->stream));
-        dev_free(c, c->d_rows, (size_t)c->rows_cap * row_bytes);
+        big_free(c, c->d_rows, (size_t)c->rows_cap * row_bytes);
         dev_free(c, c->d_af, (size_t)c->rows_cap * 8);
     }
     c->d_rows = nr;
     c->d_af = na;
     c->rows_cap = cap;
     return UTMOS_OK;
+}
+
+int big_alloc(utmos_ctx *c, void **p, size_t bytes)
+{
+    if (bytes < kBigMin) return dev_alloc(c, p, bytes);
+    int best = -1;
+    for (size_t i = 0; i < g_big_cache.size(); ++i) {
+        const BigBlock &b = g_big_cache[i];
+        if (b.device == c->device && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 &&
+            (best < 0 || b.bytes < g_big_cache[best].bytes))
+            best = (int)i;
+    }
+    if (best >= 0) {
+        *p = g_big_cache[best].ptr;
+        g_big_cache.erase(g_big_cache.begin() + best);
+    } else {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaErrorMemoryAllocation && !g_big_cache.empty()) {
+            cudaGetLastError();
+            for (auto &b : g_big_cache) cudaFree(b.ptr);      // give parked blocks back and retry
+            g_big_cache.clear();
+            e = cudaMalloc(p, bytes);
+        }
+        UT_CUDA(e);
+    }
+    c->dev_bytes += bytes;
+    return UTMOS_OK;
+}
+
+void big_free_raw(int device, void *ptr, size_t bytes)
+{
+    if (!ptr) return;
+    if (g_big_cache.size() >= kBigCacheMax) {
+        cudaFree(g_big_cache.front().ptr);
+        g_big_cache.erase(g_big_cache.begin());
+    }
+    g_big_cache.push_back(BigBlock{ptr, bytes, device});
+}
+
+// the caller guarantees that no work touching the block is still in flight (streams synchronised)
+template <typename T>
+void big_free(utmos_ctx *c, T *&p, size_t bytes)
+{
+    if (!p) return;
+    if (bytes < kBigMin) { dev_free(c, p, bytes); return; }
+    c->dev_bytes -= std::min(c->dev_bytes, bytes);
+    // a block handed out for `bytes` may be larger: the cache entry must remember the real size, which the
+    // cache itself cannot know here -> store the requested size (it only ever satisfies requests <= that)
+    big_free_raw(c->device, (void *)p, bytes);
+    p = nullptr;
 }
 
 int pinned_acquire(utmos_ctx *c)
@@ -240,7 +324,7 @@ int ensure_stage(utmos_ctx *c, long long af_rows, bool need_host)
     bool fresh = false;
     for (int i = 0; i < 2; ++i) {
         if (!c->d_stage[i]) {
-            UT_TRY(dev_alloc(c, &c->d_stage[i], kStageBytes));
+            UT_TRY(big_alloc(c, &c->d_stage[i], kStageBytes));
             UT_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
             UT_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
             fresh = true;
@@ -333,7 +417,7 @@ void free_select_state(utmos_ctx *c)
 {
     const size_t S = (size_t)c->S;
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-    dev_free(c, c->d_cols, (size_t)((c->S + 31) / 32 * 32) * (size_t)c->colPitchW * 4);
+    big_free(c, c->d_cols, (size_t)((c->S + 31) / 32 * 32) * (size_t)c->colPitchW * 4);
     dev_free(c, c->d_live, (size_t)c->colPitchW * 4);
     dev_free(c, c->d_live0, (size_t)c->colPitchW * 4);
     dev_free(c, c->d_gain_cnt, S * 4);
@@ -353,14 +437,14 @@ void free_select_state(utmos_ctx *c)
     dev_free(c, c->d_out_time, S * 8);
     dev_free(c, c->d_dbg, 128);
     for (int i = 0; i < 2; ++i) {
-        dev_free(c, c->d_lists[i], c->lists_cap[i] * 16);
+        big_free(c, c->d_lists[i], c->lists_cap[i] * 16);
         dev_free(c, c->d_list_off[i], S * 4);
         dev_free(c, c->d_list_len[i], S * 4);
         c->lists_cap[i] = 0;
     }
     dev_free(c, c->d_cursor, S * 4);
     dev_free(c, c->d_pool_cursor, 16);
-    dev_free(c, c->d_pool, c->pool_cap * 2);
+    big_free(c, c->d_pool, c->pool_cap * 2);
     c->pool_cap = 0;
     c->lists_valid = false;
     dev_free(c, c->d_dbg_score, S * 8);
@@ -400,6 +484,8 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     }
     p.tail_budget = c->tail_budget;
     p.tail_rows = c->tail_rows;
+    p.dbg_time = c->dbg_time;
+    p.dsmem_gains = (c->flags & UTMOS_F_DSMEM_GAINS) ? 1 : 0;
     p.st = c->d_state;
     p.V = c->V;
     p.colPitchW = c->colPitchW;
@@ -475,17 +561,21 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
     utmos_device_count(&n);
     if (n <= 0) { set_error("no CUDA device visible: utmos_b200 has no CPU fallback"); return UTMOS_E_NOGPU; }
     if (device < 0 || device >= n) { set_error("create: device index out of range"); return UTMOS_E_ARG; }
+    Trace tr("create");
     UT_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    UT_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+    int cc_major = 0, cc_minor = 0, sm_count = 0;
+    UT_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    UT_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    UT_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major != 10) {
+        set_error(std::string("device is sm_") + std::to_string(cc_major * 10 + cc_minor) +
                   ", this library is built for sm_100a (B200) only");
         return UTMOS_E_NOGPU;
     }
+    tr.lap("device attributes");
     utmos_ctx *c = new utmos_ctx();
     c->device = device;
-    c->n_sms = prop.multiProcessorCount;
+    c->n_sms = sm_count;
     c->S = n_samples;
     c->nW = (int)((n_samples + 31) / 32);
     c->pitchW = (c->nW + 3) / 4 * 4;
@@ -509,7 +599,9 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
         if ((rc = dev_alloc(c, (void **)&c->d_state, sizeof(SelState))) != UTMOS_OK) break;
         if (cudaMemsetAsync(c->d_state, 0, sizeof(SelState), c->stream) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = UTMOS_E_CUDA; break; }
+        tr.lap("streams + state");
         if (rows_hint > 0) rc = grow_rows(c, rows_hint);
+        tr.lap("row buffer");
     } while (0);
     if (rc != UTMOS_OK) { utmos_destroy(c); return rc; }
     *ctx_out = c;
@@ -527,13 +619,13 @@ int utmos_destroy(utmos_ctx *c)
     ingest_scratch_free(c->scratch, c->stream);
     pinned_release(c);
     for (int i = 0; i < 2; ++i) {
-        if (c->d_stage[i]) cudaFreeAsync(c->d_stage[i], c->stream);
+        big_free(c, c->d_stage[i], kStageBytes);
         if (c->d_af_stage[i]) cudaFreeAsync(c->d_af_stage[i], c->stream);
         if (c->h_af_stage[i]) cudaFreeHost(c->h_af_stage[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
     }
-    if (c->d_rows) cudaFreeAsync(c->d_rows, c->stream);
+    big_free(c, c->d_rows, (size_t)c->rows_cap * (size_t)c->pitchW * 4);
     if (c->d_af) cudaFreeAsync(c->d_af, c->stream);
     if (c->d_nrows) cudaFreeAsync(c->d_nrows, c->stream);
     if (c->d_state) cudaFreeAsync(c->d_state, c->stream);
@@ -592,8 +684,10 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
 {
     if (!c) { set_error("null context"); return UTMOS_E_ARG; }
     if (c->finalized) { set_error("finalize called twice"); return UTMOS_E_ARG; }
+    Trace tr("finalize");
     UT_CUDA(cudaSetDevice(c->device));
     UT_TRY(sync_all(c));
+    tr.lap("wait for ingest");
     long long v = 0;
     UT_CUDA(cudaMemcpy(&v, c->d_nrows, 8, cudaMemcpyDeviceToHost));
     c->V = v;
@@ -643,28 +737,30 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
         UT_CUDA(cudaMemsetAsync(c->d_gain0_lo, 0, S * 8, c->stream));
         UT_CUDA(cudaMemsetAsync(c->d_gain0_hi, 0, S * 8, c->stream));
     }
+    tr.lap("small allocations");
     // sample-major copy when it fits (keeps ~2 GiB of head-room)
     if (!(c->flags & UTMOS_F_NO_TRANSPOSE) && v > 0) {
         const size_t bytes = (size_t)S32 * (size_t)c->colPitchW * 4;
+        // keep head-room for the edge lists / staging: the copy must leave at least 1/8 of the device free
+        int rc_alloc = UTMOS_E_NOMEM;
         size_t free_b = 0, total_b = 0;
-        UT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        {
-            cudaMemPool_t pool;
-            unsigned long long reserved = 0, used = 0;
-            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess &&
-                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
-                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
-                free_b += (size_t)(reserved - used);
-            cudaGetLastError();
+        bool roomy = true;
+        if (bytes > (8ull << 30)) {                       // only worth asking the driver for multi-GB copies
+            UT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            size_t parked = 0;
+            for (auto &b : g_big_cache) parked += b.bytes;
+            roomy = free_b + parked > bytes + total_b / 8;
         }
-        const size_t reserve = 2ull << 30;
-        if (free_b > bytes + reserve) {
-            UT_TRY(dev_alloc(c, (void **)&c->d_cols, bytes));
-        } else if (c->flags & UTMOS_F_FORCE_TRANSPOSE) {
-            set_error("finalize: sample-major copy does not fit in device memory");
-            return UTMOS_E_NOMEM;
+        if (roomy) rc_alloc = big_alloc(c, (void **)&c->d_cols, bytes);
+        if (rc_alloc != UTMOS_OK) {
+            c->d_cols = nullptr;
+            if (c->flags & UTMOS_F_FORCE_TRANSPOSE) {
+                set_error("finalize: sample-major copy does not fit in device memory");
+                return UTMOS_E_NOMEM;
+            }
         }
     }
+    tr.lap("sample-major allocation");
     if (c->d_cols) {
         t_begin(c, T_TRANSPOSE, c->stream);
         UT_TRY(launch_transpose(c->stream, c->d_rows, v, c->pitchW, (int)c->S, c->d_cols, c->colPitchW, &c->n_launch));
@@ -679,7 +775,9 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
         UT_TRY(launch_gain_init(c->stream, p, c->d_var_count, &c->n_launch));
     }
     t_end(c, c->stream);
+    tr.lap("launches");
     UT_TRY(sync_all(c));
+    tr.lap("transpose + gains (device)");
     SelState st;
     UT_CUDA(cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost));
     if (st.af_invalid) {
@@ -695,6 +793,7 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
     }
     if (num_vars_out) *num_vars_out = v;
     if (!(c->flags & UTMOS_F_STEP_KERNELS)) UT_TRY(persistent_grid(c->device, &c->grid, &c->block));
+    tr.lap("readback + occupancy");
     c->finalized = true;
     return UTMOS_OK;
 }
@@ -784,8 +883,8 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         auto reserve_lists = [&](int which, unsigned long long entries) -> int {
             const size_t need = (size_t)std::max<unsigned long long>(entries, 1) * estride;
             if (need > c->lists_cap[which]) {
-                dev_free(c, c->d_lists[which], c->lists_cap[which] * 16);
-                UT_TRY(dev_alloc(c, (void **)&c->d_lists[which], need * 16));
+                big_free(c, c->d_lists[which], c->lists_cap[which] * 16);     // stream is idle here (just synchronised)
+                UT_TRY(big_alloc(c, (void **)&c->d_lists[which], need * 16));
                 c->lists_cap[which] = need;
             }
             return UTMOS_OK;
@@ -820,9 +919,9 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 // first compaction: edge lists from the bit matrix
                 UT_TRY(reserve_lists(c->lists_cur, st.live_bits));
                 if ((size_t)st.live_bits + 64 > c->pool_cap) {
-                    dev_free(c, c->d_pool, c->pool_cap * 2);
+                    big_free(c, c->d_pool, c->pool_cap * 2);
                     c->pool_cap = (size_t)st.live_bits + 64;
-                    UT_TRY(dev_alloc(c, (void **)&c->d_pool, c->pool_cap * 2));
+                    UT_TRY(big_alloc(c, (void **)&c->d_pool, c->pool_cap * 2));
                 }
                 q = make_params(c, false);
                 UT_TRY(launch_build_lists(c->stream, q, c->d_lists[c->lists_cur], c->d_list_off[c->lists_cur],
@@ -903,6 +1002,8 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
 {
     if (!c) { set_error("set_option: null context"); return UTMOS_E_ARG; }
     if (option == UTMOS_OPT_REGAIN_ROWS) { c->regain_rows = value; return UTMOS_OK; }
+    if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
+    if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");
     return UTMOS_E_ARG;
 }

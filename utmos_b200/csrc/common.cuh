@@ -84,6 +84,8 @@ struct SelParams {
     int af;                            // 0 count mode, 1 AF flavours
     unsigned long long tail_budget;    // head kernels hand over to the tail kernel once st->live_bits <= this (0 = never)
     unsigned int tail_rows;            // ... and the pick at hand newly covers fewer rows than this
+    int dbg_time;                      // 1: record %globaltimer per pick (profiling; costs latency)
+    int dsmem_gains;                   // 1: cluster kernel keeps the gains in distributed shared memory
     unsigned int regain_rows;          // picks that newly cover >= this many rows trigger a gain recompute (0 = never)
 };
 

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(1024) argmax_step_kernel(SelParams p)
             p.out_idx[i] = b.idx;
             p.out_new[i] = b.cnt;
             p.out_score[i] = b.score;
-            p.out_time[i] = global_timer_ns();
+            if (p.dbg_time) p.out_time[i] = global_timer_ns();
             st->step = i + 1;
             st->tot += b.cnt;
             p.mask[b.idx] = 0;                            // utmos/select.py:100
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(1024, 1) select_persistent_kernel(SelParams p,
             p.out_idx[step] = b.idx;
             p.out_new[step] = b.cnt;
             p.out_score[step] = b.score;
-            p.out_time[step] = global_timer_ns();
+            if (p.dbg_time) p.out_time[step] = global_timer_ns();
             p.mask[b.idx] = 0;                             // utmos/select.py:100
         }
         step += 1;
@@ -549,6 +549,7 @@ struct ClusterCfg {
     int liveW;          // live-mask words per CTA (multiple of 32)
     int off_lo, off_hi, off_w, off_mask, off_live, off_part;   // byte offsets into dynamic smem (cnt at 0)
     int lanes_per_row;  // power of two: lanes that share one row when retiring
+    int gains_l2;       // 1: gains stay in global memory (L2 atomics); 0: distributed shared memory (DSMEM atomics)
 };
 
 
@@ -574,9 +575,15 @@ __device__ __forceinline__ void retire_row_dsmem(const SelParams &p, const Clust
             const int k = k0 + u * 32 + lane;
             const int owner = k / wpc;
             const int base = (k - owner * wpc) << 5;
-            unsigned int *rc = cluster.map_shared_rank(s_cnt, owner) + base;
+            unsigned int *rc;
             unsigned long long *rl = nullptr, *rh = nullptr;
-            if (p.af) { rl = cluster.map_shared_rank(s_lo, owner) + base; rh = cluster.map_shared_rank(s_hi, owner) + base; }
+            if (cfg.gains_l2) {
+                rc = p.gain_cnt + (k << 5);
+                if (p.af) { rl = p.gain_lo + (k << 5); rh = p.gain_hi + (k << 5); }
+            } else {
+                rc = cluster.map_shared_rank(s_cnt, owner) + base;
+                if (p.af) { rl = cluster.map_shared_rank(s_lo, owner) + base; rh = cluster.map_shared_rank(s_hi, owner) + base; }
+            }
             while (w) {
                 const int j = __ffs(w) - 1;
                 w &= w - 1;
@@ -612,9 +619,11 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
     // ---- load this CTA's slice of the state into shared memory
     for (int i = tid; i < cfg.per; i += blockDim.x) {
         const bool ok = i < n_mine;
-        s_cnt[i] = ok ? p.gain_cnt[s0 + i] : 0u;
         s_mask[i] = ok ? p.mask[s0 + i] : (uint8_t)2;
-        if (p.af) { s_lo[i] = ok ? p.gain_lo[s0 + i] : 0ull; s_hi[i] = ok ? p.gain_hi[s0 + i] : 0ull; }
+        if (!cfg.gains_l2) {
+            s_cnt[i] = ok ? p.gain_cnt[s0 + i] : 0u;
+            if (p.af) { s_lo[i] = ok ? p.gain_lo[s0 + i] : 0ull; s_hi[i] = ok ? p.gain_hi[s0 + i] : 0ull; }
+        }
         if (has_w) s_w[i] = ok ? p.weights[s0 + i] : 0.0;
     }
     for (int i = tid; i < cfg.liveW; i += blockDim.x) s_live[i] = w0 + i < p.colPitchW ? p.live[w0 + i] : 0u;
@@ -634,11 +643,17 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
         Best b{-1.0e308, 0x7fffffff, 0u};
         unsigned long long acc = 0;
         for (int i = tid; i < n_mine; i += blockDim.x) {
-            const unsigned int c = s_cnt[i];
+            const unsigned int c = cfg.gains_l2 ? __ldcg(p.gain_cnt + s0 + i) : s_cnt[i];
             acc += c;
             double g = 0.0;
             if (s_mask[i] == 1) {
-                g = p.af ? fixed_to_double(s_lo[i], s_hi[i], p.L, p.scale) : (double)c;
+                if (p.af) {
+                    const unsigned long long lo = cfg.gains_l2 ? __ldcg(p.gain_lo + s0 + i) : s_lo[i];
+                    const unsigned long long hi = cfg.gains_l2 ? __ldcg(p.gain_hi + s0 + i) : s_hi[i];
+                    g = fixed_to_double(lo, hi, p.L, p.scale);
+                } else {
+                    g = (double)c;
+                }
                 if (has_w) g *= s_w[i];
             }
             if (arg_better(g, s0 + i, b.score, b.idx)) { b.score = g; b.idx = s0 + i; b.cnt = c; }
@@ -683,7 +698,7 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
                 p.out_idx[step] = b.idx;
                 p.out_new[step] = b.cnt;
                 p.out_score[step] = b.score;
-                p.out_time[step] = global_timer_ns();
+                if (p.dbg_time) p.out_time[step] = global_timer_ns();
             }
             if (rank == owner) s_mask[b.idx - s0] = 0;    // utmos/select.py:100
         }
@@ -772,11 +787,17 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
                                 uint32_t ww = w4[e];
                                 if (!ww) continue;
                                 const int k = j * 4 + e;
-                                const int owner = k / wpc;
-                                const int sb = (k - owner * wpc) << 5;
-                                unsigned int *rc = cluster.map_shared_rank(s_cnt, owner) + sb;
+                                unsigned int *rc;
                                 unsigned long long *rl = nullptr, *rh = nullptr;
-                                if (p.af) { rl = cluster.map_shared_rank(s_lo, owner) + sb; rh = cluster.map_shared_rank(s_hi, owner) + sb; }
+                                if (cfg.gains_l2) {
+                                    rc = p.gain_cnt + (k << 5);
+                                    if (p.af) { rl = p.gain_lo + (k << 5); rh = p.gain_hi + (k << 5); }
+                                } else {
+                                    const int owner = k / wpc;
+                                    const int sb = (k - owner * wpc) << 5;
+                                    rc = cluster.map_shared_rank(s_cnt, owner) + sb;
+                                    if (p.af) { rl = cluster.map_shared_rank(s_lo, owner) + sb; rh = cluster.map_shared_rank(s_hi, owner) + sb; }
+                                }
                                 while (ww) {
                                     const int jj = __ffs(ww) - 1;
                                     ww &= ww - 1;
@@ -816,9 +837,11 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
     // ---- write the state back so the selection can be resumed / inspected
     cluster.sync();
     for (int i = tid; i < n_mine; i += blockDim.x) {
-        p.gain_cnt[s0 + i] = s_cnt[i];
         p.mask[s0 + i] = s_mask[i];
-        if (p.af) { p.gain_lo[s0 + i] = s_lo[i]; p.gain_hi[s0 + i] = s_hi[i]; }
+        if (!cfg.gains_l2) {
+            p.gain_cnt[s0 + i] = s_cnt[i];
+            if (p.af) { p.gain_lo[s0 + i] = s_lo[i]; p.gain_hi[s0 + i] = s_hi[i]; }
+        }
     }
     for (int i = tid; i < cfg.liveW; i += blockDim.x)
         if (w0 + i < p.colPitchW) p.live[w0 + i] = s_live[i];
@@ -946,6 +969,7 @@ int launch_persistent(cudaStream_t stream, const SelParams &p, int grid, int blo
 // Cluster flavour: returns UTMOS_OK and *cluster_out = 0 when the state does not fit / clusters are unavailable.
 static int cluster_layout(const SelParams &p, int CL, ClusterCfg *cfg, size_t *smem_bytes)
 {
+    cfg->gains_l2 = p.dsmem_gains ? 0 : 1;
     const int per = ((p.S + CL - 1) / CL + 31) / 32 * 32;
     const long long liveW = ((p.colPitchW + CL - 1) / CL + 31) / 32 * 32;
     if (liveW > (1 << 20)) return 0;

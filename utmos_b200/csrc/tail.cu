@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             p.out_idx[step] = b.idx;
             p.out_new[step] = b.cnt;
             p.out_score[step] = best_score;
-            p.out_time[step] = global_timer_ns();
+            if (p.dbg_time) p.out_time[step] = global_timer_ns();
             s_mask[b.idx] = 0;                            // utmos/select.py:100
         }
         step += 1;
