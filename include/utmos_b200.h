@@ -125,6 +125,23 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
                      uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
                      uint8_t *singleton_out);
 
+/* ---- multi-GPU: rows sharded over ranks (one process per GPU), gains replicated ----
+ * Every rank ingests ITS rows into its own context, then:
+ *   utmos_rows            informative rows this rank kept (host all-reduces them -> UTMOS_OPT_GLOBAL_ROWS)
+ *   utmos_finalize        local var_count / gains
+ *   utmos_mgpu_export     allocates the exchange block (per-step delta inboxes + flags) and returns its 64-byte
+ *                         CUDA IPC handle; the host all-gathers the handles (torch.distributed / MPI / files)
+ *   utmos_mgpu_connect    maps every peer's block (NVLink P2P); handles = world x 64 bytes in rank order
+ *   utmos_get_gains0 / utmos_set_gains0   step-0 gains out (local) and in (summed over ranks by the host)
+ * After that utmos_select_begin / utmos_select_steps run the multi-GPU kernel: per step every rank finds the same
+ * winner, retires its own rows into a delta vector, stores the delta straight into the peers' inboxes and
+ * applies the sum.  All ranks must call utmos_select_steps with the same arguments; all return the same rows. */
+int utmos_rows(utmos_ctx *ctx, int64_t *rows_out);
+int utmos_mgpu_export(utmos_ctx *ctx, int rank, int world, uint8_t *handle_out /* 64 bytes */);
+int utmos_mgpu_connect(utmos_ctx *ctx, const uint8_t *handles /* world x 64 bytes */);
+int utmos_get_gains0(utmos_ctx *ctx, uint32_t *cnt_out, uint64_t *lo_out, uint64_t *hi_out);
+int utmos_set_gains0(utmos_ctx *ctx, const uint32_t *cnt, const uint64_t *lo, const uint64_t *hi, int64_t global_rows);
+
 /* ---- introspection (tests, benchmark) ---- */
 
 /* Current per-sample state: gain counts (new_count each sample would get now) and unweighted, unmasked scores. */
@@ -140,6 +157,7 @@ int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
 /* Tunables.  UTMOS_OPT_REGAIN_ROWS: a pick that newly covers >= value rows triggers one streaming recompute of
  * all gains from the sample-major copy instead of per-bit subtraction (0 = never, -1 = default max(4096, V/128)). */
 #define UTMOS_OPT_REGAIN_ROWS 1
+#define UTMOS_OPT_GLOBAL_ROWS 4       /* multi-GPU: informative rows summed over all ranks; set before utmos_finalize */
 #define UTMOS_OPT_STEP_TIMES 2        /* 1: record %globaltimer per pick for utmos_debug_step_times (adds latency) */
 #define UTMOS_OPT_TAIL_ROWS 3         /* hand over to the single-CTA tail kernel once a pick covers fewer rows (default 1536) */
 int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
@@ -147,7 +165,7 @@ int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
 /* info[0]=num_vars, [1]=row pitch bytes, [2]=has sample-major copy, [3]=device bytes in use,
  * [4]=fixed-point scale (AF flavours), [5]=AF values not exactly representable (count), [6]=kernels launched,
  * [7]=selection kernel flavour used: 0 step kernels, 1 grid-wide persistent, 2 one-cluster DSMEM,
- *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2) */
+ *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2), 4 multi-GPU kernel */
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:

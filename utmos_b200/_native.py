@@ -20,7 +20,8 @@ E_NOGPU = -3
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_finalize", "utmos_select_begin",
-           "utmos_select_steps", "utmos_convert_gt", "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings",
+           "utmos_select_steps", "utmos_convert_gt", "utmos_rows", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
+           "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
 
@@ -68,6 +69,11 @@ def lib():
         "utmos_debug_step_times": (i32, [p, i64, i64, p]),
         "utmos_set_option": (i32, [p, i32, i64]),
         "utmos_debug_counters": (i32, [p, p]),
+        "utmos_rows": (i32, [p, ctypes.POINTER(i64)]),
+        "utmos_mgpu_export": (i32, [p, i32, i32, p]),
+        "utmos_mgpu_connect": (i32, [p, p]),
+        "utmos_get_gains0": (i32, [p, p, p, p]),
+        "utmos_set_gains0": (i32, [p, p, p, p, i64]),
         "utmos_timings": (i32, [p, p, i32, i32]),
         "utmos_lzf_decompress": (i64, [p, i64, p, i64]),
         "utmos_lzf_compress": (i64, [p, i64, p, i64]),
@@ -177,6 +183,35 @@ class DeviceMatrix:
         self.num_vars = nv.value
         self.var_count = vc
         return vc
+
+    # -- multi-GPU plumbing (see utmos_b200/distributed.py) ------------------------------------------
+    def rows(self):
+        """Informative rows kept so far (synchronises the ingest stream)."""
+        n = ctypes.c_int64(0)
+        check(lib().utmos_rows(self._ctx, ctypes.byref(n)))
+        return n.value
+
+    def mgpu_export(self, rank, world):
+        handle = np.zeros(64, dtype=np.uint8)
+        check(lib().utmos_mgpu_export(self._ctx, rank, world, _ptr(handle)))
+        return handle
+
+    def mgpu_connect(self, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        check(lib().utmos_mgpu_connect(self._ctx, _ptr(handles)))
+
+    def get_gains0(self):
+        cnt = np.zeros(self.n_samples, dtype=np.uint32)
+        lo = np.zeros(self.n_samples, dtype=np.uint64)
+        hi = np.zeros(self.n_samples, dtype=np.uint64)
+        check(lib().utmos_get_gains0(self._ctx, _ptr(cnt), _ptr(lo), _ptr(hi)))
+        return cnt, lo, hi
+
+    def set_gains0(self, cnt, lo, hi, global_rows):
+        cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+        lo = np.ascontiguousarray(lo, dtype=np.uint64)
+        hi = np.ascontiguousarray(hi, dtype=np.uint64)
+        check(lib().utmos_set_gains0(self._ctx, _ptr(cnt), _ptr(lo), _ptr(hi), int(global_rows)))
 
     # -- what the reference looks at ---------------------------------------------------------------
     @property

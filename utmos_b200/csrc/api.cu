@@ -114,6 +114,15 @@ struct utmos_ctx {
     unsigned long long lists_total = 0;   // entries in the current lists (live bits when they were built)
     bool lists_valid = false;
     int dbg_time = 0;
+    // multi-GPU (rows sharded over ranks)
+    int mg_rank = 0, mg_world = 1;
+    long long global_rows = -1;        // informative rows summed over the ranks (set before finalize)
+    void *mg_block = nullptr;          // IPC-exported exchange block: inboxes + flags
+    size_t mg_bytes = 0;
+    void *mg_peer[kMaxRanks] = {nullptr};
+    unsigned int *d_delta_cnt = nullptr;
+    unsigned long long *d_delta_lo = nullptr, *d_delta_hi = nullptr;
+    int mg_grid = 0, mg_block_threads = 0;
     unsigned int tail_rows = 1536;        // hand over to the single-CTA tail once picks cover fewer rows than this
     unsigned long long tail_budget = 0;   // handed to the head kernels while the tail flavour waits for sparsity
     unsigned long long total_bits = 0;    // set bits of the scoring rows at step 0
@@ -443,6 +452,12 @@ void free_select_state(utmos_ctx *c)
         c->lists_cap[i] = 0;
     }
     dev_free(c, c->d_cursor, S * 4);
+    dev_free(c, c->d_delta_cnt, S * 4);
+    dev_free(c, c->d_delta_lo, S * 8);
+    dev_free(c, c->d_delta_hi, S * 8);
+    for (int i = 0; i < kMaxRanks; ++i)
+        if (c->mg_peer[i]) { cudaIpcCloseMemHandle(c->mg_peer[i]); c->mg_peer[i] = nullptr; }
+    if (c->mg_block) { cudaFree(c->mg_block); c->mg_block = nullptr; }
     dev_free(c, c->d_pool_cursor, 16);
     big_free(c, c->d_pool, c->pool_cap * 2);
     c->pool_cap = 0;
@@ -513,6 +528,22 @@ int build_graph(utmos_ctx *c)
     cudaGraphDestroy(graph);
     UT_CUDA(e);
     return UTMOS_OK;
+}
+
+struct MgLayout {
+    size_t off_cnt, off_lo, off_hi, off_flags, bytes;
+};
+MgLayout mg_layout(size_t S, int world, bool af)
+{
+    MgLayout l;
+    size_t off = 0;
+    auto take = [&](size_t b) { const size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
+    l.off_cnt = take(2 * (size_t)world * S * 4);
+    l.off_lo = take(af ? 2 * (size_t)world * S * 8 : 0);
+    l.off_hi = take(af ? 2 * (size_t)world * S * 8 : 0);
+    l.off_flags = take((size_t)kMaxRanks * 8);
+    l.bytes = off;
+    return l;
 }
 
 }  // namespace
@@ -697,8 +728,9 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
     c->colPitchW = std::max(8ll, ((v + 31) / 32 + 7) / 8 * 8);
     const bool af = c->af_mode != UTMOS_AF_NONE;
     // limb width: sums of up to V limbs must stay below 2^63 (see oracle_fixed_scale)
+    const long long v_all = c->global_rows >= 0 ? std::max(c->global_rows, v) : v;   // every rank must use the same scale
     int lg = 0;
-    while ((1ll << lg) < v + 1) ++lg;
+    while ((1ll << lg) < v_all + 1) ++lg;
     c->L = std::min(48, 63 - lg);
     c->scale = 2 * c->L - 1;
 
@@ -819,9 +851,12 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
         UT_CUDA(cudaMemcpyAsync(c->d_gain_lo, c->d_gain0_lo, S * 8, cudaMemcpyDeviceToDevice, c->stream));
         UT_CUDA(cudaMemcpyAsync(c->d_gain_hi, c->d_gain0_hi, S * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
-    SelState st;
+    SelState st, prev;
+    UT_CUDA(cudaMemcpyAsync(&prev, c->d_state, sizeof(prev), cudaMemcpyDeviceToHost, c->stream));
+    UT_CUDA(cudaStreamSynchronize(c->stream));
     memset(&st, 0, sizeof(st));
     st.winner = -1;
+    st.mgpu_seq = prev.mgpu_seq;       // exchange sequence numbers stay monotonic over the life of the context
     UT_CUDA(cudaMemcpyAsync(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
     {
         const SelParams p0 = make_params(c, false);
@@ -860,7 +895,35 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
     UT_CUDA(cudaMemcpy(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
     const SelParams p = make_params(c, false);
     t_begin(c, T_SELECT, c->stream);
-    if (c->flags & UTMOS_F_STEP_KERNELS) {
+    if (c->mg_world > 1) {
+        const bool af = c->af_mode != UTMOS_AF_NONE;
+        const MgLayout l = mg_layout((size_t)c->S, c->mg_world, af);
+        MgpuParams m;
+        memset(&m, 0, sizeof(m));
+        m.rank = c->mg_rank;
+        m.world = c->mg_world;
+        m.global_V = c->global_rows >= 0 ? c->global_rows : c->V;
+        m.seq0 = st.mgpu_seq;
+        m.delta_cnt = c->d_delta_cnt;
+        m.delta_lo = c->d_delta_lo;
+        m.delta_hi = c->d_delta_hi;
+        char *mine = (char *)c->mg_block;
+        m.inbox_cnt = (unsigned int *)(mine + l.off_cnt);
+        m.inbox_lo = (unsigned long long *)(mine + l.off_lo);
+        m.inbox_hi = (unsigned long long *)(mine + l.off_hi);
+        m.flags = (unsigned long long *)(mine + l.off_flags);
+        for (int q = 0; q < c->mg_world; ++q) {
+            if (q == c->mg_rank) continue;
+            if (!c->mg_peer[q]) { set_error("select_steps: multi-GPU peers are not connected"); return UTMOS_E_ARG; }
+            char *pb = (char *)c->mg_peer[q];
+            m.peer_inbox_cnt[q] = (unsigned int *)(pb + l.off_cnt);
+            m.peer_inbox_lo[q] = (unsigned long long *)(pb + l.off_lo);
+            m.peer_inbox_hi[q] = (unsigned long long *)(pb + l.off_hi);
+            m.peer_flags[q] = (unsigned long long *)(pb + l.off_flags);
+        }
+        UT_TRY(launch_mgpu(c->stream, p, m, c->mg_grid, c->mg_block_threads, c->d_bar, c->d_partials, &c->n_launch));
+        c->flavour_used = 4;
+    } else if (c->flags & UTMOS_F_STEP_KERNELS) {
         while (true) {
             UT_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
             c->n_launch += 2 * kGraphSteps;
@@ -982,6 +1045,92 @@ int utmos_debug_gains(utmos_ctx *c, int64_t *count_out, double *score_out)
     return UTMOS_OK;
 }
 
+
+// ---- multi-GPU plumbing ------------------------------------------------------------------------------------
+
+int utmos_rows(utmos_ctx *c, int64_t *rows_out)
+{
+    if (!c || !rows_out) { set_error("rows: null argument"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    if (c->finalized) { *rows_out = c->V; return UTMOS_OK; }
+    UT_TRY(sync_all(c));
+    long long v = 0;
+    UT_CUDA(cudaMemcpy(&v, c->d_nrows, 8, cudaMemcpyDeviceToHost));
+    *rows_out = v;
+    return UTMOS_OK;
+}
+
+int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
+{
+    if (!c || !handle_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { set_error("mgpu_export: bad arguments"); return UTMOS_E_ARG; }
+    if (!c->finalized) { set_error("mgpu_export before finalize"); return UTMOS_E_ARG; }
+    if (c->mg_block) { set_error("mgpu_export called twice"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    const bool af = c->af_mode != UTMOS_AF_NONE;
+    const size_t S = (size_t)c->S;
+    const MgLayout l = mg_layout(S, world, af);
+    UT_CUDA(cudaMalloc(&c->mg_block, l.bytes));              // plain cudaMalloc: IPC handles need it
+    UT_CUDA(cudaMemset(c->mg_block, 0, l.bytes));
+    c->mg_bytes = l.bytes;
+    c->mg_rank = rank;
+    c->mg_world = world;
+    UT_TRY(dev_alloc(c, (void **)&c->d_delta_cnt, S * 4));
+    UT_CUDA(cudaMemsetAsync(c->d_delta_cnt, 0, S * 4, c->stream));
+    if (af) {
+        UT_TRY(dev_alloc(c, (void **)&c->d_delta_lo, S * 8));
+        UT_TRY(dev_alloc(c, (void **)&c->d_delta_hi, S * 8));
+        UT_CUDA(cudaMemsetAsync(c->d_delta_lo, 0, S * 8, c->stream));
+        UT_CUDA(cudaMemsetAsync(c->d_delta_hi, 0, S * 8, c->stream));
+    }
+    UT_CUDA(cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t h;
+    UT_CUDA(cudaIpcGetMemHandle(&h, c->mg_block));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, 64);
+    UT_TRY(mgpu_grid(c->device, &c->mg_grid, &c->mg_block_threads));
+    return UTMOS_OK;
+}
+
+int utmos_mgpu_connect(utmos_ctx *c, const uint8_t *handles)
+{
+    if (!c || !handles || !c->mg_block) { set_error("mgpu_connect: export first"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    for (int q = 0; q < c->mg_world; ++q) {
+        if (q == c->mg_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)q * 64, 64);
+        UT_CUDA(cudaIpcOpenMemHandle(&c->mg_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    return UTMOS_OK;
+}
+
+int utmos_get_gains0(utmos_ctx *c, uint32_t *cnt_out, uint64_t *lo_out, uint64_t *hi_out)
+{
+    if (!c || !c->finalized || !cnt_out) { set_error("get_gains0: bad arguments"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    const size_t S = (size_t)c->S;
+    UT_CUDA(cudaMemcpy(cnt_out, c->d_gain0_cnt, S * 4, cudaMemcpyDeviceToHost));
+    if (c->af_mode != UTMOS_AF_NONE && lo_out && hi_out) {
+        UT_CUDA(cudaMemcpy(lo_out, c->d_gain0_lo, S * 8, cudaMemcpyDeviceToHost));
+        UT_CUDA(cudaMemcpy(hi_out, c->d_gain0_hi, S * 8, cudaMemcpyDeviceToHost));
+    }
+    return UTMOS_OK;
+}
+
+int utmos_set_gains0(utmos_ctx *c, const uint32_t *cnt, const uint64_t *lo, const uint64_t *hi, int64_t global_rows)
+{
+    if (!c || !c->finalized || !cnt) { set_error("set_gains0: bad arguments"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    const size_t S = (size_t)c->S;
+    UT_CUDA(cudaMemcpy(c->d_gain0_cnt, cnt, S * 4, cudaMemcpyHostToDevice));
+    if (c->af_mode != UTMOS_AF_NONE && lo && hi) {
+        UT_CUDA(cudaMemcpy(c->d_gain0_lo, lo, S * 8, cudaMemcpyHostToDevice));
+        UT_CUDA(cudaMemcpy(c->d_gain0_hi, hi, S * 8, cudaMemcpyHostToDevice));
+    }
+    if (global_rows >= 0) c->global_rows = global_rows;
+    return UTMOS_OK;
+}
+
 int utmos_debug_step_times(utmos_ctx *c, int64_t first, int64_t n, int64_t *ns_out)
 {
     if (!c || !c->selecting || !ns_out || first < 0 || n < 0 || first + n > c->S) { set_error("debug_step_times: bad arguments"); return UTMOS_E_ARG; }
@@ -1002,6 +1151,7 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
 {
     if (!c) { set_error("set_option: null context"); return UTMOS_E_ARG; }
     if (option == UTMOS_OPT_REGAIN_ROWS) { c->regain_rows = value; return UTMOS_OK; }
+    if (option == UTMOS_OPT_GLOBAL_ROWS) { c->global_rows = value; return UTMOS_OK; }
     if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");

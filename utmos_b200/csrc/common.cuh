@@ -43,6 +43,7 @@ struct SelState {
     unsigned int want_tail;    // head kernel returned because the tail kernel should take over
     unsigned int recompact;    // tail kernel returned because at most half of its list entries are still live
     unsigned int regain;       // 1 = gains are stale: the pick retired too many rows to subtract, recompute them
+    unsigned long long mgpu_seq;    // multi-GPU exchange sequence number (monotonic over the selection)
     unsigned long long live_bits;   // sum of all gains = set bits in rows not yet covered (sum_gains_kernel)
 };
 
@@ -87,6 +88,23 @@ struct SelParams {
     int dbg_time;                      // 1: record %globaltimer per pick (profiling; costs latency)
     int dsmem_gains;                   // 1: cluster kernel keeps the gains in distributed shared memory
     unsigned int regain_rows;          // picks that newly cover >= this many rows trigger a gain recompute (0 = never)
+};
+
+// Multi-GPU exchange (variants sharded by rows, gains replicated on every rank).  All pointers are valid on THIS
+// device; peer_* point into the other ranks' memory (CUDA IPC, NVLink P2P).
+constexpr int kMaxRanks = 8;
+struct MgpuParams {
+    int rank, world;
+    long long global_V;                       // num_vars summed over the ranks (tot_captured stop rule)
+    unsigned long long seq0;                  // exchange sequence number before the first step of this launch
+    unsigned int *delta_cnt;                  // [S] this rank's decrements of the current step (two's complement)
+    unsigned long long *delta_lo, *delta_hi;  // [S] AF limbs
+    unsigned int *inbox_cnt;                  // [2][world][S] written by the peers (double buffered by step parity)
+    unsigned long long *inbox_lo, *inbox_hi;
+    unsigned long long *flags;                // [world] last sequence number each peer has published here
+    unsigned int *peer_inbox_cnt[kMaxRanks];
+    unsigned long long *peer_inbox_lo[kMaxRanks], *peer_inbox_hi[kMaxRanks];
+    unsigned long long *peer_flags[kMaxRanks];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +223,9 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
                         int *n_launch);
 int tail_plan(const SelParams &p, int *ok_out);
 int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, int *n_launch);
+int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
+                unsigned int *bar_counter, ArgPartial *partials, int *n_launch);
+int mgpu_grid(int device, int *grid_out, int *block_out);
 int cluster_plan(const SelParams &p, int *cluster_out);
 int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch);
 

@@ -856,6 +856,155 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
 }
 
 
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU flavour: one persistent cooperative kernel per GPU.  Rows are sharded over the ranks, the
+// gains are replicated.  Every step each rank (A) finds the same winner from its replica, (B) retires
+// the rows of ITS shard the winner newly covers into a local delta vector, (C) stores that delta
+// straight into every peer's inbox over NVLink (P2P stores on IPC-mapped pointers) and publishes a
+// sequence number, (D) waits for the peers' sequence numbers and adds all deltas to its replica.
+// Integer (count) and fixed-point (AF limb) deltas make the result independent of the rank count.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuParams m, unsigned int *bar_counter,
+                                                              ArgPartial *partials)
+{
+    __shared__ Best s_red[32];
+    __shared__ int s_flag;
+    __shared__ unsigned int s_epoch;
+    SelState *st = p.st;
+    if (threadIdx.x == 0) s_epoch = 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned int nblocks = gridDim.x;
+    long long step = st->step, tot = st->tot;
+    const long long limit = st->limit;
+    int stop = st->stop;
+    unsigned long long seq = m.seq0;
+    const int per = (p.S + (int)nblocks - 1) / (int)nblocks;
+    const int my_begin = min(p.S, (int)blockIdx.x * per), my_end = min(p.S, my_begin + per);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)nblocks * blockDim.x;
+    const long long warp0 = gtid >> 5, nwarps = nthreads >> 5;
+    const long long nchunks = (p.colPitchW + 31) / 32;
+    // the cover phase subtracts into the delta vectors instead of the gains
+    SelParams pd = p;
+    pd.gain_cnt = m.delta_cnt;
+    pd.gain_lo = m.delta_lo;
+    pd.gain_hi = m.delta_hi;
+    __syncthreads();
+
+    while (stop == 0 && step < limit) {
+        // ---- A: replicated argmax (identical on every rank)
+        Best b = block_best(scan_best(p, my_begin, my_end), s_red);
+        if (threadIdx.x == 0) {
+            ArgPartial a;
+            a.score = b.score; a.idx = b.idx; a.cnt = b.cnt; a.sum = 0;
+            partials[blockIdx.x] = a;
+        }
+        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        Best t{-1.0e308, 0x7fffffff, 0u};
+        for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+            Best o;
+            o.score = __ldcg(&partials[i].score);
+            o.idx = __ldcg(&partials[i].idx);
+            o.cnt = __ldcg(&partials[i].cnt);
+            t = best_of(t, o);
+        }
+        b = block_best(t, s_red);
+        if (p.S == 0 || b.score == 0.0) {                  // utmos/select.py:51-52
+            stop = UTMOS_STOP_ZERO;
+            break;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            p.out_idx[step] = b.idx;
+            p.out_new[step] = b.cnt;
+            p.out_score[step] = b.score;
+            p.mask[b.idx] = 0;                             // utmos/select.py:100
+        }
+        step += 1;
+        tot += b.cnt;
+        if (tot >= m.global_V) {                           // utmos/select.py:110-112
+            stop = UTMOS_STOP_ALL;
+            break;
+        }
+        // ---- B: this rank's newly covered rows -> local delta
+        if (p.V > 0)
+            for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(pd, b.idx, c, lane, true);
+        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        // ---- C: push the delta into every peer's inbox (NVLink P2P stores), then publish the sequence number
+        seq += 1;
+        const size_t slot = ((size_t)(seq & 1) * m.world + m.rank) * (size_t)p.S;
+        for (int q = 0; q < m.world; ++q) {
+            if (q == m.rank) continue;
+            unsigned int *dst = m.peer_inbox_cnt[q] + slot;
+            for (long long i = gtid; i < p.S; i += nthreads) dst[i] = __ldcg(m.delta_cnt + i);
+            if (p.af) {
+                unsigned long long *dl = m.peer_inbox_lo[q] + slot, *dh = m.peer_inbox_hi[q] + slot;
+                for (long long i = gtid; i < p.S; i += nthreads) { dl[i] = __ldcg(m.delta_lo + i); dh[i] = __ldcg(m.delta_hi + i); }
+            }
+        }
+        __threadfence_system();
+        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (blockIdx.x == 0 && threadIdx.x < m.world && (int)threadIdx.x != m.rank)
+            st_release_sys_u64(m.peer_flags[threadIdx.x] + m.rank, seq);
+        // ---- D: wait for every peer's delta of this step, apply the sum to the replica, clear the local delta
+        if (threadIdx.x == 0) {
+            int bad = 0;
+            for (int q = 0; q < m.world && !bad; ++q) {
+                if (q == m.rank) continue;
+                long long spins = 0;
+                while (ld_acquire_sys_u64(m.flags + q) < seq) {
+                    if (++spins > (kSpinLimit >> 3)) { atomicExch(&st->abort_flag, 2u); bad = 1; break; }
+                    if ((spins & 0xfff) == 0 && ld_acquire_u32(&st->abort_flag)) { bad = 1; break; }
+                }
+            }
+            s_flag = bad;
+        }
+        __syncthreads();
+        if (s_flag) return;
+        const size_t base = (size_t)(seq & 1) * m.world * (size_t)p.S;
+        for (long long i = gtid; i < p.S; i += nthreads) {
+            unsigned int d = __ldcg(m.delta_cnt + i);
+            unsigned long long dl = 0, dh = 0;
+            if (p.af) { dl = __ldcg(m.delta_lo + i); dh = __ldcg(m.delta_hi + i); }
+            for (int q = 0; q < m.world; ++q) {
+                if (q == m.rank) continue;
+                const size_t o = base + (size_t)q * p.S + i;
+                d += __ldcv(m.inbox_cnt + o);
+                if (p.af) { dl += __ldcv(m.inbox_lo + o); dh += __ldcv(m.inbox_hi + o); }
+            }
+            if (d) p.gain_cnt[i] += d;
+            m.delta_cnt[i] = 0;
+            if (p.af) {
+                if (dl) p.gain_lo[i] += dl;
+                if (dh) p.gain_hi[i] += dh;
+                m.delta_lo[i] = 0;
+                m.delta_hi[i] = 0;
+            }
+        }
+        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->step = step;
+        st->tot = tot;
+        st->stop = stop;
+        st->winner = -1;
+        st->regain = 0;
+        st->mgpu_seq = seq;
+    }
+}
+
 __global__ void debug_scores_kernel(SelParams p, double *score_out)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1054,6 +1203,32 @@ int launch_regain(cudaStream_t stream, const SelParams &p, int *n_launch)
     return UTMOS_OK;
 }
 
+
+
+int mgpu_grid(int device, int *grid_out, int *block_out)
+{
+    int n_sms = 0, per_sm = 0, coop = 0;
+    UT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+    UT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) { set_error("device does not support cooperative launch"); return UTMOS_E_NOGPU; }
+    UT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_mgpu_kernel, 1024, 0));
+    if (per_sm < 1) { set_error("multi-GPU kernel does not fit on an SM"); return UTMOS_E_CUDA; }
+    *grid_out = n_sms < 64 ? n_sms : 64;      // few CTAs keep the grid barrier cheap; the loop is latency bound
+    *block_out = 1024;
+    return UTMOS_OK;
+}
+
+int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
+                unsigned int *bar_counter, ArgPartial *partials, int *n_launch)
+{
+    UT_CUDA(cudaMemsetAsync(bar_counter, 0, sizeof(unsigned int), stream));
+    SelParams pp = p;
+    MgpuParams mm = m;
+    void *args[] = {&pp, &mm, &bar_counter, &partials};
+    UT_CUDA(cudaLaunchCooperativeKernel((void *)select_mgpu_kernel, dim3(grid), dim3(block), args, 0, stream));
+    *n_launch += 1;
+    return UTMOS_OK;
+}
 
 int launch_debug_scores(cudaStream_t stream, const SelParams &p, double *score_out, int *n_launch)
 {
