@@ -98,6 +98,26 @@ def test_cli_answer_keys(key, argv, tmp_path, monkeypatch, flags):
     assert out.read_text() == H.answer_key(key)
 
 
+def test_cli_lowmem_creates_reusable_hdf5(tmp_path):
+    """utmos_ssshtests.sh:197-235: `--lowmem NEW.hdf5 inputs` answers like the in-memory run, and the file it
+    leaves behind can be selected from again (bool and float32 --af flavours)."""
+    new = str(tmp_path / "made.hdf5")
+    out = tmp_path / "r1.txt"
+    usel.select_main(["--maxmem", "0", "--lowmem", new, H.fixture("chunk2.jl"), "-o", str(out)])
+    assert out.read_text() == H.answer_key("select_first.txt")
+    out2 = tmp_path / "r2.txt"
+    usel.select_main(["--lowmem", new, "-o", str(out2)])
+    assert out2.read_text() == H.answer_key("select_first.txt")
+    new_af = str(tmp_path / "made.af.hdf5")
+    out3 = tmp_path / "r3.txt"
+    usel.select_main(["--maxmem", "0", "-c", "20", "--af", "--lowmem", new_af, H.fixture("chunk0.jl"),
+                      H.fixture("chunk1.jl"), "-o", str(out3)])
+    assert out3.read_text() == H.answer_key("select_af_h5.txt")
+    out4 = tmp_path / "r4.txt"
+    usel.select_main(["--af", "-c", "20", new_af, "-o", str(out4)])
+    assert out4.read_text() == H.answer_key("select_af_h5.txt")
+
+
 def test_cli_bool_hdf5_with_af_exits(monkeypatch):
     """utmos/select.py:429-431"""
     with pytest.raises(SystemExit) as err:

@@ -156,3 +156,35 @@ def test_synth_mirror_is_deterministic_and_informative():
     assert bits.any(axis=1).all()
     assert not np.unpackbits(gt1, axis=1)[:, 333:].any()
     assert ((af1 > 0) & (af1 <= 1)).all()
+
+
+def test_h5writer_roundtrip_bool_float_and_multilevel_btree(tmp_path):
+    parts = H.load_jl_parts(["chunk0.jl", "chunk1.jl"])
+    samples = np.asarray(parts[0]["samples"]).astype("S")
+    for float_data in (False, True):
+        path = str(tmp_path / f"w{int(float_data)}.hdf5")
+        writer = h5lite.H5Writer(path, samples, float_data=float_data)
+        for part in parts:
+            writer.append_packed(part["GT"], part["AF"])
+        matrix, var_count = orc.load_parts(parts, 2504, float32_af=float_data)
+        writer.close(var_count)
+        with h5lite.H5File(path) as h5:
+            assert h5["data"].chunks == (99, 2504)                      # utmos/select.py:205
+            assert h5["data"].dtype == (np.float32 if float_data else np.dtype(bool))
+            assert np.array_equal(h5["data"].read(), matrix)
+            assert np.array_equal(h5["var_count"].read(), var_count)
+            assert list(h5["samples"].read()) == list(samples)
+    # > 64 chunks forces a two-level chunk B-tree; ragged last chunk
+    n_samples = 60000
+    path = str(tmp_path / "big.hdf5")
+    writer = h5lite.H5Writer(path, synth.sample_names(n_samples).astype("S"))
+    rng = np.random.default_rng(0)
+    blocks = [rng.random((n, n_samples)) < 0.01 for n in (50, 1, 133, 260, 7)]
+    for block in blocks:
+        writer.append_dense(block)
+    full = np.concatenate(blocks)
+    writer.close(full.sum(axis=0))
+    with h5lite.H5File(path) as h5:
+        assert h5["data"].chunks == (4, n_samples) and h5["data"].shape == full.shape
+        assert len(h5["data"]._chunk_index()) == (full.shape[0] + 3) // 4 > 64
+        assert np.array_equal(h5["data"].read(), full)

@@ -304,10 +304,234 @@ def _parse_filters(p):
 
 
 # ------------------------------------------------------------------------------------------------
-# writer (placeholder until the dialect writer lands)
+# writer: the same dialect (superblock v0, v1 headers, symbol-table root, chunked + LZF, v1 chunk B-trees)
 # ------------------------------------------------------------------------------------------------
+_BOOL_TYPE = bytes.fromhex("180200000100000010080000010000000000080046414c5345000000545255450000000000010000")
+_F32_TYPE = bytes.fromhex("11201f000400000000002000170800177f00000000000000")
+_I64_TYPE = bytes.fromhex("10080000080000000000400000000000")
+_FILL = bytes.fromhex("0203000100000000")
+_GROUP_LEAF_K, _GROUP_INTERNAL_K, _CHUNK_K = 4, 16, 32
+
+
+def _pad8(b):
+    return b + b"\x00" * (-len(b) % 8)
+
+
+def _message(mtype, payload, flags=0):
+    payload = _pad8(payload)
+    return struct.pack("<HHB3x", mtype, len(payload), flags) + payload
+
+
+class _ChunkedDataset:
+    """Bookkeeping of one chunked dataset while the file is being written."""
+
+    def __init__(self, writer, dtype_msg, itemsize, row_shape, chunk_rows, unlimited):
+        self.w = writer
+        self.dtype_msg, self.itemsize = dtype_msg, itemsize
+        self.row_shape = tuple(row_shape)            # trailing dims (empty for 1-D)
+        self.chunk_rows = int(chunk_rows)
+        self.unlimited = unlimited
+        self.rows = 0
+        self.chunks = []                             # (first_row, address, nbytes, filter_mask)
+        self.pending = None
+
+    @property
+    def chunk_shape(self):
+        return (self.chunk_rows,) + self.row_shape
+
+    @property
+    def chunk_nbytes(self):
+        return int(np.prod(self.chunk_shape)) * self.itemsize
+
+    def append(self, block):
+        """block: ndarray [n, *row_shape] of the dataset dtype."""
+        if block.shape[0] == 0:
+            return
+        if self.pending is not None and self.pending.shape[0]:
+            block = np.concatenate([self.pending, block])
+        n_full = block.shape[0] // self.chunk_rows
+        for i in range(n_full):
+            self._emit(block[i * self.chunk_rows:(i + 1) * self.chunk_rows])
+        self.pending = np.ascontiguousarray(block[n_full * self.chunk_rows:])
+
+    def _emit(self, rows):
+        raw = np.ascontiguousarray(rows).tobytes()
+        comp = _native.lzf_compress(raw)
+        mask = 0
+        if comp is None:                              # did not shrink: stored raw, filter skipped (bit 0)
+            comp, mask = raw, 1
+        addr = self.w._write(comp)
+        self.chunks.append((self.rows, addr, len(comp), mask))
+        self.rows += rows.shape[0]
+
+    def finish(self):
+        if self.pending is not None and self.pending.shape[0]:
+            tail = self.pending
+            full = np.zeros(self.chunk_shape, dtype=tail.dtype)
+            full[:tail.shape[0]] = tail
+            n = tail.shape[0]
+            self._emit(full)
+            self.rows += n - self.chunk_rows          # the padding rows are not part of the dataset
+        self.pending = None
+
+    # -- v1 B-tree of chunks ------------------------------------------------------------------
+    def _key(self, nbytes, mask, first_row):
+        offs = (first_row,) + (0,) * len(self.row_shape) + (0,)
+        return struct.pack(f"<II{len(offs)}Q", nbytes, mask, *offs)
+
+    def _end_key(self, first_row):
+        offs = (first_row,) + self.row_shape + (self.itemsize,)
+        return struct.pack(f"<II{len(offs)}Q", 0, 0, *offs)
+
+    def write_btree(self):
+        """Returns the root node address (UNDEF when there are no chunks)."""
+        if not self.chunks:
+            return UNDEF
+        rank1 = len(self.row_shape) + 2
+        key_size = 8 + 8 * rank1
+        node_size = 24 + 2 * _CHUNK_K * (key_size + 8) + key_size
+        cap = 2 * _CHUNK_K
+        # level 0: (first key bytes, end row, child address) per chunk
+        entries = [(self._key(nb, mask, first), first + self.chunk_rows, addr) for first, addr, nb, mask in self.chunks]
+        level = 0
+        while True:
+            groups = [entries[i:i + cap] for i in range(0, len(entries), cap)]
+            addrs = [self.w._reserve(node_size) for _ in groups]
+            nxt = []
+            for gi, grp in enumerate(groups):
+                left = addrs[gi - 1] if gi > 0 else UNDEF
+                right = addrs[gi + 1] if gi + 1 < len(groups) else UNDEF
+                body = b"TREE" + struct.pack("<BBHQQ", 1, level, len(grp), left, right)
+                for key, _end, child in grp:
+                    body += key + struct.pack("<Q", child)
+                body += self._end_key(grp[-1][1])
+                self.w._write_at(addrs[gi], body.ljust(node_size, b"\x00"))
+                nxt.append((grp[0][0], grp[-1][1], addrs[gi]))
+            if len(nxt) == 1:
+                return nxt[0][2]
+            entries = nxt
+            level += 1
+
+    def header_messages(self, btree_addr):
+        rank = 1 + len(self.row_shape)
+        dims = (self.rows,) + self.row_shape
+        maxd = ((UNDEF if self.unlimited else self.rows),) + self.row_shape
+        space = struct.pack("<BBB5x", 1, rank, 1) + struct.pack(f"<{rank}Q", *dims) + struct.pack(f"<{rank}Q", *maxd)
+        filt = (struct.pack("<BB6x", 1, 1) + struct.pack("<HHHH", LZF_FILTER, 8, 1, 3) + b"lzf".ljust(8, b"\x00") +
+                struct.pack("<III", 4, 261, self.chunk_nbytes) + b"\x00" * 4)
+        cdims = self.chunk_shape + (self.itemsize,)
+        layout = struct.pack("<BBB", 3, 2, rank + 1) + struct.pack("<Q", btree_addr) + struct.pack(f"<{rank + 1}I", *cdims)
+        return [_message(0x01, space), _message(0x03, self.dtype_msg, 1), _message(0x05, _FILL, 1),
+                _message(0x0B, filt, 1), _message(0x08, layout)]
+
+
 class H5Writer:
-    """Creates the ``--lowmem NEW.hdf5`` file (utmos/select.py:198-238)."""
+    """Creates the ``--lowmem NEW.hdf5`` file of utmos/select.py:198-238: datasets ``samples`` (fixed strings),
+    ``data`` (bool, or float32 ``GT*AF``; chunks ``(max(1, int(1e6/4/S)), S)``, LZF) and ``var_count`` (int64)."""
 
     def __init__(self, path, samples, float_data=False):
-        raise NotImplementedError("writing --lowmem hdf5 files is not implemented yet; load the inputs directly")
+        self.path = path
+        self.samples = np.asarray(samples).astype("S")
+        self.n_samples = len(self.samples)
+        self.float_data = bool(float_data)
+        self._fh = open(path, "wb")
+        self._pos = 0
+        self._write(b"\x00" * 96)                                  # superblock + root entry, patched in close()
+        c_rows = max(1, int(1e6 / 4 / self.n_samples))             # utmos/select.py:205
+        if self.float_data:
+            self.data = _ChunkedDataset(self, _F32_TYPE, 4, (self.n_samples,), c_rows, True)
+        else:
+            self.data = _ChunkedDataset(self, _BOOL_TYPE, 1, (self.n_samples,), c_rows, True)
+
+    # -- raw file access ------------------------------------------------------------------------
+    def _write(self, payload):
+        addr = self._pos
+        self._fh.seek(addr)
+        self._fh.write(payload)
+        self._pos += len(payload)
+        return addr
+
+    def _reserve(self, nbytes):
+        self._pos = (self._pos + 7) // 8 * 8
+        addr = self._pos
+        self._pos += nbytes
+        return addr
+
+    def _write_at(self, addr, payload):
+        self._fh.seek(addr)
+        self._fh.write(payload)
+
+    # -- rows -------------------------------------------------------------------------------------
+    def append_packed(self, gt_packed, af):
+        """One .jl part: informative rows only (utmos/select.py:275-280), dense bool or float32 GT*AF (:219-223)."""
+        gt_packed = np.asarray(gt_packed)
+        af = None if af is None else np.asarray(af, dtype=np.float64).reshape(-1)
+        step = 8192
+        for r0 in range(0, gt_packed.shape[0], step):
+            dense = np.unpackbits(gt_packed[r0:r0 + step], axis=1, count=self.n_samples).astype(bool)
+            keep = dense.any(axis=1)
+            dense = dense[keep]
+            if self.float_data:
+                dense = (dense * af[r0:r0 + step][keep].reshape(-1, 1)).astype(np.float32)
+            self.data.append(dense)
+
+    def append_dense(self, block):
+        self.data.append(np.asarray(block, dtype=np.float32 if self.float_data else bool))
+
+    # -- finish -----------------------------------------------------------------------------------
+    def _write_header(self, messages):
+        body = b"".join(messages)
+        head = struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body))
+        addr = self._reserve(16 + len(body))
+        self._write_at(addr, head + body)
+        return addr
+
+    def close(self, var_count):
+        self.data.finish()
+        width = max(1, self.samples.dtype.itemsize)
+        str_type = struct.pack("<BBBBI", 0x13, 0x01, 0, 0, width)
+        ds_samples = _ChunkedDataset(self, str_type, width, (), max(1, self.n_samples), True)
+        ds_samples.append(self.samples.astype(f"S{width}"))
+        ds_samples.finish()
+        ds_vc = _ChunkedDataset(self, _I64_TYPE, 8, (), max(1, self.n_samples), False)
+        ds_vc.append(np.asarray(var_count, dtype="<i8"))
+        ds_vc.finish()
+        self._pos = (self._pos + 7) // 8 * 8
+        headers = {}
+        for name, ds in (("data", self.data), ("samples", ds_samples), ("var_count", ds_vc)):
+            headers[name] = self._write_header(ds.header_messages(ds.write_btree()))
+        # local heap: names at 8-byte aligned offsets, offset 0 is the empty string
+        names = sorted(headers)
+        heap = bytearray(8)
+        offsets = {}
+        for name in names:
+            offsets[name] = len(heap)
+            heap += _pad8(name.encode() + b"\x00")
+        free_off = len(heap)
+        heap += struct.pack("<QQ", 1, 32) + b"\x00" * 16          # one free block of 32 bytes ends the segment
+        heap_data = self._reserve(len(heap))
+        self._write_at(heap_data, bytes(heap))
+        heap_addr = self._reserve(32)
+        self._write_at(heap_addr, b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, heap_data))
+        # symbol table node + group B-tree
+        snod_size = 8 + 2 * _GROUP_LEAF_K * 40
+        snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+        for name in names:
+            snod += struct.pack("<QQII16x", offsets[name], headers[name], 0, 0)
+        snod_addr = self._reserve(snod_size)
+        self._write_at(snod_addr, snod.ljust(snod_size, b"\x00"))
+        tree_size = 24 + 2 * _GROUP_INTERNAL_K * 16 + 8
+        tree = (b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF) +
+                struct.pack("<QQQ", 0, snod_addr, offsets[names[-1]]))
+        tree_addr = self._reserve(tree_size)
+        self._write_at(tree_addr, tree.ljust(tree_size, b"\x00"))
+        root = self._write_header([_message(0x11, struct.pack("<QQ", tree_addr, heap_addr))])
+        eof = self._pos
+        sb = (SIGNATURE + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0) +
+              struct.pack("<HHI", _GROUP_LEAF_K, _GROUP_INTERNAL_K, 0) +
+              struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF) +
+              struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", tree_addr, heap_addr))
+        assert len(sb) == 96
+        self._write_at(0, sb)
+        self._fh.truncate(eof)
+        self._fh.close()
