@@ -230,13 +230,18 @@ def main():
         tim["host_ms"] = [round((b - a) * 1e3, 3) for a, b in zip(t[:-1], t[1:])]
         return idx, new, score, stop, var_count, info, tim
 
+    wall_vs_event = []
+
     def timed(resident):
         for _ in range(args.warmup):
             one_selection(resident)
         barrier()
+        _native.timer_start(device)                  # device synchronised, CUDA event recorded
         t0 = time.perf_counter()
         outs = [one_selection(resident) for _ in range(args.steps)]
-        elapsed = time.perf_counter() - t0           # every selection ends synchronised (results copied to host)
+        wall = time.perf_counter() - t0              # every selection ends synchronised (results copied to host)
+        elapsed = _native.timer_stop(device) / 1e3   # device synchronised again; event-to-event seconds
+        wall_vs_event.append((wall, elapsed))
         barrier()
         if dist is not None:
             import torch
@@ -273,12 +278,17 @@ def main():
                         "tail_us_per_step_median": float(np.median(gaps[200:])),
                         "tail_us_per_step_p90": float(np.percentile(gaps[200:], 90)),
                         "max_us": float(gaps.max())}
+    if args.step_times and rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "step_series.json"), "w") as fh:
+            json.dump({"gap_us": gaps.tolist(), "new": new.tolist()}, fh)
     peak, peak_kind = peaks()
     n_steps = len(idx)
     sel_bytes = select_bytes(info["num_vars"], info["row_pitch_bytes"], n_samples, n_steps, int(new.sum())) // world
     achieved = sel_bytes / 1e9 / (phases["select_ms"] / 1e3) if phases["select_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": ["argmax_step_kernel+cover_step_kernel", "select_persistent_kernel", "select_cluster_kernel",
-                           "select_tail_kernel (head: select_cluster_kernel + regain_kernel)", "select_mgpu_kernel"][info["flavour"]],
+                           "select_tail_kernel (head: select_cluster_kernel + regain_kernel)", "select_mgpu_kernel",
+                           "select_tail_kernel replicated on every rank (head: select_mgpu_kernel, hand-over: build_edges_kernel over NVLink)"][info["flavour"]],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
                 "note": "latency-bound: %d dependent greedy steps, %.2f us per step" %
@@ -326,7 +336,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32-popcount/i64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "samples": n_samples, "variants_per_gpu": n_vars, "seed": args.seed,
-                       "parallelism": ("variants sharded over %d GPUs (%d rows each), gains replicated, per-step P2P delta exchange" % (world, n_vars)) if world > 1 else "single GPU",
+                       "parallelism": ("variants sharded over %d GPUs (%d rows each), gains replicated; head: per-step P2P delta exchange; tail: edge lists merged on every rank over NVLink, replicated single-CTA kernel" % (world, n_vars)) if world > 1 else "single GPU",
                        "l2": "inputs (345 MB packed + 353 MB sample-major copy) exceed the 126 MB L2",
                        "greedy_steps": n_steps, "stop": int(stop), "flags": args.flags},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
@@ -335,7 +345,7 @@ def main():
             "gpu_launches": int(info["kernel_launches"]) * args.steps,
             "roofline": roofline, "streaming_kernels": streaming, "phases_ms": phases,
             "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "step_profile": step_profile, "host_ms_create_append_finalize_begin_steps_close": {"resident": np.mean([o[6]["host_ms"] for o in outs_res], axis=0).round(3).tolist(), "e2e": np.mean([o[6]["host_ms"] for o in outs_e2e], axis=0).round(3).tolist()}, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:12]], "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
+            "step_profile": step_profile, "host_ms_create_append_finalize_begin_steps_close": {"resident": np.mean([o[6]["host_ms"] for o in outs_res], axis=0).round(3).tolist(), "e2e": np.mean([o[6]["host_ms"] for o in outs_e2e], axis=0).round(3).tolist()}, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:12]], "timing": {"clock": "CUDA events around the K timed steps (utmos_timer_start/stop: device synchronised on both sides), max over ranks", "host_wall_s_resident_e2e": [round(w, 6) for w, _ in wall_vs_event], "event_s_resident_e2e": [round(e, 6) for _, e in wall_vs_event]}, "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

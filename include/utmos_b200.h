@@ -125,10 +125,14 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
                      uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
                      uint8_t *singleton_out);
 
+/* CUDA-event milliseconds the K1 kernel launches of the last utmos_convert_gt call took (copies excluded). */
+int utmos_convert_kernel_ms(double *ms_out);
+
 /* ---- multi-GPU: rows sharded over ranks (one process per GPU), gains replicated ----
  * Every rank ingests ITS rows into its own context, then:
  *   utmos_rows            informative rows this rank kept (host all-reduces them -> UTMOS_OPT_GLOBAL_ROWS)
  *   utmos_finalize        local var_count / gains
+ *   utmos_mgpu_layout     merged row numbering (see below)
  *   utmos_mgpu_export     allocates the exchange block (per-step delta inboxes + flags) and returns its 64-byte
  *                         CUDA IPC handle; the host all-gathers the handles (torch.distributed / MPI / files)
  *   utmos_mgpu_connect    maps every peer's block (NVLink P2P); handles = world x 64 bytes in rank order
@@ -137,6 +141,12 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
  * winner, retires its own rows into a delta vector, stores the delta straight into the peers' inboxes and
  * applies the sum.  All ranks must call utmos_select_steps with the same arguments; all return the same rows. */
 int utmos_rows(utmos_ctx *ctx, int64_t *rows_out);
+/* Merged row numbering for the hand-over to the replicated tail: once the part of the matrix that still scores is
+ * sparse, every rank writes its live rows as edge-list entries into the exchange blocks of ALL ranks (NVLink
+ * stores) and all ranks run the same single-CTA tail kernel.  row_base = sum over lower ranks of their rows
+ * rounded up to 32, merged_rows = that sum over all ranks; allow_tail = 0 keeps the per-step exchange for the
+ * whole selection (must be the same on every rank).  Call after utmos_set_gains0, before utmos_mgpu_export. */
+int utmos_mgpu_layout(utmos_ctx *ctx, int64_t row_base, int64_t merged_rows, int allow_tail);
 int utmos_mgpu_export(utmos_ctx *ctx, int rank, int world, uint8_t *handle_out /* 64 bytes */);
 int utmos_mgpu_connect(utmos_ctx *ctx, const uint8_t *handles /* world x 64 bytes */);
 int utmos_get_gains0(utmos_ctx *ctx, uint32_t *cnt_out, uint64_t *lo_out, uint64_t *hi_out);
@@ -165,12 +175,18 @@ int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
 /* info[0]=num_vars, [1]=row pitch bytes, [2]=has sample-major copy, [3]=device bytes in use,
  * [4]=fixed-point scale (AF flavours), [5]=AF values not exactly representable (count), [6]=kernels launched,
  * [7]=selection kernel flavour used: 0 step kernels, 1 grid-wide persistent, 2 one-cluster DSMEM,
- *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2), 4 multi-GPU kernel */
+ *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2), 4 multi-GPU kernel (per-step exchange),
+ *   5 multi-GPU head followed by the replicated tail */
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:
  * ms[0]=h2d copies, [1]=ingest kernels, [2]=transpose, [3]=column reduce / gain init, [4]=select loop */
 int utmos_timings(utmos_ctx *ctx, double *ms, int n, int reset);
+
+/* Device stopwatch (benchmark): start/stop synchronise the device and record a CUDA event each; *ms_out is the
+ * event-to-event time, i.e. it covers every kernel and copy issued by any context on that device in between. */
+int utmos_timer_start(int device);
+int utmos_timer_stop(int device, double *ms_out);
 
 /* ---- host-side codecs of the hdf5 chunk streamer (no device work) ----
  * hdf5 filter 32000 "lzf" as written by h5py for compression="lzf" (utmos/select.py:208-238).

@@ -35,7 +35,7 @@ class CpuShard:
     def __init__(self, n_samples, af_mode, rows_hint=0, device=0, flags=0):
         self.n, self.af_mode = n_samples, af_mode
         self.parts, self.afs = [], []
-        self.exported = self.connected = None
+        self.exported = self.connected = self.layout = None
 
     def append_packed(self, gt, af=None):
         self.parts.append(np.asarray(gt))
@@ -56,7 +56,15 @@ class CpuShard:
         self.gain0 = self.dense.sum(axis=0).astype(np.uint32)
         return self.vc
 
+    def info(self):
+        return {"has_sample_major": 1}
+
+    def mgpu_layout(self, row_base, merged_rows, allow_tail=True):
+        assert row_base % 32 == 0 and merged_rows % 32 == 0 and merged_rows >= row_base and allow_tail
+        self.layout = (row_base, merged_rows)
+
     def mgpu_export(self, rank, world):
+        assert self.layout is not None                        # layout before export
         self.exported = (rank, world)
         return np.full(64, rank, dtype=np.uint8)
 

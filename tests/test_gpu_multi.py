@@ -74,7 +74,7 @@ def test_two_gpus_match_single_gpu_and_reference(use_af):
     gold = H.golden_json("full_order_af.json" if use_af else "full_order_count.json")
     names = np.asarray(H.load_jl_parts(["chunk0.jl"])[0]["samples"]).astype(str)
     num_vars, vc, idx, new, score, stop, flavour = out["fixture"]
-    assert flavour == 4 and num_vars == 1989
+    assert flavour == 5 and num_vars == 1989          # multi-GPU head + replicated tail
     assert [names[i] for i in idx] == [g[0] for g in gold["rows"]]
     assert new == [g[2] for g in gold["rows"]]
     assert [vc[i] for i in idx] == [g[1] for g in gold["rows"]]

@@ -20,8 +20,8 @@ E_NOGPU = -3
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_finalize", "utmos_select_begin",
-           "utmos_select_steps", "utmos_convert_gt", "utmos_rows", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
-           "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings",
+           "utmos_select_steps", "utmos_convert_gt", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
+           "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
 
@@ -64,17 +64,21 @@ def lib():
         "utmos_select_begin": (i32, [p, p, p]),
         "utmos_select_steps": (i32, [p, i64, p, p, p, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
         "utmos_convert_gt": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p]),
+        "utmos_convert_kernel_ms": (i32, [ctypes.POINTER(ctypes.c_double)]),
         "utmos_debug_gains": (i32, [p, p, p]),
         "utmos_info": (i32, [p, p, i32]),
         "utmos_debug_step_times": (i32, [p, i64, i64, p]),
         "utmos_set_option": (i32, [p, i32, i64]),
         "utmos_debug_counters": (i32, [p, p]),
         "utmos_rows": (i32, [p, ctypes.POINTER(i64)]),
+        "utmos_mgpu_layout": (i32, [p, i64, i64, i32]),
         "utmos_mgpu_export": (i32, [p, i32, i32, p]),
         "utmos_mgpu_connect": (i32, [p, p]),
         "utmos_get_gains0": (i32, [p, p, p, p]),
         "utmos_set_gains0": (i32, [p, p, p, p, i64]),
         "utmos_timings": (i32, [p, p, i32, i32]),
+        "utmos_timer_start": (i32, [i32]),
+        "utmos_timer_stop": (i32, [i32, ctypes.POINTER(ctypes.c_double)]),
         "utmos_lzf_decompress": (i64, [p, i64, p, i64]),
         "utmos_lzf_compress": (i64, [p, i64, p, i64]),
         "utmos_device_alloc": (i32, [i32, pp, i64]),
@@ -94,6 +98,18 @@ def check(code):
     """Raise NativeError for a non-zero return code."""
     if code != 0:
         raise NativeError(code, lib().utmos_last_error().decode("utf-8", "replace"))
+
+
+def timer_start(device=0):
+    """Device stopwatch: synchronise the device and record the start CUDA event."""
+    check(lib().utmos_timer_start(int(device)))
+
+
+def timer_stop(device=0):
+    """Synchronise the device, record the stop event; milliseconds between the two events."""
+    ms = ctypes.c_double(0.0)
+    check(lib().utmos_timer_stop(int(device), ctypes.byref(ms)))
+    return ms.value
 
 
 def device_count():
@@ -190,6 +206,9 @@ class DeviceMatrix:
         n = ctypes.c_int64(0)
         check(lib().utmos_rows(self._ctx, ctypes.byref(n)))
         return n.value
+
+    def mgpu_layout(self, row_base, merged_rows, allow_tail=True):
+        check(lib().utmos_mgpu_layout(self._ctx, int(row_base), int(merged_rows), 1 if allow_tail else 0))
 
     def mgpu_export(self, rank, world):
         handle = np.zeros(64, dtype=np.uint8)
@@ -306,6 +325,13 @@ def convert_gt(gt, device=0):
     check(lib().utmos_convert_gt(device, _ptr(gt), n_vars, n_samples, ploidy, _ptr(packed), _ptr(af),
                                  ctypes.byref(het), ctypes.byref(hom), _ptr(single)))
     return packed, af.reshape(-1, 1), het.value, hom.value, single.astype(bool)
+
+
+def convert_kernel_ms():
+    """CUDA-event milliseconds of the K1 kernel launches of the last convert_gt call."""
+    ms = ctypes.c_double(0.0)
+    check(lib().utmos_convert_kernel_ms(ctypes.byref(ms)))
+    return ms.value
 
 
 def lzf_decompress(data, out_len):

@@ -52,6 +52,7 @@ struct Trace {
 };
 constexpr size_t kStageBytes = 64ull << 20;      // per staging buffer (two pinned host + two device)
 constexpr int kGraphSteps = 32;                  // step pairs per CUDA graph replay
+constexpr unsigned long long kListBudget = 1ull << 24;   // edge-list entries (16 B each; 32 B for AF flavours)
 enum { T_H2D = 0, T_INGEST = 1, T_TRANSPOSE = 2, T_GAIN = 3, T_SELECT = 4, T_COUNT = 5 };
 
 struct Pending {
@@ -123,6 +124,14 @@ struct utmos_ctx {
     unsigned int *d_delta_cnt = nullptr;
     unsigned long long *d_delta_lo = nullptr, *d_delta_hi = nullptr;
     int mg_grid = 0, mg_block_threads = 0;
+    // hand-over to the replicated tail (mgpu.cu): merged numbering of the rows of all ranks
+    long long mg_row_base = 0;         // first merged row id of this rank (multiple of 32)
+    long long mg_merged_rows = 0;      // sum over ranks of their rows rounded up to 32
+    bool mg_allow_tail = false;        // every rank has a sample-major copy (set by utmos_mgpu_layout)
+    bool mg_tail = false;              // the merged lists are built: every rank runs the same tail kernel
+    unsigned long long mg_list_cap = 0;   // entries of the merged lists region of the exchange block
+    unsigned int *d_lcnt = nullptr, *d_my_base = nullptr, *d_pool_base = nullptr;
+    bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 1536;        // hand over to the single-CTA tail once picks cover fewer rows than this
     unsigned long long tail_budget = 0;   // handed to the head kernels while the tail flavour waits for sparsity
     unsigned long long total_bits = 0;    // set bits of the scoring rows at step 0
@@ -193,6 +202,7 @@ PinnedCache g_pinned;
 
 int pinned_acquire(utmos_ctx *c);
 void pinned_release(utmos_ctx *c);
+void mg_block_release(void *ptr);
 
 void t_begin(utmos_ctx *c, int cat, cudaStream_t s)
 {
@@ -445,6 +455,14 @@ void free_select_state(utmos_ctx *c)
     dev_free(c, c->d_out_score, S * 8);
     dev_free(c, c->d_out_time, S * 8);
     dev_free(c, c->d_dbg, 128);
+    if (c->lists_external) {             // regions of the exchange block, not allocations of their own
+        c->d_lists[0] = nullptr;
+        c->d_pool = nullptr;
+        c->lists_external = false;
+    }
+    dev_free(c, c->d_lcnt, S * 4);
+    dev_free(c, c->d_my_base, S * 4);
+    dev_free(c, c->d_pool_base, 16);
     for (int i = 0; i < 2; ++i) {
         big_free(c, c->d_lists[i], c->lists_cap[i] * 16);
         dev_free(c, c->d_list_off[i], S * 4);
@@ -455,9 +473,8 @@ void free_select_state(utmos_ctx *c)
     dev_free(c, c->d_delta_cnt, S * 4);
     dev_free(c, c->d_delta_lo, S * 8);
     dev_free(c, c->d_delta_hi, S * 8);
-    for (int i = 0; i < kMaxRanks; ++i)
-        if (c->mg_peer[i]) { cudaIpcCloseMemHandle(c->mg_peer[i]); c->mg_peer[i] = nullptr; }
-    if (c->mg_block) { cudaFree(c->mg_block); c->mg_block = nullptr; }
+    for (int i = 0; i < kMaxRanks; ++i) c->mg_peer[i] = nullptr;     // mappings stay in the process-wide cache
+    if (c->mg_block) { mg_block_release(c->mg_block); c->mg_block = nullptr; }
     dev_free(c, c->d_pool_cursor, 16);
     big_free(c, c->d_pool, c->pool_cap * 2);
     c->pool_cap = 0;
@@ -466,6 +483,91 @@ void free_select_state(utmos_ctx *c)
     dev_free(c, c->d_bar, 64);
     dev_free(c, c->d_partials, sizeof(ArgPartial) * 2048);
 }
+
+struct MgLayout {
+    size_t off_cnt, off_lo, off_hi, off_flags, small_bytes;     // per-step exchange: inboxes + flags (zeroed at export)
+    size_t off_live, off_lists, off_pool, bytes;                 // merged tail structures (replicated on every rank)
+    size_t live_words, pool_cap;
+};
+MgLayout mg_layout(size_t S, int world, bool af, unsigned long long list_cap, long long merged_rows)
+{
+    MgLayout l;
+    size_t off = 0;
+    auto take = [&](size_t b) { const size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
+    l.off_cnt = take(2 * (size_t)world * S * 4);
+    l.off_lo = take(af ? 2 * (size_t)world * S * 8 : 0);
+    l.off_hi = take(af ? 2 * (size_t)world * S * 8 : 0);
+    l.off_flags = take((size_t)kMaxRanks * 8);
+    l.small_bytes = off;
+    l.live_words = list_cap ? (size_t)std::max(8ll, (merged_rows / 32 + 7) / 8 * 8) : 0;
+    l.pool_cap = list_cap ? (size_t)(mgpu_pool_share(list_cap) + 64ull * (size_t)world) : 0;
+    l.off_live = take(l.live_words * 4);
+    l.off_lists = take((size_t)list_cap * (af ? 32 : 16));
+    l.off_pool = take(l.pool_cap * 2);
+    l.bytes = off;
+    return l;
+}
+
+// Exchange blocks are cudaMalloc'ed once and kept for the life of the process: creating and IPC-mapping hundreds
+// of MB per selection costs milliseconds and cudaFree synchronises the device.  A block handed back by a context
+// is reused by the next one that fits; peers keep their mapping of it (keyed by the 64-byte IPC handle).
+struct MgBlock {
+    int device;
+    size_t bytes;
+    void *ptr;
+    cudaIpcMemHandle_t handle;
+    bool busy;
+};
+std::vector<MgBlock> g_mg_blocks;
+struct MgPeerMap {
+    int device;
+    cudaIpcMemHandle_t handle;
+    void *ptr;
+};
+std::vector<MgPeerMap> g_mg_peers;
+
+int mg_block_acquire(int device, size_t bytes, void **ptr_out, cudaIpcMemHandle_t *handle_out)
+{
+    int best = -1;
+    for (size_t i = 0; i < g_mg_blocks.size(); ++i) {
+        const MgBlock &b = g_mg_blocks[i];
+        if (!b.busy && b.device == device && b.bytes >= bytes && (best < 0 || b.bytes < g_mg_blocks[best].bytes)) best = (int)i;
+    }
+    if (best < 0) {
+        MgBlock b;
+        b.device = device;
+        b.bytes = bytes;
+        b.busy = false;
+        UT_CUDA(cudaMalloc(&b.ptr, bytes));                  // plain cudaMalloc: IPC handles need it
+        UT_CUDA(cudaIpcGetMemHandle(&b.handle, b.ptr));
+        g_mg_blocks.push_back(b);
+        best = (int)g_mg_blocks.size() - 1;
+    }
+    g_mg_blocks[best].busy = true;
+    *ptr_out = g_mg_blocks[best].ptr;
+    *handle_out = g_mg_blocks[best].handle;
+    return UTMOS_OK;
+}
+
+void mg_block_release(void *ptr)
+{
+    for (auto &b : g_mg_blocks)
+        if (b.ptr == ptr) b.busy = false;
+}
+
+int mg_peer_map(int device, const cudaIpcMemHandle_t &h, void **ptr_out)
+{
+    for (auto &m : g_mg_peers)
+        if (m.device == device && memcmp(&m.handle, &h, sizeof(h)) == 0) { *ptr_out = m.ptr; return UTMOS_OK; }
+    MgPeerMap m;
+    m.device = device;
+    m.handle = h;
+    UT_CUDA(cudaIpcOpenMemHandle(&m.ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g_mg_peers.push_back(m);
+    *ptr_out = m.ptr;
+    return UTMOS_OK;
+}
+
 
 SelParams make_params(const utmos_ctx *c, bool step0)
 {
@@ -493,12 +595,13 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     {
         // a pick that newly covers this many rows is cheaper to absorb by one streaming recompute of all gains
         // (S columns, ~V*S/8 bytes) than by one atomic per set bit of those rows
-        long long thr = c->regain_rows >= 0 ? c->regain_rows : std::max(4096ll, c->V / 128);
+        // (measured on the 1kGP shape: one recompute = 90 us; subtracting a pick of V/170 rows costs the same)
+        long long thr = c->regain_rows >= 0 ? c->regain_rows : std::max(4096ll, c->V / 170);
         if (!c->d_cols || (c->flags & UTMOS_F_STEP_KERNELS)) thr = 0;
         p.regain_rows = (unsigned int)std::min(thr, 0xffffffffll);
     }
     p.tail_budget = c->tail_budget;
-    p.tail_rows = c->tail_rows;
+    p.tail_rows = c->tail_rows * (unsigned int)std::max(1, c->mg_world);   // N ranks: N times the rows per pick at the same sparsity
     p.dbg_time = c->dbg_time;
     p.dsmem_gains = (c->flags & UTMOS_F_DSMEM_GAINS) ? 1 : 0;
     p.st = c->d_state;
@@ -510,6 +613,17 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.L = c->L;
     p.scale = c->scale;
     p.af = c->af_mode != UTMOS_AF_NONE;
+    if (c->mg_tail) {
+        // replicated tail over the merged structures of all ranks (mgpu.cu): global row numbering, no bit matrix
+        const MgLayout l = mg_layout((size_t)c->S, c->mg_world, p.af != 0, c->mg_list_cap, c->mg_merged_rows);
+        p.rows = nullptr;
+        p.cols = nullptr;
+        p.q_lo = p.q_hi = nullptr;
+        p.live = (uint32_t *)((char *)c->mg_block + l.off_live);
+        p.colPitchW = (long long)l.live_words;
+        p.V = c->global_rows >= 0 ? c->global_rows : c->V;
+        p.regain_rows = 0;
+    }
     return p;
 }
 
@@ -528,22 +642,6 @@ int build_graph(utmos_ctx *c)
     cudaGraphDestroy(graph);
     UT_CUDA(e);
     return UTMOS_OK;
-}
-
-struct MgLayout {
-    size_t off_cnt, off_lo, off_hi, off_flags, bytes;
-};
-MgLayout mg_layout(size_t S, int world, bool af)
-{
-    MgLayout l;
-    size_t off = 0;
-    auto take = [&](size_t b) { const size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
-    l.off_cnt = take(2 * (size_t)world * S * 4);
-    l.off_lo = take(af ? 2 * (size_t)world * S * 8 : 0);
-    l.off_hi = take(af ? 2 * (size_t)world * S * 8 : 0);
-    l.off_flags = take((size_t)kMaxRanks * 8);
-    l.bytes = off;
-    return l;
 }
 
 }  // namespace
@@ -865,6 +963,7 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
     UT_CUDA(cudaStreamSynchronize(c->stream));      // host buffers (mask, weights, st) may go away
     if ((c->flags & UTMOS_F_STEP_KERNELS) && (!c->graph_exec || had_weights != c->has_weights)) UT_TRY(build_graph(c));
     c->lists_valid = false;
+    c->mg_tail = false;
     c->selecting = true;
     return UTMOS_OK;
 }
@@ -895,35 +994,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
     UT_CUDA(cudaMemcpy(c->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
     const SelParams p = make_params(c, false);
     t_begin(c, T_SELECT, c->stream);
-    if (c->mg_world > 1) {
-        const bool af = c->af_mode != UTMOS_AF_NONE;
-        const MgLayout l = mg_layout((size_t)c->S, c->mg_world, af);
-        MgpuParams m;
-        memset(&m, 0, sizeof(m));
-        m.rank = c->mg_rank;
-        m.world = c->mg_world;
-        m.global_V = c->global_rows >= 0 ? c->global_rows : c->V;
-        m.seq0 = st.mgpu_seq;
-        m.delta_cnt = c->d_delta_cnt;
-        m.delta_lo = c->d_delta_lo;
-        m.delta_hi = c->d_delta_hi;
-        char *mine = (char *)c->mg_block;
-        m.inbox_cnt = (unsigned int *)(mine + l.off_cnt);
-        m.inbox_lo = (unsigned long long *)(mine + l.off_lo);
-        m.inbox_hi = (unsigned long long *)(mine + l.off_hi);
-        m.flags = (unsigned long long *)(mine + l.off_flags);
-        for (int q = 0; q < c->mg_world; ++q) {
-            if (q == c->mg_rank) continue;
-            if (!c->mg_peer[q]) { set_error("select_steps: multi-GPU peers are not connected"); return UTMOS_E_ARG; }
-            char *pb = (char *)c->mg_peer[q];
-            m.peer_inbox_cnt[q] = (unsigned int *)(pb + l.off_cnt);
-            m.peer_inbox_lo[q] = (unsigned long long *)(pb + l.off_lo);
-            m.peer_inbox_hi[q] = (unsigned long long *)(pb + l.off_hi);
-            m.peer_flags[q] = (unsigned long long *)(pb + l.off_flags);
-        }
-        UT_TRY(launch_mgpu(c->stream, p, m, c->mg_grid, c->mg_block_threads, c->d_bar, c->d_partials, &c->n_launch));
-        c->flavour_used = 4;
-    } else if (c->flags & UTMOS_F_STEP_KERNELS) {
+    if (c->flags & UTMOS_F_STEP_KERNELS && c->mg_world == 1) {
         while (true) {
             UT_CUDA(cudaGraphLaunch(c->graph_exec, c->stream));
             c->n_launch += 2 * kGraphSteps;
@@ -932,32 +1003,67 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             if (st.stop != 0 || st.step >= limit) break;
         }
     } else {
+        const bool multi = c->mg_world > 1;
+        const bool af = c->af_mode != UTMOS_AF_NONE;
         int CL = 0, tail_ok = 0;
-        if (!(c->flags & UTMOS_F_NO_CLUSTER)) UT_TRY(cluster_plan(p, &CL));
-        if (!(c->flags & UTMOS_F_NO_TAIL)) UT_TRY(tail_plan(p, &tail_ok));
-        // Head: greedy steps by the cluster (or grid-wide) kernel; a pick that covers very many rows ends the
-        // launch and the conditional regain kernel recomputes the gains.  While the tail flavour is still
-        // waiting for the live part of the matrix to become sparse, launches are kept short (4 steps) so the
-        // host can switch as soon as the per-sample live-row lists fit the budget.
-        // Tail: one CTA runs all remaining steps from the lists.
-        const unsigned long long list_budget = 1ull << 24;          // entries (16 B each; 32 B for AF flavours)
-        const size_t estride = c->af_mode != UTMOS_AF_NONE ? 2 : 1;
+        if (!multi && !(c->flags & UTMOS_F_NO_CLUSTER)) UT_TRY(cluster_plan(p, &CL));
+        if (!multi && !(c->flags & UTMOS_F_NO_TAIL)) UT_TRY(tail_plan(p, &tail_ok));
+        if (multi) tail_ok = c->mg_list_cap > 0;          // same decision on every rank (utmos_mgpu_export)
+        // Head: greedy steps by the cluster (or grid-wide, or multi-GPU) kernel; a pick that covers very many rows
+        // ends the launch and the conditional regain kernel recomputes the gains.  While the tail flavour is still
+        // waiting for the live part of the matrix to become sparse, launches are kept short so the host can switch
+        // as soon as the per-sample live-row lists fit the budget.
+        // Tail: one CTA runs all remaining steps from the lists (on every rank, identically, when multi-GPU).
+        const unsigned long long list_budget = multi ? c->mg_list_cap - 64 : kListBudget;
+        const size_t estride = af ? 2 : 1;
         c->tail_budget = tail_ok ? list_budget : 0;
         auto reserve_lists = [&](int which, unsigned long long entries) -> int {
             const size_t need = (size_t)std::max<unsigned long long>(entries, 1) * estride;
             if (need > c->lists_cap[which]) {
+                if (c->lists_external && which == 0) { set_error("merged edge lists exceed the exchange block"); return UTMOS_E_NOMEM; }
                 big_free(c, c->d_lists[which], c->lists_cap[which] * 16);     // stream is idle here (just synchronised)
                 UT_TRY(big_alloc(c, (void **)&c->d_lists[which], need * 16));
                 c->lists_cap[which] = need;
             }
             return UTMOS_OK;
         };
+        MgLayout l;
+        MgpuParams m;
+        memset(&m, 0, sizeof(m));
+        if (multi) {
+            l = mg_layout((size_t)c->S, c->mg_world, af, c->mg_list_cap, c->mg_merged_rows);
+            m.rank = c->mg_rank;
+            m.world = c->mg_world;
+            m.global_V = c->global_rows >= 0 ? c->global_rows : c->V;
+            m.delta_cnt = c->d_delta_cnt;
+            m.delta_lo = c->d_delta_lo;
+            m.delta_hi = c->d_delta_hi;
+            char *mine = (char *)c->mg_block;
+            m.inbox_cnt = (unsigned int *)(mine + l.off_cnt);
+            m.inbox_lo = (unsigned long long *)(mine + l.off_lo);
+            m.inbox_hi = (unsigned long long *)(mine + l.off_hi);
+            m.flags = (unsigned long long *)(mine + l.off_flags);
+            for (int q = 0; q < c->mg_world; ++q) {
+                if (q == c->mg_rank) continue;
+                if (!c->mg_peer[q]) { set_error("select_steps: multi-GPU peers are not connected"); return UTMOS_E_ARG; }
+                char *pb = (char *)c->mg_peer[q];
+                m.peer_inbox_cnt[q] = (unsigned int *)(pb + l.off_cnt);
+                m.peer_inbox_lo[q] = (unsigned long long *)(pb + l.off_lo);
+                m.peer_inbox_hi[q] = (unsigned long long *)(pb + l.off_hi);
+                m.peer_flags[q] = (unsigned long long *)(pb + l.off_flags);
+            }
+        }
         while (true) {
             SelParams q = make_params(c, false);
             if (c->lists_valid) {
                 UT_TRY(launch_tail(c->stream, q, c->lists_total, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
-                c->flavour_used = 3;
+                c->flavour_used = multi ? 5 : 3;
+            } else if (multi) {
+                m.seq0 = st.mgpu_seq;
+                UT_TRY(launch_mgpu(c->stream, q, m, c->mg_grid, c->mg_block_threads, c->d_bar, c->d_partials, &c->n_launch));
+                UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                c->flavour_used = 4;
             } else {
                 // a few launches are queued between host checks; once the live part is sparse enough the queued
                 // head kernels return immediately (they test st->live_bits at launch)
@@ -979,11 +1085,71 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             UT_CUDA(cudaStreamSynchronize(c->stream));
             if (st.stop != 0 || st.step >= limit || st.abort_flag) break;
             if (tail_ok && !c->lists_valid && st.want_tail && st.live_bits <= list_budget) {
+                if (multi) {
+                    // replicated tail: every rank writes its live rows into the merged lists of all ranks (mgpu.cu)
+                    GatherParams g;
+                    memset(&g, 0, sizeof(g));
+                    g.rank = c->mg_rank; g.world = c->mg_world; g.S = (int)c->S;
+                    g.lcnt = c->d_lcnt;
+                    g.inbox_cnt = m.inbox_cnt;
+                    g.flags = m.flags;
+                    g.st = c->d_state;
+                    g.live_word0 = c->mg_row_base / 32;
+                    g.live_words = (c->V + 31) / 32;
+                    EdgeDst d;
+                    memset(&d, 0, sizeof(d));
+                    d.world = c->mg_world;
+                    for (int r = 0; r < c->mg_world; ++r) {
+                        char *blk = r == c->mg_rank ? (char *)c->mg_block : (char *)c->mg_peer[r];
+                        g.peer_inbox_cnt[r] = (unsigned int *)(blk + l.off_cnt);
+                        g.peer_flags[r] = (unsigned long long *)(blk + l.off_flags);
+                        g.live_dst[r] = (uint32_t *)(blk + l.off_live);
+                        d.lists[r] = (uint4 *)(blk + l.off_lists);
+                        d.pool[r] = (unsigned short *)(blk + l.off_pool);
+                    }
+                    d.slot_base = c->d_my_base;
+                    d.pool_base = c->d_pool_base;
+                    d.row_base = c->mg_row_base;
+                    char *mine = (char *)c->mg_block;
+                    // my merged live mask: zero the padding words; the ranks fill their own word ranges
+                    UT_CUDA(cudaMemsetAsync(mine + l.off_live, 0, l.live_words * 4, c->stream));
+                    UT_TRY(launch_live_counts(c->stream, q, c->d_lcnt, &c->n_launch));
+                    g.seq = st.mgpu_seq + 1;       // (a) all-gather of the per-rank live counts; also orders the memset above
+                    UT_TRY(launch_gather_counts(c->stream, g, &c->n_launch));
+                    UT_TRY(launch_gather_offsets(c->stream, g, c->d_list_off[0], c->d_list_len[0], c->d_my_base, c->d_cursor,
+                                                 c->d_pool_base, &c->n_launch));
+                    UT_TRY(launch_build_edges(c->stream, q, d, c->d_cursor, c->d_pool_cursor, &c->n_launch));
+                    UT_TRY(launch_gather_live(c->stream, g, q.live, &c->n_launch));
+                    g.seq = st.mgpu_seq + 2;       // (b) everybody's entries have landed everywhere
+                    UT_TRY(launch_gather_done(c->stream, g, &c->n_launch));
+                    st.mgpu_seq += 2;
+                    UT_CUDA(cudaMemcpyAsync(&c->d_state->mgpu_seq, &st.mgpu_seq, sizeof(st.mgpu_seq), cudaMemcpyHostToDevice, c->stream));
+                    UT_CUDA(cudaStreamSynchronize(c->stream));
+                    SelState chk;
+                    UT_CUDA(cudaMemcpy(&chk, c->d_state, sizeof(chk), cudaMemcpyDeviceToHost));
+                    if (chk.abort_flag) { st.abort_flag = chk.abort_flag; break; }
+                    if (!c->lists_external) {
+                        big_free(c, c->d_lists[0], c->lists_cap[0] * 16);
+                        big_free(c, c->d_pool, c->pool_cap * 2);
+                    }
+                    c->d_lists[0] = (uint4 *)(mine + l.off_lists);
+                    c->lists_cap[0] = (size_t)c->mg_list_cap * estride;
+                    c->d_pool = (unsigned short *)(mine + l.off_pool);
+                    c->pool_cap = l.pool_cap;
+                    c->lists_external = true;
+                    c->lists_cur = 0;
+                    c->mg_tail = true;
+                    c->lists_total = st.live_bits;
+                    c->lists_valid = true;
+                    continue;
+                }
                 // first compaction: edge lists from the bit matrix
                 UT_TRY(reserve_lists(c->lists_cur, st.live_bits));
-                if ((size_t)st.live_bits + 64 > c->pool_cap) {
+                // pooled carrier lists are padded to 8 entries per row (rows with >= 7 carriers): <= 15/7 per live bit
+                const size_t pool_need = (size_t)mgpu_pool_share(st.live_bits);
+                if (pool_need > c->pool_cap) {
                     big_free(c, c->d_pool, c->pool_cap * 2);
-                    c->pool_cap = (size_t)st.live_bits + 64;
+                    c->pool_cap = pool_need;
                     UT_TRY(big_alloc(c, (void **)&c->d_pool, c->pool_cap * 2));
                 }
                 q = make_params(c, false);
@@ -1003,9 +1169,6 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 c->lists_cur = nxt;
                 c->lists_total = st.live_bits;
             }
-        }
-        if (st.limit != limit) {
-            st.limit = limit;
         }
     }
     t_end(c, c->stream);
@@ -1060,6 +1223,16 @@ int utmos_rows(utmos_ctx *c, int64_t *rows_out)
     return UTMOS_OK;
 }
 
+int utmos_mgpu_layout(utmos_ctx *c, int64_t row_base, int64_t merged_rows, int allow_tail)
+{
+    if (!c || row_base < 0 || merged_rows < row_base || (row_base & 31) || (merged_rows & 31)) { set_error("mgpu_layout: bad arguments"); return UTMOS_E_ARG; }
+    if (c->mg_block) { set_error("mgpu_layout after mgpu_export"); return UTMOS_E_ARG; }
+    c->mg_row_base = row_base;
+    c->mg_merged_rows = merged_rows;
+    c->mg_allow_tail = allow_tail != 0;
+    return UTMOS_OK;
+}
+
 int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
 {
     if (!c || !handle_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { set_error("mgpu_export: bad arguments"); return UTMOS_E_ARG; }
@@ -1068,9 +1241,16 @@ int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
     UT_CUDA(cudaSetDevice(c->device));
     const bool af = c->af_mode != UTMOS_AF_NONE;
     const size_t S = (size_t)c->S;
-    const MgLayout l = mg_layout(S, world, af);
-    UT_CUDA(cudaMalloc(&c->mg_block, l.bytes));              // plain cudaMalloc: IPC handles need it
-    UT_CUDA(cudaMemset(c->mg_block, 0, l.bytes));
+    // merged edge lists for the replicated tail: as many entries as the tail hand-over budget allows (utmos_set_gains0
+    // has stored the set bits of all ranks' scoring rows); every rank computes the same capacity
+    c->mg_list_cap = 0;
+    if (c->mg_allow_tail && c->mg_merged_rows > 0 && c->mg_merged_rows < 0xffffffffll && c->S <= 65535 &&
+        !(c->flags & (UTMOS_F_NO_TAIL | UTMOS_F_NO_TRANSPOSE)))
+        c->mg_list_cap = std::min<unsigned long long>(kListBudget, c->total_bits) + 64;
+    const MgLayout l = mg_layout(S, world, af, c->mg_list_cap, c->mg_merged_rows);
+    cudaIpcMemHandle_t h;
+    UT_TRY(mg_block_acquire(c->device, l.bytes, &c->mg_block, &h));
+    UT_CUDA(cudaMemsetAsync(c->mg_block, 0, l.small_bytes, c->stream));     // inboxes and flags; big regions are rewritten before use
     c->mg_bytes = l.bytes;
     c->mg_rank = rank;
     c->mg_world = world;
@@ -1082,9 +1262,10 @@ int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
         UT_CUDA(cudaMemsetAsync(c->d_delta_lo, 0, S * 8, c->stream));
         UT_CUDA(cudaMemsetAsync(c->d_delta_hi, 0, S * 8, c->stream));
     }
+    UT_TRY(dev_alloc(c, (void **)&c->d_lcnt, S * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_my_base, S * 4));
+    UT_TRY(dev_alloc(c, (void **)&c->d_pool_base, 16));
     UT_CUDA(cudaStreamSynchronize(c->stream));
-    cudaIpcMemHandle_t h;
-    UT_CUDA(cudaIpcGetMemHandle(&h, c->mg_block));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(handle_out, &h, 64);
     UT_TRY(mgpu_grid(c->device, &c->mg_grid, &c->mg_block_threads));
@@ -1099,7 +1280,7 @@ int utmos_mgpu_connect(utmos_ctx *c, const uint8_t *handles)
         if (q == c->mg_rank) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)q * 64, 64);
-        UT_CUDA(cudaIpcOpenMemHandle(&c->mg_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+        UT_TRY(mg_peer_map(c->device, h, &c->mg_peer[q]));
     }
     return UTMOS_OK;
 }
@@ -1128,6 +1309,8 @@ int utmos_set_gains0(utmos_ctx *c, const uint32_t *cnt, const uint64_t *lo, cons
         UT_CUDA(cudaMemcpy(c->d_gain0_hi, hi, S * 8, cudaMemcpyHostToDevice));
     }
     if (global_rows >= 0) c->global_rows = global_rows;
+    c->total_bits = 0;
+    for (size_t i = 0; i < S; ++i) c->total_bits += cnt[i];
     return UTMOS_OK;
 }
 
@@ -1176,6 +1359,43 @@ int utmos_timings(utmos_ctx *c, double *ms, int n, int reset)
     return UTMOS_OK;
 }
 
+// Device-side stopwatch for callers that time whole selections (bench.py): both ends synchronise the device and
+// record a CUDA event, so the elapsed time covers every kernel and copy of every context in between.
+static cudaEvent_t g_timer_ev[kMaxRanks * 2] = {nullptr};
+
+int utmos_timer_start(int device)
+{
+    if (device < 0 || device >= kMaxRanks) { set_error("timer: device index out of range"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(device));
+    for (int i = 0; i < 2; ++i)
+        if (!g_timer_ev[device * 2 + i]) UT_CUDA(cudaEventCreate(&g_timer_ev[device * 2 + i]));
+    UT_CUDA(cudaDeviceSynchronize());
+    UT_CUDA(cudaEventRecord(g_timer_ev[device * 2], 0));
+    return UTMOS_OK;
+}
+
+int utmos_timer_stop(int device, double *ms_out)
+{
+    if (device < 0 || device >= kMaxRanks || !ms_out || !g_timer_ev[device * 2]) { set_error("timer: not started"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(device));
+    UT_CUDA(cudaDeviceSynchronize());
+    UT_CUDA(cudaEventRecord(g_timer_ev[device * 2 + 1], 0));
+    UT_CUDA(cudaEventSynchronize(g_timer_ev[device * 2 + 1]));
+    float ms = 0.f;
+    UT_CUDA(cudaEventElapsedTime(&ms, g_timer_ev[device * 2], g_timer_ev[device * 2 + 1]));
+    *ms_out = ms;
+    return UTMOS_OK;
+}
+
+static double g_convert_kernel_ms = 0.0;
+
+int utmos_convert_kernel_ms(double *ms_out)
+{
+    if (!ms_out) { set_error("convert_kernel_ms: null argument"); return UTMOS_E_ARG; }
+    *ms_out = g_convert_kernel_ms;
+    return UTMOS_OK;
+}
+
 int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_samples, int64_t ploidy,
                      uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
                      uint8_t *singleton_out)
@@ -1195,6 +1415,7 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
     double *d_af = nullptr;
     unsigned long long *d_hh = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int rc = UTMOS_OK, launches = 0;
     unsigned long long hh[2] = {0, 0};
     do {
@@ -1207,17 +1428,24 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
         CV(cudaMalloc(&d_af, (size_t)chunk * 8));
         CV(cudaMalloc(&d_hh, 16));
         CV(cudaMemsetAsync(d_hh, 0, 16, stream));
+        g_convert_kernel_ms = 0.0;
+        CV(cudaEventCreate(&ev0));
+        CV(cudaEventCreate(&ev1));
         for (long long r0 = 0; r0 < n_vars && rc == UTMOS_OK; r0 += chunk) {
             const long long m = std::min(chunk, n_vars - r0);
             CV(cudaMemcpyAsync(d_gt, gt + (size_t)r0 * row_in, (size_t)m * row_in, cudaMemcpyHostToDevice, stream));
+            CV(cudaEventRecord(ev0, stream));
             rc = launch_convert_gt(stream, d_gt, m, (int)n_samples, (int)ploidy, d_packed, pitch, d_af, d_hh, d_single,
                                    &launches);
             if (rc != UTMOS_OK) break;
+            CV(cudaEventRecord(ev1, stream));
             CV(cudaMemcpyAsync(packed_out + (size_t)r0 * (size_t)pitch, d_packed, (size_t)m * (size_t)pitch,
                                cudaMemcpyDeviceToHost, stream));
             CV(cudaMemcpyAsync(af_out + r0, d_af, (size_t)m * 8, cudaMemcpyDeviceToHost, stream));
             if (singleton_out) CV(cudaMemcpyAsync(singleton_out + r0, d_single, (size_t)m, cudaMemcpyDeviceToHost, stream));
             CV(cudaStreamSynchronize(stream));
+            float kms = 0.f;
+            if (cudaEventElapsedTime(&kms, ev0, ev1) == cudaSuccess) g_convert_kernel_ms += kms;
         }
         if (rc != UTMOS_OK) break;
         CV(cudaMemcpy(hh, d_hh, 16, cudaMemcpyDeviceToHost));
@@ -1229,6 +1457,8 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
     if (d_af) cudaFree(d_af);
     if (d_hh) cudaFree(d_hh);
     if (stream) cudaStreamDestroy(stream);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     if (rc != UTMOS_OK) return rc;
     if (num_het_out) *num_het_out = (int64_t)hh[0];
     if (num_hom_out) *num_hom_out = (int64_t)hh[1];

@@ -107,6 +107,32 @@ struct MgpuParams {
     unsigned long long *peer_flags[kMaxRanks];
 };
 
+// Where build_edges_kernel writes the per-sample edge lists (tail.cu).  Single GPU: world = 1 and the context's own
+// buffers.  Multi-GPU: the same slots of every rank's merged buffers (replicated tail, see mgpu.cu).
+struct EdgeDst {
+    int world;
+    uint4 *lists[kMaxRanks];
+    unsigned short *pool[kMaxRanks];
+    const unsigned int *slot_base;     // [S] first entry slot of sample s for THIS rank's rows
+    const unsigned int *pool_base;     // device scalar: first pool slot of this rank (null = 0)
+    long long row_base;                // added to local row ids (merged live mask numbering)
+};
+
+// Multi-GPU hand-over to the replicated tail: all-gather of the per-rank live counts and completion flags.
+struct GatherParams {
+    int rank, world, S;
+    unsigned long long seq;                    // sequence number of this exchange
+    const unsigned int *lcnt;                  // [S] live rows of THIS rank that carry sample s
+    unsigned int *inbox_cnt;                   // [2][world][S] mine (peers write their slot)
+    unsigned long long *flags;                 // [world] mine
+    unsigned int *peer_inbox_cnt[kMaxRanks];
+    unsigned long long *peer_flags[kMaxRanks];
+    uint32_t *live_dst[kMaxRanks];             // merged live masks of every rank
+    long long live_word0;                      // first word of this rank's rows in the merged mask
+    long long live_words;                      // words this rank contributes (ceil(V/32))
+    SelState *st;
+};
+
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
@@ -192,6 +218,7 @@ struct IngestScratch {
     uint8_t *flags = nullptr;          // [chunk rows]
     unsigned int *block_counts = nullptr;
     unsigned int *block_offsets = nullptr;
+    unsigned long long *tile_state = nullptr;   // [0] ticket, [1 + t] decoupled look-back state of tile t
     long long cap_rows = 0;
 };
 int ingest_scratch_reserve(IngestScratch &sc, long long rows, cudaStream_t stream);
@@ -221,7 +248,17 @@ int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, un
 int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *old_lists, const unsigned int *old_off,
                         const unsigned int *old_len, uint4 *new_lists, unsigned int *new_off, unsigned int *new_len,
                         int *n_launch);
+int launch_build_edges(cudaStream_t stream, const SelParams &p, const EdgeDst &d, unsigned int *cursor,
+                       unsigned int *pool_cursor, int *n_launch);
 int tail_plan(const SelParams &p, int *ok_out);
+// mgpu.cu
+int launch_live_counts(cudaStream_t stream, const SelParams &p, unsigned int *lcnt, int *n_launch);
+int launch_gather_counts(cudaStream_t stream, const GatherParams &g, int *n_launch);
+int launch_gather_offsets(cudaStream_t stream, const GatherParams &g, unsigned int *list_off, unsigned int *list_len,
+                          unsigned int *my_base, unsigned int *cursor, unsigned int *pool_base, int *n_launch);
+int launch_gather_live(cudaStream_t stream, const GatherParams &g, const uint32_t *live, int *n_launch);
+int launch_gather_done(cudaStream_t stream, const GatherParams &g, int *n_launch);
+unsigned long long mgpu_pool_share(unsigned long long live_bits);
 int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, int *n_launch);
 int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
                 unsigned int *bar_counter, ArgPartial *partials, int *n_launch);

@@ -14,6 +14,8 @@
 // Algorithmic bytes: read ploidy*V*S (int8), write V*ceil(S/8) + 9*V.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace utmos {
@@ -97,12 +99,144 @@ __global__ void __launch_bounds__(256) gt_pack_af_kernel(const int8_t *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// diploid fast path.  A CTA stages a tile of consecutive rows (one contiguous byte range of R * 2S genotype
+// bytes) in shared memory with aligned 128-bit streaming loads, then one warp per row: a lane takes 8 samples
+// (16 genotype bytes) per turn and emits exactly one MSB-first output byte, so a warp writes 32 consecutive
+// bytes.  Allele 0 / allele 1 / called counts stay in registers and are shuffled down once per row; the rare
+// alleles >= 2 go to a per-warp shared histogram.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCvtWarps = 8;
+constexpr size_t kCvtSmemRaw = 96 * 1024;
+
+__device__ __forceinline__ uint32_t cvt_le32(const uint32_t *s32, unsigned int o)
+{
+    const unsigned int a = o >> 2;
+    return __funnelshift_r(s32[a], s32[a + 1], (o & 3u) * 8u);
+}
+
+__global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const int8_t *__restrict__ gt, long long V, int S,
+                                                                         int rows_per_tile, uint8_t *__restrict__ packed,
+                                                                         long long pitch, double *__restrict__ af,
+                                                                         unsigned long long *het_hom,
+                                                                         uint8_t *__restrict__ singleton)
+{
+    extern __shared__ __align__(16) uint8_t c_smem[];
+    __shared__ unsigned int s_hist[kCvtWarps][128];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row_bytes = 2ll * S;
+    const long long total_bytes = V * row_bytes;
+    for (int i = lane; i < 128; i += 32) s_hist[warp][i] = 0;
+    unsigned long long het_tot = 0, hom_tot = 0;
+    for (long long row0 = (long long)blockIdx.x * rows_per_tile; row0 < V; row0 += (long long)gridDim.x * rows_per_tile) {
+        const int nr = (int)min((long long)rows_per_tile, V - row0);
+        const long long start = row0 * row_bytes, end = start + nr * row_bytes;
+        const long long a0 = start & ~15ll;
+        const unsigned int mis = (unsigned int)(start - a0);
+        const int n16 = (int)((end - a0 + 15) >> 4);
+        uint4 *s16 = reinterpret_cast<uint4 *>(c_smem);
+        __syncthreads();                                   // previous tile fully consumed
+        for (int i = tid; i < n16 + 2; i += kCvtWarps * 32) {
+            const long long off = a0 + 16ll * i;
+            uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);     // -1 = missing allele
+            if (i < n16) {
+                if (off + 16 <= total_bytes) {
+                    v = ld_stream_u128(reinterpret_cast<const uint4 *>(gt + off));
+                } else {
+                    uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                    for (int b = 0; b < 16 && off + b < total_bytes; ++b) {
+                        w[b >> 2] &= ~(0xffu << (8 * (b & 3)));
+                        w[b >> 2] |= (uint32_t)(uint8_t)__ldg(gt + off + b) << (8 * (b & 3));
+                    }
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            s16[i] = v;
+        }
+        __syncthreads();
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(c_smem);
+        for (int i = warp; i < nr; i += kCvtWarps) {
+            const long long r = row0 + i;
+            const unsigned int o = mis + (unsigned int)(i * row_bytes);
+            uint8_t *out = packed + r * pitch;
+            unsigned int an = 0, zero = 0, one = 0, het = 0, hom = 0;
+            bool rare = false;
+            for (int s0 = lane * 8; s0 < S; s0 += 256) {
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = cvt_le32(s32, o + 2u * s0 + 4u * k);
+                uint32_t byte = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t pair = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                    const int g0 = (int)(int8_t)(pair & 0xffu), g1 = (int)(int8_t)(pair >> 8);
+                    if (s0 + j < S) {
+                        if (g0 >= 0) { an += 1; if (g0 == 0) zero += 1; else if (g0 == 1) one += 1; else { rare = true; atomicAdd(&s_hist[warp][g0], 1u); } }
+                        if (g1 >= 0) { an += 1; if (g1 == 0) zero += 1; else if (g1 == 1) one += 1; else { rare = true; atomicAdd(&s_hist[warp][g1], 1u); } }
+                        const bool called = g0 >= 0 && g1 >= 0;
+                        const bool is_het = called && g0 != g1;
+                        const bool is_hom = called && g0 == g1 && g0 > 0;
+                        het += is_het ? 1u : 0u;
+                        hom += is_hom ? 1u : 0u;
+                        if (is_het || is_hom) byte |= 0x80u >> j;
+                    }
+                }
+                out[s0 >> 3] = (uint8_t)byte;
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                an += __shfl_xor_sync(0xffffffffu, an, sh);
+                zero += __shfl_xor_sync(0xffffffffu, zero, sh);
+                one += __shfl_xor_sync(0xffffffffu, one, sh);
+                het += __shfl_xor_sync(0xffffffffu, het, sh);
+                hom += __shfl_xor_sync(0xffffffffu, hom, sh);
+            }
+            unsigned int m = one;
+            if (__any_sync(0xffffffffu, rare)) {
+                __syncwarp();
+                for (int a = 2 + lane; a < 128; a += 32) { m = max(m, s_hist[warp][a]); s_hist[warp][a] = 0; }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, sh));
+                __syncwarp();
+            }
+            if (lane == 0) {
+                // max over alleles of count/an == (max count)/an: the divide is monotone in the numerator
+                af[r] = an ? (double)m / (double)an : CUDART_NAN;
+                if (singleton) singleton[r] = (one == 1u || zero == 1u) ? 1 : 0;
+                het_tot += het;
+                hom_tot += hom;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (het_tot) atomicAdd(het_hom + 0, het_tot);
+        if (hom_tot) atomicAdd(het_hom + 1, hom_tot);
+    }
+}
+
 }  // namespace
 
 int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S, int ploidy, uint8_t *packed,
                       long long pitch_out, double *af, unsigned long long *het_hom, uint8_t *singleton, int *n_launch)
 {
     if (V <= 0) return UTMOS_OK;
+    if (ploidy == 2 && ((uintptr_t)gt & 15u) == 0 && 2ull * (size_t)S + 64 <= kCvtSmemRaw && pitch_out == (S + 7) / 8) {
+        int R = (int)std::min<size_t>(64, (kCvtSmemRaw - 64) / (2 * (size_t)S));
+        if (R > kCvtWarps) R = R / kCvtWarps * kCvtWarps;           // whole rounds of one row per warp
+        const size_t smem = ((size_t)R * 2 * (size_t)S + 31) / 16 * 16 + 48;
+        static bool configured = false;
+        if (!configured) {
+            UT_CUDA(cudaFuncSetAttribute(gt_pack_af_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kCvtSmemRaw + 64)));
+            configured = true;
+        }
+        const long long tiles = (V + R - 1) / R;
+        const unsigned grid = (unsigned)std::min<long long>(tiles, 148ll * 8);
+        gt_pack_af_tile_kernel<<<grid, kCvtWarps * 32, smem, stream>>>(gt, V, S, R, packed, pitch_out, af, het_hom, singleton);
+        *n_launch += 1;
+        UT_CUDA(cudaGetLastError());
+        return UTMOS_OK;
+    }
     const unsigned grid = (unsigned)(V < 148ll * 16 ? V : 148ll * 16);
     if (ploidy == 2)
         gt_pack_af_kernel<2><<<grid, 256, 0, stream>>>(gt, V, S, ploidy, packed, pitch_out, af, het_hom, singleton);

@@ -7,6 +7,8 @@
 // every later kernel can use aligned 128-bit loads.
 //
 // Algorithmic bytes per chunk: read V*P (+8V AF), write V'*pitch (+8V').
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace utmos {
@@ -189,6 +191,156 @@ __global__ void __launch_bounds__(kThreads) scatter_rows_kernel(const void *raw,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast path for packed .jl rows (the common case): ONE pass.  A CTA stages a tile of consecutive raw rows in
+// shared memory with aligned 128-bit streaming loads (rows are contiguous, so the tile is one byte range
+// whatever the row pitch), flags the informative rows, gets its output offset by a decoupled look-back over
+// the tiles before it (tile order = ticket order, so the chain always makes progress), and writes the kept
+// rows -- which are consecutive in the output -- as aligned 128-bit stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFastMaxRows = 256;
+constexpr size_t kFastSmemRaw = 64 * 1024;        // largest row pitch the fast path stages
+constexpr size_t kFastTileBytes = 27 * 1024;      // preferred tile: 8 CTAs per SM keep loads in flight while others compute
+constexpr unsigned long long kTileAgg = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// little-endian 4 bytes at byte offset o of the staged tile (any alignment)
+__device__ __forceinline__ uint32_t smem_le32(const uint32_t *s32, unsigned int o)
+{
+    const unsigned int a = o >> 2;
+    return __funnelshift_r(s32[a], s32[a + 1], (o & 3u) * 8u);
+}
+
+__global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *__restrict__ raw, long long n_rows,
+                                                                 long long pitch_in, const double *__restrict__ af_in,
+                                                                 int S, int pitchW, int rows_per_tile, long long n_tiles,
+                                                                 unsigned long long *state, const long long *d_nrows,
+                                                                 long long *d_chunk_total, uint32_t *__restrict__ rows_out,
+                                                                 double *__restrict__ af_out)
+{
+    extern __shared__ __align__(16) uint8_t f_smem[];
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned long long s_excl;
+    __shared__ unsigned short s_src[kFastMaxRows];
+    __shared__ uint8_t s_flag[kFastMaxRows];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (unsigned int)atomicAdd(state, 1ull);
+    __syncthreads();
+    const long long tile = s_tile;
+    if (tile >= n_tiles) return;
+    const long long row0 = tile * rows_per_tile;
+    const int nr = (int)min((long long)rows_per_tile, n_rows - row0);
+    const long long total_bytes = n_rows * pitch_in;
+    const long long start = row0 * pitch_in, end = start + (long long)nr * pitch_in;
+    const long long a0 = start & ~15ll;
+    const unsigned int mis = (unsigned int)(start - a0);
+    const int n16 = (int)((end - a0 + 15) >> 4);
+    uint4 *s16 = reinterpret_cast<uint4 *>(f_smem);
+    for (int i = tid; i < n16 + 2; i += kThreads) {            // two extra zeroed pieces: reads past the last row stay in bounds
+        const long long off = a0 + 16ll * i;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i < n16) {
+            if (off + 16 <= total_bytes) {
+                v = ld_stream_u128(reinterpret_cast<const uint4 *>(raw + off));
+            } else {
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                for (int b = 0; b < 16 && off + b < total_bytes; ++b) w[b >> 2] |= (uint32_t)__ldg(raw + off + b) << (8 * (b & 3));
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        s16[i] = v;
+    }
+    __syncthreads();
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(f_smem);
+    const int nW = (S + 31) / 32;
+    const uint32_t last_mask = (S & 31) ? ((1u << (S & 31)) - 1u) : 0xffffffffu;
+    for (int i = warp; i < nr; i += kThreads / 32) {
+        const unsigned int o = mis + (unsigned int)i * (unsigned int)pitch_in;
+        uint32_t any = 0;
+        for (int k = lane; k < nW; k += 32) {
+            uint32_t x = smem_le32(s32, o + 4u * k);              // bit order does not matter for "any"
+            if (k == nW - 1) x = msb_bytes_to_word(x) & last_mask;
+            any |= x;
+        }
+        any = __ballot_sync(0xffffffffu, any != 0);
+        if (lane == 0) s_flag[i] = any ? 1 : 0;
+    }
+    __syncthreads();
+    const unsigned int keep = (tid < nr && s_flag[tid]) ? 1u : 0u;
+    unsigned int total;
+    const unsigned int ex = block_exclusive_scan(keep, &total);
+    if (keep) s_src[ex] = (unsigned short)tid;
+    if (warp == 0) {
+        // decoupled look-back: publish this tile's count, then sum the tiles before it
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_release_u64(state + 1, kTilePrefix | total);
+        } else {
+            if (lane == 0) st_release_u64(state + 1 + tile, kTileAgg | total);
+            long long j = tile - 1;
+            while (true) {
+                const long long idx = j - lane;
+                unsigned long long v;
+                unsigned int pm, zm, need;
+                int first_p;
+                do {
+                    v = idx >= 0 ? ld_acquire_u64(state + 1 + idx) : kTilePrefix;
+                    pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                    zm = __ballot_sync(0xffffffffu, (v >> 62) == 0ull);
+                    first_p = pm ? __ffs(pm) - 1 : 32;
+                    need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
+                } while (zm & need);
+                unsigned long long c = lane <= first_p ? (v & kTileValue) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (first_p < 32) break;
+                j -= 32;
+            }
+            if (lane == 0) st_release_u64(state + 1 + tile, kTilePrefix | (excl + total));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (tile == n_tiles - 1) *d_chunk_total = (long long)(excl + total);
+        }
+    }
+    __syncthreads();
+    if (total == 0) return;
+    const long long base = *d_nrows + (long long)s_excl;
+    const int q4 = pitchW >> 2;
+    uint4 *out16 = reinterpret_cast<uint4 *>(rows_out + base * pitchW);
+    const int units = (int)total * q4;
+    for (int u = tid; u < units; u += kThreads) {
+        const int k = u / q4, q = u - k * q4;
+        const unsigned int o = mis + (unsigned int)s_src[k] * (unsigned int)pitch_in + 16u * q;
+        const unsigned int a = o >> 2, sh = (o & 3u) * 8u;
+        const uint32_t r0 = s32[a], r1 = s32[a + 1], r2 = s32[a + 2], r3 = s32[a + 3], r4 = s32[a + 4];
+        uint32_t w[4] = {__funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh), __funnelshift_r(r2, r3, sh),
+                         __funnelshift_r(r3, r4, sh)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int wi = q * 4 + e;
+            uint32_t x = wi < nW ? msb_bytes_to_word(w[e]) : 0u;
+            if (wi == nW - 1) x &= last_mask;
+            w[e] = x;
+        }
+        out16[u] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (af_out && af_in)
+        for (int k = tid; k < (int)total; k += kThreads) af_out[base + k] = af_in[row0 + s_src[k]];
+}
+
 __global__ void bump_rows_kernel(long long *d_nrows, const long long *d_chunk_total) { *d_nrows += *d_chunk_total; }
 
 }  // namespace
@@ -201,6 +353,7 @@ int ingest_scratch_reserve(IngestScratch &sc, long long rows, cudaStream_t strea
     UT_CUDA(cudaMallocAsync(&sc.flags, (size_t)rows, stream));
     UT_CUDA(cudaMallocAsync(&sc.block_counts, sizeof(unsigned int) * (size_t)nb, stream));
     UT_CUDA(cudaMallocAsync(&sc.block_offsets, sizeof(unsigned int) * (size_t)nb, stream));
+    UT_CUDA(cudaMallocAsync(&sc.tile_state, sizeof(unsigned long long) * (size_t)(rows + 2), stream));
     sc.cap_rows = rows;
     return UTMOS_OK;
 }
@@ -210,6 +363,7 @@ void ingest_scratch_free(IngestScratch &sc, cudaStream_t stream)
     if (sc.flags) cudaFreeAsync(sc.flags, stream);
     if (sc.block_counts) cudaFreeAsync(sc.block_counts, stream);
     if (sc.block_offsets) cudaFreeAsync(sc.block_offsets, stream);
+    if (sc.tile_state) cudaFreeAsync(sc.tile_state, stream);
     sc = IngestScratch();
 }
 
@@ -239,8 +393,29 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
 {
     if (n_rows <= 0) return UTMOS_OK;
     UT_TRY(ingest_scratch_reserve(sc, n_rows, stream));
-    *n_launch += 4;
     long long *d_total = d_nrows + 1;
+    if (kind == RAW_PACKED_MSB && ((uintptr_t)raw & 15u) == 0 && (size_t)pitch_in + 64 <= kFastSmemRaw &&
+        n_rows * pitch_in < (1ll << 46)) {
+        const size_t tile_budget = std::max(kFastTileBytes, (size_t)pitch_in + 64);
+        const int R = (int)std::min<long long>(kFastMaxRows, (long long)((tile_budget - 64) / (size_t)pitch_in));
+        const long long n_tiles = (n_rows + R - 1) / R;
+        const size_t smem = ((size_t)R * (size_t)pitch_in + 31) / 16 * 16 + 48;
+        static bool configured = false;
+        if (!configured) {
+            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kFastSmemRaw + 64)));
+            configured = true;
+        }
+        UT_CUDA(cudaMemsetAsync(sc.tile_state, 0, sizeof(unsigned long long) * (size_t)(n_tiles + 1), stream));
+        ingest_packed_kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>(
+            (const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles, sc.tile_state, d_nrows, d_total,
+            rows_out, af_out);
+        bump_rows_kernel<<<1, 1, 0, stream>>>(d_nrows, d_total);
+        *n_launch += 2;
+        UT_CUDA(cudaGetLastError());
+        return UTMOS_OK;
+    }
+    *n_launch += 4;
     switch (kind) {
     case RAW_PACKED_MSB:
         return ingest_kind<RAW_PACKED_MSB>(stream, sc, raw, n_rows, pitch_in, af_in, nullptr, S, pitchW, rows_out,

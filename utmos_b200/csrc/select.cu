@@ -22,48 +22,65 @@ namespace utmos {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// K2b: bit-matrix transpose.  CTA tile = 128 rows x 32 words (1024 samples) staged through shared
-// memory; each warp transposes 32x32 bit blocks with ballots; output is written as 16-byte pieces
-// (128 row-bits) per sample.
+// K2b: bit-matrix transpose.  CTA tile = 256 rows x 16 words (512 samples): rows are read as 64-byte
+// pieces (streaming 128-bit loads; 36 KB of shared memory per CTA keeps 6 CTAs per SM in flight) into shared memory, every warp transposes 32x32 bit blocks in
+// registers (5 butterfly stages of one shuffle + a masked merge each), and every sample gets its 256 row
+// bits as one aligned 32-byte sector (two 128-bit stores).  Algorithmic bytes: read + write V*pitch.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTRows = 128;
+constexpr int kTRows = 256;
+constexpr int kTWords = 16;
+constexpr int kTInPitch = 17;       // words; odd pitch -> column reads are bank-conflict free
+constexpr int kTOutPitch = 9;
+constexpr size_t kTransposeSmem = ((size_t)kTRows * kTInPitch + (size_t)kTWords * 32 * kTOutPitch) * 4;
+
+// lane l holds row l of a 32x32 bit block; afterwards lane j holds column j (bit i = old row i, bit j)
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
+{
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+        const uint32_t m = k == 16 ? 0x0000ffffu : k == 8 ? 0x00ff00ffu : k == 4 ? 0x0f0f0f0fu : k == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+        x = (lane & k) ? ((x & ~m) | ((y & ~m) >> k)) : ((x & m) | ((y & m) << k));
+    }
+    return x;
+}
 
 __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__restrict__ rows, long long V,
                                                              int pitchW, int S32, uint32_t *__restrict__ cols,
                                                              long long colPitchW)
 {
-    __shared__ uint32_t s_in[kTRows][33];
-    __shared__ uint32_t s_out[1024][5];
+    extern __shared__ __align__(16) uint32_t t_smem[];
+    uint32_t *s_in = t_smem;                                   // [kTRows][kTInPitch]
+    uint32_t *s_out = t_smem + kTRows * kTInPitch;             // [1024][kTOutPitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long r0 = (long long)blockIdx.x * kTRows;
-    const int w0 = blockIdx.y * 32;
+    const int w0 = blockIdx.y * kTWords;
 
-    for (int i = warp; i < kTRows; i += 8) {
-        const long long r = r0 + i;
-        const int w = w0 + lane;
-        s_in[i][lane] = (r < V && w < pitchW) ? rows[r * pitchW + w] : 0u;
+    for (int i = threadIdx.x; i < kTRows * (kTWords / 4); i += 256) {
+        const int row = i / (kTWords / 4), q = i % (kTWords / 4);
+        const long long r = r0 + row;
+        const int w = w0 + q * 4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < V && w < pitchW) v = ld_stream_u128(reinterpret_cast<const uint4 *>(rows + r * pitchW + w));
+        uint32_t *d = s_in + row * kTInPitch + q * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
-    // warp `warp` -> row group g = warp & 3 (32 rows), word columns c = (warp >> 2) * 16 .. +16
-    const int g = warp & 3;
-    const int c_begin = (warp >> 2) * 16;
-    for (int c = c_begin; c < c_begin + 16; ++c) {
-        const uint32_t x = s_in[g * 32 + lane][c];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t b = __ballot_sync(0xffffffffu, (x >> j) & 1u);
-            if (lane == j) mine = b;
-        }
-        s_out[c * 32 + lane][g] = mine;
+    // warp g transposes the 32 blocks of row group g (rows g*32 .. g*32+31)
+    const int g = warp;
+#pragma unroll 4
+    for (int c = 0; c < kTWords; ++c) {
+        const uint32_t x = transpose32(s_in[(g * 32 + lane) * kTInPitch + c], lane);
+        s_out[(c * 32 + lane) * kTOutPitch + g] = x;
     }
     __syncthreads();
-    // 1024 samples x 4 words: thread t writes samples t, t+256, ... as one 16-byte store each
-    for (int sl = threadIdx.x; sl < 1024; sl += 256) {
+    for (int sl = threadIdx.x; sl < kTWords * 32; sl += 256) {
         const int s = w0 * 32 + sl;
         if (s >= S32) continue;
-        const uint4 v = make_uint4(s_out[sl][0], s_out[sl][1], s_out[sl][2], s_out[sl][3]);
-        *reinterpret_cast<uint4 *>(cols + (long long)s * colPitchW + (r0 >> 5)) = v;
+        const uint32_t *o = s_out + sl * kTOutPitch;
+        uint4 *dst = reinterpret_cast<uint4 *>(cols + (long long)s * colPitchW + (long long)blockIdx.x * (kTRows / 32));
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
 }
 
@@ -904,26 +921,49 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
     pd.gain_hi = m.delta_hi;
     __syncthreads();
 
+    int want_tail = 0;
+    __shared__ unsigned long long s_sumw[32];
     while (stop == 0 && step < limit) {
-        // ---- A: replicated argmax (identical on every rank)
+        // ---- A: replicated argmax (identical on every rank) + sum of the gains (= live set bits, all ranks)
+        {
+            unsigned long long acc = 0;
+            if (p.tail_budget)
+                for (int s = my_begin + (int)threadIdx.x; s < my_end; s += (int)blockDim.x) acc += __ldcg(p.gain_cnt + s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) s_sumw[threadIdx.x >> 5] = acc;
+        }
         Best b = block_best(scan_best(p, my_begin, my_end), s_red);
         if (threadIdx.x == 0) {
             ArgPartial a;
             a.score = b.score; a.idx = b.idx; a.cnt = b.cnt; a.sum = 0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a.sum += s_sumw[i];
             partials[blockIdx.x] = a;
         }
         if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
         Best t{-1.0e308, 0x7fffffff, 0u};
+        unsigned long long live_now = 0;
         for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) {
             Best o;
             o.score = __ldcg(&partials[i].score);
             o.idx = __ldcg(&partials[i].idx);
             o.cnt = __ldcg(&partials[i].cnt);
+            live_now += __ldcg(&partials[i].sum);
             t = best_of(t, o);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) live_now += __shfl_xor_sync(0xffffffffu, live_now, o);
+        __syncthreads();
+        if (lane == 0) s_sumw[threadIdx.x >> 5] = live_now;
         b = block_best(t, s_red);
+        live_now = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) live_now += s_sumw[i];
         if (p.S == 0 || b.score == 0.0) {                  // utmos/select.py:51-52
             stop = UTMOS_STOP_ZERO;
+            break;
+        }
+        if (p.tail_budget && live_now <= p.tail_budget && b.cnt < p.tail_rows) {
+            want_tail = 1;                                 // sparse enough: hand over to the replicated tail (mgpu.cu)
             break;
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1001,6 +1041,7 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
         st->stop = stop;
         st->winner = -1;
         st->regain = 0;
+        st->want_tail = want_tail;
         st->mgpu_seq = seq;
     }
 }
@@ -1022,12 +1063,17 @@ int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int
 {
     if (V <= 0 || S <= 0) return UTMOS_OK;
     const int S32 = (S + 31) / 32 * 32;
-    // colPitchW is a multiple of 8 words and covers ceil(V/32); tiles of 128 rows = 4 words
-    const long long row_tiles = colPitchW / 4;
-    const int col_tiles = (pitchW + 31) / 32;
-    if (row_tiles > 0x7fffffffll) { set_error("transpose: too many rows"); return UTMOS_E_ARG; }
+    // colPitchW is a multiple of 8 words and covers ceil(V/32); one tile = 256 rows = 8 words
+    const long long row_tiles = colPitchW / (kTRows / 32);
+    const int col_tiles = (pitchW + kTWords - 1) / kTWords;
+    if (row_tiles > 0x7fffffffll || col_tiles > 65535) { set_error("transpose: matrix too large"); return UTMOS_E_ARG; }
+    static bool configured = false;
+    if (!configured) {
+        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
+        configured = true;
+    }
     dim3 grid((unsigned)row_tiles, (unsigned)col_tiles);
-    transpose_bits_kernel<<<grid, 256, 0, stream>>>(rows, V, pitchW, S32, cols, colPitchW);
+    transpose_bits_kernel<<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW);
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;

@@ -19,6 +19,8 @@
 // re-compacted by a streaming filter pass, so dead entries never dominate.
 //
 // Reference semantics: utmos/select.py:24-53 (scores, mask, weights, argmax, zero stop) and :91-112.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace utmos {
@@ -98,18 +100,21 @@ __device__ __forceinline__ uint4 pack_entry(unsigned int r, unsigned int n, cons
 
 // First compaction, from the bit matrix: one warp per live row.  A row with k carriers yields k entries, one
 // in the list of each carrier.  ESTRIDE = 1 (count) or 2 (AF flavours: second uint4 = fixed-point AF limbs).
+// EdgeDst says where the entries go: single GPU = this context's buffers; multi-GPU = the SAME slots of every
+// rank's merged buffers (peer pointers, NVLink stores), so all ranks end up with byte-identical lists.
 template <int ESTRIDE>
-__global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, uint4 *lists, const unsigned int *list_off,
-                                                          unsigned int *cursor, unsigned short *pool,
+__global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d, unsigned int *cursor,
                                                           unsigned int *pool_cursor)
 {
     __shared__ unsigned short s_car[8][8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned int pool_base = d.pool_base ? *d.pool_base : 0u;
     for (long long r = warp0; r < p.V; r += nwarps) {
         if (!((p.live[r >> 5] >> (r & 31)) & 1u)) continue;
         const uint32_t *row = p.rows + r * p.pitchW;
+        const unsigned int rg = (unsigned int)(r + d.row_base);          // row id in the (merged) live mask
         int mine = 0;
         for (int k = lane; k < p.nW; k += 32) mine += __popc(__ldg(row + k));
         int incl = mine;
@@ -140,28 +145,37 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, uint4 *li
                 for (int j = 0; j < total; ++j)
                     if (j != lane) others[m++] = s_car[wib][j];
                 const unsigned int s = s_car[wib][lane];
-                const unsigned int slot = atomicAdd(cursor + s, 1u);
-                uint4 *dst = lists + ((size_t)list_off[s] + slot) * ESTRIDE;
-                dst[0] = pack_entry((unsigned int)r, (unsigned int)(total - 1), others);
-                if (ESTRIDE == 2) dst[1] = tailq;
+                const size_t slot = ((size_t)d.slot_base[s] + atomicAdd(cursor + s, 1u)) * ESTRIDE;
+                const uint4 e0 = pack_entry(rg, (unsigned int)(total - 1), others);
+                for (int q = 0; q < d.world; ++q) {
+                    d.lists[q][slot] = e0;
+                    if (ESTRIDE == 2) d.lists[q][slot + 1] = tailq;
+                }
             }
             __syncwarp();
         } else {
             // carriers of this row go to the pool once; every carrier's entry points at them
+            // (padded to a multiple of 8 entries with 0xffff so the tail kernel can use aligned 128-bit loads)
+            const int padded = (total + 7) & ~7;
             unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(pool_cursor, (unsigned int)total);
+            if (lane == 0) base = pool_base + atomicAdd(pool_cursor, (unsigned int)padded);
             base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < padded - total)
+                for (int q = 0; q < d.world; ++q) d.pool[q][base + total + lane] = (unsigned short)0xffffu;
             int pos = incl - mine;
             for (int k = lane; k < p.nW; k += 32) {
                 uint32_t x = __ldg(row + k);
                 while (x) {
                     const unsigned int s = (unsigned int)((k << 5) + (__ffs(x) - 1));
                     x &= x - 1;
-                    pool[base + pos++] = (unsigned short)s;
-                    const unsigned int slot = atomicAdd(cursor + s, 1u);
-                    uint4 *dst = lists + ((size_t)list_off[s] + slot) * ESTRIDE;
-                    dst[0] = make_uint4((unsigned int)r, kPooled, base, (unsigned int)total);
-                    if (ESTRIDE == 2) dst[1] = tailq;
+                    const size_t slot = ((size_t)d.slot_base[s] + atomicAdd(cursor + s, 1u)) * ESTRIDE;
+                    const uint4 e0 = make_uint4(rg, kPooled, base, (unsigned int)total);
+                    for (int q = 0; q < d.world; ++q) {
+                        d.pool[q][base + pos] = (unsigned short)s;
+                        d.lists[q][slot] = e0;
+                        if (ESTRIDE == 2) d.lists[q][slot + 1] = tailq;
+                    }
+                    pos++;
                 }
             }
         }
@@ -254,20 +268,28 @@ __device__ __forceinline__ Cand warp_argmax(Cand c)
 }
 
 struct TailCfg {
-    int off_lo, off_hi, off_w, off_mask, off_loff, off_llen, off_live, off_queue;   // byte offsets, counts at 0
-    int qcap;            // pooled-row queue entries (3 words each: pool base, carriers, row)
+    int off_lo, off_hi, off_w, off_mask, off_loff, off_llen, off_live;   // byte offsets, counts at 0
     int live_words;      // > 0: live mask held in shared memory
-    int lanes_per_row;   // power of two: lanes sharing one overflow row
     unsigned int min_recompact;   // do not bother re-compacting below this many live entries
 };
 
-template <int ESTRIDE>
+// integer argmax for count mode without weights: key = gain count of a selectable sample (0 otherwise);
+// np.argmax order = larger key, then lower index.  All lanes return the warp's winner.
+__device__ __forceinline__ uint2 warp_argmax_u32(unsigned int key, unsigned int idx)
+{
+    const unsigned int mk = __reduce_max_sync(0xffffffffu, key);
+    const unsigned int mi = __reduce_min_sync(0xffffffffu, key == mk ? idx : 0x7fffffffu);
+    return make_uint2(mk, mi);
+}
+
+// ESTRIDE 1: count entries; 2: AF flavours (second uint4 = fixed-point AF limbs of the row).
+// FAST: count mode without weights -> integer keys (two REDUX per reduction level instead of the float64 path).
+template <int ESTRIDE, bool FAST>
 __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailCfg cfg, unsigned long long lists_total)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Cand s_red[32];
     __shared__ unsigned long long s_sum[32];
-    __shared__ unsigned int s_qn;
     constexpr bool AF = ESTRIDE == 2;
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(smem);
     unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(smem + cfg.off_lo);
@@ -277,7 +299,6 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     unsigned int *s_loff = reinterpret_cast<unsigned int *>(smem + cfg.off_loff);
     unsigned int *s_llen = reinterpret_cast<unsigned int *>(smem + cfg.off_llen);
     uint32_t *s_live = reinterpret_cast<uint32_t *>(smem + cfg.off_live);
-    unsigned int *s_queue = reinterpret_cast<unsigned int *>(smem + cfg.off_queue);
     const unsigned short *pool = p.pool;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool has_w = p.weights != nullptr;
@@ -298,9 +319,8 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     int stop = st->stop;
     int recompact = 0;
     int since_check = 0;
-    if (tid == 0) s_qn = 0;
     __syncthreads();
-    long long t_arg = 0, t_walk = 0, t_ret = 0, t_mark = clock64();
+    long long t_arg = 0, t_walk = 0, t_mark = clock64();
 #define UT_TICK(acc) do { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } while (0)
 
     while (stop == 0 && step < limit) {
@@ -323,53 +343,78 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             }
         }
         // ---- argmax over all samples (shared memory, np.argmax order)
-        Cand b{0u, 0u, 0x7fffffff, 0u};
-        for (int i = tid; i < p.S; i += blockDim.x) {
-            const unsigned int c = s_cnt[i];
-            double g = 0.0;
-            if (s_mask[i] == 1) {
-                g = AF ? fixed_to_double(s_lo[i], s_hi[i], p.L, p.scale) : (double)c;
-                if (has_w) g *= s_w[i];
+        int best_idx, next_idx;             // the pick, and the best of the other warps' winners (a likely next pick)
+        unsigned int best_cnt;
+        double best_score;
+        if (FAST) {
+            unsigned int bk = 0, bi = 0x7fffffffu;
+            for (int i = tid; i < p.S; i += blockDim.x) {
+                const unsigned int k = s_mask[i] == 1 ? s_cnt[i] : 0u;
+                if (k > bk || bi == 0x7fffffffu) { bk = k; bi = (unsigned int)i; }     // i ascends: first index kept on ties
             }
-            const unsigned long long k = score_key(g);
-            Cand c2{(unsigned int)(k >> 32), (unsigned int)k, i, c};
-            if (cand_better(c2, b)) b = c2;
+            const uint2 w = warp_argmax_u32(bk, bi);
+            if (lane == 0) *reinterpret_cast<uint2 *>(&s_red[warp]) = w;
+            __syncthreads();
+            const uint2 mine = *reinterpret_cast<const uint2 *>(&s_red[lane]);
+            const uint2 b = warp_argmax_u32(mine.x, mine.y);
+            const uint2 t2 = warp_argmax_u32(mine.y == b.y ? 0u : mine.x, mine.y == b.y ? 0x7fffffffu : mine.y);
+            best_idx = (int)b.y;
+            best_cnt = b.x;
+            best_score = (double)b.x;
+            next_idx = t2.x > 0u ? (int)t2.y : 0x7fffffff;
+        } else {
+            Cand b{0u, 0u, 0x7fffffff, 0u};
+            for (int i = tid; i < p.S; i += blockDim.x) {
+                const unsigned int c = s_cnt[i];
+                double g = 0.0;
+                if (s_mask[i] == 1) {
+                    g = AF ? fixed_to_double(s_lo[i], s_hi[i], p.L, p.scale) : (double)c;
+                    if (has_w) g *= s_w[i];
+                }
+                const unsigned long long k = score_key(g);
+                Cand c2{(unsigned int)(k >> 32), (unsigned int)k, i, c};
+                if (cand_better(c2, b)) b = c2;
+            }
+            b = warp_argmax(b);
+            if (lane == 0) s_red[warp] = b;
+            __syncthreads();
+            const Cand mine = s_red[lane];
+            b = warp_argmax(mine);
+            Cand t2 = mine;
+            if (mine.idx == b.idx) { t2.hi = 0u; t2.lo = 0u; t2.idx = 0x7fffffff; }
+            t2 = warp_argmax(t2);
+            best_idx = b.idx;
+            best_cnt = b.cnt;
+            best_score = key_score(b.hi, b.lo);
+            next_idx = (t2.idx != 0x7fffffff && key_score(t2.hi, t2.lo) > 0.0) ? t2.idx : 0x7fffffff;
         }
-        b = warp_argmax(b);
-        if (lane == 0) s_red[warp] = b;
-        __syncthreads();
-        const Cand mine = s_red[lane];
-        b = warp_argmax(mine);
-        const double best_score = key_score(b.hi, b.lo);
         if (p.S == 0 || best_score == 0.0) {              // utmos/select.py:51-52
             stop = UTMOS_STOP_ZERO;
             break;
         }
-        Cand t2 = mine;
-        if (mine.idx == b.idx) { t2.hi = 0u; t2.lo = 0u; t2.idx = 0x7fffffff; }
-        t2 = warp_argmax(t2);                             // best of the other warps' winners: a likely next pick
         if (tid == 0) {
-            p.out_idx[step] = b.idx;
-            p.out_new[step] = b.cnt;
+            p.out_idx[step] = best_idx;
+            p.out_new[step] = best_cnt;
             p.out_score[step] = best_score;
             if (p.dbg_time) p.out_time[step] = global_timer_ns();
-            s_mask[b.idx] = 0;                            // utmos/select.py:100
+            s_mask[best_idx] = 0;                         // utmos/select.py:100
         }
         step += 1;
-        tot += b.cnt;
+        tot += best_cnt;
         if (tot >= p.V) {                                 // utmos/select.py:110-112
             stop = UTMOS_STOP_ALL;
             break;
         }
         UT_TICK(t_arg);
         // ---- stream the winner's list; a live bit that we clear marks a newly covered row
-        const uint4 *lst = p.lists + (size_t)s_loff[b.idx] * ESTRIDE;
-        const int len = (int)s_llen[b.idx];
-        if (t2.idx != 0x7fffffff && key_score(t2.hi, t2.lo) > 0.0) {   // warm L2 with the runner-up's list
-            const uint4 *l2 = p.lists + (size_t)s_loff[t2.idx] * ESTRIDE;
-            const int lines = ((int)s_llen[t2.idx] * ESTRIDE + 7) >> 3;    // 128-byte lines
+        const uint4 *lst = p.lists + (size_t)s_loff[best_idx] * ESTRIDE;
+        const int len = (int)s_llen[best_idx];
+        if (next_idx != 0x7fffffff) {                     // warm L2 with the runner-up's list
+            const uint4 *l2 = p.lists + (size_t)s_loff[next_idx] * ESTRIDE;
+            const int lines = ((int)s_llen[next_idx] * ESTRIDE + 7) >> 3;    // 128-byte lines
             for (int i = tid; i < lines; i += blockDim.x) prefetch_l2(l2 + (size_t)i * 8);
         }
+        const int sub = lane & 7, slot = lane >> 3;
         for (int base = 0; base < len; base += 4 * (int)blockDim.x) {
             uint4 e[4];
 #pragma unroll
@@ -379,25 +424,26 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                if (base + u * (int)blockDim.x + warp * 32 >= len) break;       // warp-uniform
+                const int i = base + u * (int)blockDim.x + tid;
                 const unsigned int r = e[u].x;
                 bool fresh = false;
                 if (r != 0xffffffffu) {
+                    // a row appears once in a list, so nobody else clears this bit during the walk: test with a plain
+                    // load (shared-memory atomics cost ~2 cycles per lane) and clear only the bits that are set
                     const uint32_t bit = 1u << (r & 31);
-                    const uint32_t old = live_smem ? atomicAnd(s_live + (r >> 5), ~bit) : atomicAnd(p.live + (r >> 5), ~bit);
-                    fresh = (old & bit) != 0;
+                    uint32_t *lw = (live_smem ? s_live : p.live) + (r >> 5);
+                    fresh = (*reinterpret_cast<volatile uint32_t *>(lw) & bit) != 0;
+                    if (fresh) atomicAnd(lw, ~bit);
                 }
                 const unsigned int n = e[u].y & 0xffffu;
+                unsigned long long nl = 0, nh = 0;
+                if (AF && fresh) {
+                    const uint4 qv = __ldg(lst + (size_t)i * ESTRIDE + 1);
+                    nl = 0ull - (((unsigned long long)qv.y << 32) | qv.x);
+                    nh = 0ull - (((unsigned long long)qv.w << 32) | qv.z);
+                }
                 if (fresh && n != kPooled) {
-                    unsigned long long nl = 0, nh = 0;
-                    if (AF) {
-                        const int i = base + u * (int)blockDim.x + tid;
-                        const uint4 qv = __ldg(lst + (size_t)i * ESTRIDE + 1);
-                        nl = 0ull - (((unsigned long long)qv.y << 32) | qv.x);
-                        nh = 0ull - (((unsigned long long)qv.w << 32) | qv.z);
-                        atomicAdd(s_lo + b.idx, nl);     // the pick's own gain (keeps sum(gains) == live entries)
-                        atomicAdd(s_hi + b.idx, nh);
-                    }
-                    atomicAdd(s_cnt + b.idx, 0xffffffffu);
                     const unsigned int c[kInline] = {e[u].y >> 16, e[u].z & 0xffffu, e[u].z >> 16, e[u].w & 0xffffu,
                                                      e[u].w >> 16};
 #pragma unroll
@@ -408,28 +454,40 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                         }
                     }
                 }
-                // rows with many carriers: their carrier list is in the pool -> warp-aggregated queue append
-                const bool big = fresh && n == kPooled;
-                const unsigned int m = __ballot_sync(0xffffffffu, big);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    unsigned int pos0 = 0;
-                    if (lane == leader) pos0 = atomicAdd(&s_qn, (unsigned int)__popc(m));
-                    pos0 = __shfl_sync(0xffffffffu, pos0, leader);
-                    if (big) {
-                        const unsigned int pos = pos0 + __popc(m & ((1u << lane) - 1u));
-                        if ((int)pos < cfg.qcap) {
-                            s_queue[3 * pos] = e[u].z;
-                            s_queue[3 * pos + 1] = e[u].w;
-                            s_queue[3 * pos + 2] = r;
-                        } else {
-                            // queue full (exotic inputs only): this thread retires the row alone
-                            unsigned long long nl = 0, nh = 0;
-                            if (AF) { nl = 0ull - p.q_lo[r]; nh = 0ull - p.q_hi[r]; }
-                            for (unsigned int k = 0; k < e[u].w; ++k) {
-                                const unsigned int s = pool[e[u].z + k];
-                                atomicAdd(s_cnt + s, 0xffffffffu);
-                                if (AF) { atomicAdd(s_lo + s, nl); atomicAdd(s_hi + s, nh); }
+                // rows with many carriers keep their carrier list (uint16, padded to 8 with 0xffff, 16-byte aligned)
+                // in the pool: the warp retires them here, four rows at a time, 8 lanes x 128-bit loads per row
+                unsigned int m = __ballot_sync(0xffffffffu, fresh && n == kPooled);
+                while (m) {
+                    int src = -1;
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        if (m) {
+                            const int bpos = __ffs(m) - 1;
+                            m &= m - 1;
+                            if (slot == s4) src = bpos;
+                        }
+                    }
+                    const int from = src < 0 ? 0 : src;
+                    const unsigned int pbase = __shfl_sync(0xffffffffu, e[u].z, from);
+                    const unsigned int cnt_from = __shfl_sync(0xffffffffu, e[u].w, from);   // every lane takes part
+                    const unsigned int cnt = src < 0 ? 0u : cnt_from;
+                    unsigned long long gl = 0, gh = 0;
+                    if (AF) { gl = __shfl_sync(0xffffffffu, nl, from); gh = __shfl_sync(0xffffffffu, nh, from); }
+                    const uint4 *pl = reinterpret_cast<const uint4 *>(pool + pbase);
+                    const unsigned int n8 = (cnt + 7) >> 3;
+                    for (unsigned int k0 = sub; k0 < n8; k0 += 16) {
+                        const uint4 v0 = __ldg(pl + k0);
+                        const uint4 v1 = k0 + 8 < n8 ? __ldg(pl + k0 + 8) : make_uint4(~0u, ~0u, ~0u, ~0u);
+                        const unsigned int ww[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
+                                if (cs != 0xffffu) {
+                                    atomicAdd(s_cnt + cs, 0xffffffffu);
+                                    if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
+                                }
                             }
                         }
                     }
@@ -437,41 +495,15 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             }
         }
         __syncthreads();
-        UT_TICK(t_walk);
-        // ---- pooled rows: 8 lanes per row stream its carrier list (uint16) and decrement every carrier
-        const int qn = min((int)s_qn, cfg.qcap);
-        if (qn > 0) {
-            const int sub = lane & 7, slot = lane >> 3;
-            for (int q0 = warp * 4; q0 < qn; q0 += 32 * 4) {
-                const int q = q0 + slot;
-                if (q < qn) {
-                    const unsigned int pbase = s_queue[3 * q], cnt = s_queue[3 * q + 1];
-                    unsigned long long nl = 0, nh = 0;
-                    if (AF) { const unsigned int r = s_queue[3 * q + 2]; nl = 0ull - p.q_lo[r]; nh = 0ull - p.q_hi[r]; }
-                    for (unsigned int k0 = 0; k0 < cnt; k0 += 32) {
-                        unsigned int c4[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const unsigned int k = k0 + u * 8 + sub;
-                            c4[u] = k < cnt ? (unsigned int)__ldg(pool + pbase + k) : 0xffffffffu;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (c4[u] != 0xffffffffu) {
-                                atomicAdd(s_cnt + c4[u], 0xffffffffu);
-                                if (AF) { atomicAdd(s_lo + c4[u], nl); atomicAdd(s_hi + c4[u], nh); }
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) s_qn = 0;                       // ordered before the next walk by the argmax barrier
+        // every live row of the pick is covered now: its own gain is zero (keeps sum(gains) == live list entries)
+        if (tid == 0) {
+            s_cnt[best_idx] = 0;
+            if (AF) { s_lo[best_idx] = 0; s_hi[best_idx] = 0; }
         }
-        UT_TICK(t_ret);
+        UT_TICK(t_walk);
     }
 #undef UT_TICK
-    if (tid == 0 && p.dbg) { p.dbg[8] += t_arg; p.dbg[9] += t_walk; p.dbg[10] += t_ret; p.dbg[11] += 1; }
+    if (tid == 0 && p.dbg) { p.dbg[8] += t_arg; p.dbg[9] += t_walk; p.dbg[11] += 1; }
 
     __syncthreads();
     for (int i = tid; i < p.S; i += blockDim.x) {
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
 
 int tail_layout(const SelParams &p, TailCfg *cfg, size_t *smem_bytes)
 {
-    if (p.S > 65535 || p.V >= 0xffffffffll) return 0;       // carriers are uint16, rows uint32 in the edge lists
+    if (p.S > 65535 || p.V >= 0xffffffffll) return 0;       // carriers are uint16 (0xffff = padding), rows uint32
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int)o; };
     const size_t S = (size_t)p.S;
@@ -504,18 +536,11 @@ int tail_layout(const SelParams &p, TailCfg *cfg, size_t *smem_bytes)
     cfg->off_loff = take(S * 4);
     cfg->off_llen = take(S * 4);
     const size_t budget = 225 * 1024;
-    if (off + 4096 > budget) return 0;
+    if (off + 1024 > budget) return 0;
     const size_t live_bytes = (size_t)p.colPitchW * 4;
     cfg->live_words = 0;
     cfg->off_live = (int)off;
-    if (off + live_bytes + 4096 <= budget) { cfg->off_live = take(live_bytes); cfg->live_words = (int)p.colPitchW; }
-    size_t q = (budget - off) / 12;
-    if (q > 4096) q = 4096;
-    cfg->qcap = (int)q;
-    cfg->off_queue = take(q * 12);
-    int G = 1;
-    while (G < 32 && (p.pitchW / 4 + G - 1) / G > 8) G <<= 1;
-    cfg->lanes_per_row = G;
+    if (off + live_bytes + 1024 <= budget) { cfg->off_live = take(live_bytes); cfg->live_words = (int)p.colPitchW; }
     cfg->min_recompact = 1u << 16;
     *smem_bytes = off;
     return 1;
@@ -538,14 +563,28 @@ int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, un
                        unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,
                        int *n_launch)
 {
-    UT_CUDA(cudaMemsetAsync(pool_cursor, 0, 4, stream));
     list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.S, list_off, list_len, cursor);
+    *n_launch += 1;
+    EdgeDst d;
+    memset(&d, 0, sizeof(d));
+    d.world = 1;
+    d.lists[0] = lists;
+    d.pool[0] = pool;
+    d.slot_base = list_off;
+    return launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch);
+}
+
+// cursor[S] must be zero; entries go to d.lists[q][slot_base[s] + k] for every q < d.world
+int launch_build_edges(cudaStream_t stream, const SelParams &p, const EdgeDst &d, unsigned int *cursor,
+                       unsigned int *pool_cursor, int *n_launch)
+{
+    UT_CUDA(cudaMemsetAsync(pool_cursor, 0, 4, stream));
     long long blocks = (p.V + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (p.af) build_edges_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p, lists, list_off, cursor, pool, pool_cursor);
-    else build_edges_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p, lists, list_off, cursor, pool, pool_cursor);
-    *n_launch += 2;
+    if (p.af) build_edges_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    else build_edges_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
 }
@@ -570,18 +609,22 @@ int tail_plan(const SelParams &p, int *ok_out)
     return UTMOS_OK;
 }
 
+template <int ESTRIDE, bool FAST>
+static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg &cfg, size_t smem, unsigned long long lists_total)
+{
+    UT_CUDA(cudaFuncSetAttribute(select_tail_kernel<ESTRIDE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_tail_kernel<ESTRIDE, FAST><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
+    return UTMOS_OK;
+}
+
 int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, int *n_launch)
 {
     TailCfg cfg;
     size_t smem = 0;
     if (!tail_layout(p, &cfg, &smem)) { set_error("tail kernel: state does not fit in shared memory"); return UTMOS_E_ARG; }
-    if (p.af) {
-        UT_CUDA(cudaFuncSetAttribute(select_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        select_tail_kernel<2><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
-    } else {
-        UT_CUDA(cudaFuncSetAttribute(select_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        select_tail_kernel<1><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
-    }
+    if (p.af) UT_TRY((launch_tail_t<2, false>(stream, p, cfg, smem, lists_total)));
+    else if (p.weights) UT_TRY((launch_tail_t<1, false>(stream, p, cfg, smem, lists_total)));
+    else UT_TRY((launch_tail_t<1, true>(stream, p, cfg, smem, lists_total)));
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;

@@ -85,17 +85,22 @@ class ShardedMatrix:
     def finalize(self):
         comm = self.comm
         kept = self.local.rows()
-        total = int(comm.all_reduce_sum(np.array([kept], dtype=np.int64))[0])
+        rows_all = comm.all_gather_bytes(np.array([kept], dtype=np.int64).view(np.uint8)).view(np.int64).reshape(-1)
+        total = int(rows_all.sum())
         self.local.set_option(4, total)                       # same fixed-point scale on every rank
         local_vc = self.local.finalize()
         if comm.world > 1:
-            handle = self.local.mgpu_export(comm.rank, comm.world)
-            self.local.mgpu_connect(comm.all_gather_bytes(handle))
             cnt, lo, hi = self.local.get_gains0()
-            cnt = comm.all_reduce_sum(cnt.astype(np.int64)).astype(np.uint32)
+            has_cols = int(self.local.info()["has_sample_major"])
+            summed = comm.all_reduce_sum(np.concatenate([cnt.astype(np.int64), [has_cols]]))
             lo = comm.all_reduce_sum(lo)
             hi = comm.all_reduce_sum(hi)
-            self.local.set_gains0(cnt, lo, hi, total)
+            self.local.set_gains0(summed[:-1].astype(np.uint32), lo, hi, total)
+            # merged row numbering for the hand-over to the replicated tail (every rank's rows padded to 32)
+            padded = (rows_all + 31) // 32 * 32
+            self.local.mgpu_layout(int(padded[:comm.rank].sum()), int(padded.sum()), int(summed[-1]) == comm.world)
+            handle = self.local.mgpu_export(comm.rank, comm.world)
+            self.local.mgpu_connect(comm.all_gather_bytes(handle))
         self.num_vars = total
         self.var_count = comm.all_reduce_sum(np.asarray(local_vc, dtype=np.int64))
         comm.barrier()
