@@ -131,8 +131,14 @@ struct utmos_ctx {
     bool mg_tail = false;              // the merged lists are built: every rank runs the same tail kernel
     unsigned long long mg_list_cap = 0;   // entries of the merged lists region of the exchange block
     unsigned int *d_lcnt = nullptr, *d_my_base = nullptr, *d_pool_base = nullptr;
+    unsigned int *d_local0_cnt = nullptr, *d_local_cnt = nullptr;          // this rank's share of the gains (step 0 / now)
+    unsigned long long *d_local0_lo = nullptr, *d_local0_hi = nullptr, *d_local_lo = nullptr, *d_local_hi = nullptr;
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
-    unsigned int tail_rows = 1536;        // hand over to the single-CTA tail once picks cover fewer rows than this
+    unsigned int tail_rows = 1536;        // hand over to the list-driven tail once picks cover fewer rows than this
+    unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
+                                          // (measured on the 1kGP shape: not faster than one CTA, so off by default)
+    uint32_t *d_live_priv = nullptr;      // private live masks of the cluster flavour when they do not fit in shared memory
+    size_t live_priv_bytes = 0;
     unsigned long long tail_budget = 0;   // handed to the head kernels while the tail flavour waits for sparsity
     unsigned long long total_bits = 0;    // set bits of the scoring rows at step 0
     long long regain_rows = -1;        // -1 = default heuristic
@@ -460,6 +466,14 @@ void free_select_state(utmos_ctx *c)
         c->d_pool = nullptr;
         c->lists_external = false;
     }
+    dev_free(c, c->d_live_priv, c->live_priv_bytes);
+    c->live_priv_bytes = 0;
+    dev_free(c, c->d_local0_cnt, S * 4);
+    dev_free(c, c->d_local_cnt, S * 4);
+    dev_free(c, c->d_local0_lo, S * 8);
+    dev_free(c, c->d_local0_hi, S * 8);
+    dev_free(c, c->d_local_lo, S * 8);
+    dev_free(c, c->d_local_hi, S * 8);
     dev_free(c, c->d_lcnt, S * 4);
     dev_free(c, c->d_my_base, S * 4);
     dev_free(c, c->d_pool_base, 16);
@@ -949,6 +963,13 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
         UT_CUDA(cudaMemcpyAsync(c->d_gain_lo, c->d_gain0_lo, S * 8, cudaMemcpyDeviceToDevice, c->stream));
         UT_CUDA(cudaMemcpyAsync(c->d_gain_hi, c->d_gain0_hi, S * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
+    if (c->d_local0_cnt) {
+        UT_CUDA(cudaMemcpyAsync(c->d_local_cnt, c->d_local0_cnt, S * 4, cudaMemcpyDeviceToDevice, c->stream));
+        if (c->af_mode != UTMOS_AF_NONE) {
+            UT_CUDA(cudaMemcpyAsync(c->d_local_lo, c->d_local0_lo, S * 8, cudaMemcpyDeviceToDevice, c->stream));
+            UT_CUDA(cudaMemcpyAsync(c->d_local_hi, c->d_local0_hi, S * 8, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    }
     SelState st, prev;
     UT_CUDA(cudaMemcpyAsync(&prev, c->d_state, sizeof(prev), cudaMemcpyDeviceToHost, c->stream));
     UT_CUDA(cudaStreamSynchronize(c->stream));
@@ -1038,6 +1059,10 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             m.delta_cnt = c->d_delta_cnt;
             m.delta_lo = c->d_delta_lo;
             m.delta_hi = c->d_delta_hi;
+            m.local_cnt = c->d_local_cnt;
+            m.local_lo = c->d_local_lo;
+            m.local_hi = c->d_local_hi;
+            if (!m.local_cnt) { set_error("select_steps: utmos_set_gains0 must run before a multi-GPU selection"); return UTMOS_E_ARG; }
             char *mine = (char *)c->mg_block;
             m.inbox_cnt = (unsigned int *)(mine + l.off_cnt);
             m.inbox_lo = (unsigned long long *)(mine + l.off_lo);
@@ -1056,7 +1081,19 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         while (true) {
             SelParams q = make_params(c, false);
             if (c->lists_valid) {
-                UT_TRY(launch_tail(c->stream, q, c->lists_total, &c->n_launch));
+                // heavy picks: cluster of 8 CTAs, each applying the decrements of the samples it owns; light picks: one CTA
+                unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
+                uint32_t *live_priv = nullptr;
+                if (single_rows > 0 && !tail_live_in_smem(q)) {
+                    const size_t need = (size_t)kTailCluster * (size_t)q.colPitchW * 4;
+                    if (need > c->live_priv_bytes) {
+                        dev_free(c, c->d_live_priv, c->live_priv_bytes);
+                        UT_TRY(dev_alloc(c, (void **)&c->d_live_priv, need));
+                        c->live_priv_bytes = need;
+                    }
+                    live_priv = c->d_live_priv;
+                }
+                UT_TRY(launch_tail(c->stream, q, c->lists_total, single_rows, live_priv, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 c->flavour_used = multi ? 5 : 3;
             } else if (multi) {
@@ -1303,6 +1340,24 @@ int utmos_set_gains0(utmos_ctx *c, const uint32_t *cnt, const uint64_t *lo, cons
     if (!c || !c->finalized || !cnt) { set_error("set_gains0: bad arguments"); return UTMOS_E_ARG; }
     UT_CUDA(cudaSetDevice(c->device));
     const size_t S = (size_t)c->S;
+    const bool af = c->af_mode != UTMOS_AF_NONE;
+    if (!c->d_local0_cnt) {
+        // keep THIS rank's share of the step-0 gains: the multi-GPU head recomputes shares after heavy picks
+        UT_TRY(dev_alloc(c, (void **)&c->d_local0_cnt, S * 4));
+        UT_TRY(dev_alloc(c, (void **)&c->d_local_cnt, S * 4));
+        if (af) {
+            UT_TRY(dev_alloc(c, (void **)&c->d_local0_lo, S * 8));
+            UT_TRY(dev_alloc(c, (void **)&c->d_local0_hi, S * 8));
+            UT_TRY(dev_alloc(c, (void **)&c->d_local_lo, S * 8));
+            UT_TRY(dev_alloc(c, (void **)&c->d_local_hi, S * 8));
+        }
+        UT_CUDA(cudaMemcpyAsync(c->d_local0_cnt, c->d_gain0_cnt, S * 4, cudaMemcpyDeviceToDevice, c->stream));
+        if (af) {
+            UT_CUDA(cudaMemcpyAsync(c->d_local0_lo, c->d_gain0_lo, S * 8, cudaMemcpyDeviceToDevice, c->stream));
+            UT_CUDA(cudaMemcpyAsync(c->d_local0_hi, c->d_gain0_hi, S * 8, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        UT_CUDA(cudaStreamSynchronize(c->stream));
+    }
     UT_CUDA(cudaMemcpy(c->d_gain0_cnt, cnt, S * 4, cudaMemcpyHostToDevice));
     if (c->af_mode != UTMOS_AF_NONE && lo && hi) {
         UT_CUDA(cudaMemcpy(c->d_gain0_lo, lo, S * 8, cudaMemcpyHostToDevice));
@@ -1337,6 +1392,7 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
     if (option == UTMOS_OPT_GLOBAL_ROWS) { c->global_rows = value; return UTMOS_OK; }
     if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
+    if (option == UTMOS_OPT_TAIL_SINGLE_ROWS) { c->tail_single_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");
     return UTMOS_E_ARG;
 }

@@ -43,6 +43,7 @@ struct SelState {
     unsigned int want_tail;    // head kernel returned because the tail kernel should take over
     unsigned int recompact;    // tail kernel returned because at most half of its list entries are still live
     unsigned int regain;       // 1 = gains are stale: the pick retired too many rows to subtract, recompute them
+    unsigned int tail_single;  // the cluster flavour of the tail kernel handed over to the single-CTA flavour
     unsigned long long mgpu_seq;    // multi-GPU exchange sequence number (monotonic over the selection)
     unsigned long long live_bits;   // sum of all gains = set bits in rows not yet covered (sum_gains_kernel)
 };
@@ -99,6 +100,8 @@ struct MgpuParams {
     unsigned long long seq0;                  // exchange sequence number before the first step of this launch
     unsigned int *delta_cnt;                  // [S] this rank's decrements of the current step (two's complement)
     unsigned long long *delta_lo, *delta_hi;  // [S] AF limbs
+    unsigned int *local_cnt;                  // [S] THIS rank's share of the gains (live rows of its shard per sample)
+    unsigned long long *local_lo, *local_hi;  //     a heavy pick recomputes them by streaming: delta = new - old
     unsigned int *inbox_cnt;                  // [2][world][S] written by the peers (double buffered by step parity)
     unsigned long long *inbox_lo, *inbox_hi;
     unsigned long long *flags;                // [world] last sequence number each peer has published here
@@ -259,7 +262,10 @@ int launch_gather_offsets(cudaStream_t stream, const GatherParams &g, unsigned i
 int launch_gather_live(cudaStream_t stream, const GatherParams &g, const uint32_t *live, int *n_launch);
 int launch_gather_done(cudaStream_t stream, const GatherParams &g, int *n_launch);
 unsigned long long mgpu_pool_share(unsigned long long live_bits);
-int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, int *n_launch);
+constexpr int kTailCluster = 8;     // CTAs of the owner-computes flavour of the tail kernel
+int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int single_rows,
+                uint32_t *live_priv, int *n_launch);
+int tail_live_in_smem(const SelParams &p);
 int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
                 unsigned int *bar_counter, ArgPartial *partials, int *n_launch);
 int mgpu_grid(int device, int *grid_out, int *block_out);

@@ -970,6 +970,7 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
             p.out_idx[step] = b.idx;
             p.out_new[step] = b.cnt;
             p.out_score[step] = b.score;
+            if (p.dbg_time) p.out_time[step] = global_timer_ns();
             p.mask[b.idx] = 0;                             // utmos/select.py:100
         }
         step += 1;
@@ -978,10 +979,60 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
             stop = UTMOS_STOP_ALL;
             break;
         }
-        // ---- B: this rank's newly covered rows -> local delta
+        // ---- B: this rank's newly covered rows -> local delta.  A pick that covers very many rows (the first few:
+        // common variants) is not subtracted bit by bit: the live mask is updated, then this rank's share of every
+        // gain is recomputed by streaming its sample-major copy, and the delta is (new share - old share).
+        const bool regain = p.cols && p.regain_rows && b.cnt >= p.regain_rows * (unsigned int)m.world;
         if (p.V > 0)
-            for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(pd, b.idx, c, lane, true);
+            for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(pd, b.idx, c, lane, !regain);
         if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (regain) {
+            const uint4 *lv = reinterpret_cast<const uint4 *>(p.live);
+            const long long n4 = p.colPitchW / 4;
+            for (int s = blockIdx.x; s < p.S; s += (int)nblocks) {
+                const uint4 *col = reinterpret_cast<const uint4 *>(p.cols + (long long)s * p.colPitchW);
+                unsigned int alive = 0;
+                unsigned long long lo = 0, hi = 0;
+                if (p.V > 0) {
+                    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+                        const uint4 c4 = ld_stream_u128(col + i);
+                        const uint4 l4 = __ldcg(lv + i);
+                        uint32_t w[4] = {c4.x & l4.x, c4.y & l4.y, c4.z & l4.z, c4.w & l4.w};
+                        alive += __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+                        if (p.af) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                uint32_t x = w[u];
+                                while (x) {
+                                    const long long r = (i * 4 + u) * 32 + (__ffs(x) - 1);
+                                    x &= x - 1;
+                                    lo += __ldg(p.q_lo + r);
+                                    hi += __ldg(p.q_hi + r);
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    alive += __shfl_xor_sync(0xffffffffu, alive, o);
+                    if (p.af) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+                }
+                __shared__ unsigned int s_ra[32];
+                __shared__ unsigned long long s_rl[32], s_rh[32];
+                __syncthreads();
+                if (lane == 0) { s_ra[threadIdx.x >> 5] = alive; s_rl[threadIdx.x >> 5] = lo; s_rh[threadIdx.x >> 5] = hi; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned int a = 0;
+                    unsigned long long l = 0, h = 0;
+                    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s_ra[i]; l += s_rl[i]; h += s_rh[i]; }
+                    m.delta_cnt[s] = a - m.local_cnt[s];                 // two's complement, <= 0
+                    if (p.af) { m.delta_lo[s] = l - m.local_lo[s]; m.delta_hi[s] = h - m.local_hi[s]; }
+                }
+            }
+            if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        }
         // ---- C: push the delta into every peer's inbox (NVLink P2P stores), then publish the sequence number
         seq += 1;
         const size_t slot = ((size_t)(seq & 1) * m.world + m.rank) * (size_t)p.S;
@@ -1025,10 +1076,13 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
                 if (p.af) { dl += __ldcv(m.inbox_lo + o); dh += __ldcv(m.inbox_hi + o); }
             }
             if (d) p.gain_cnt[i] += d;
+            m.local_cnt[i] += __ldcg(m.delta_cnt + i);                   // this rank's share follows its own delta
             m.delta_cnt[i] = 0;
             if (p.af) {
                 if (dl) p.gain_lo[i] += dl;
                 if (dh) p.gain_hi[i] += dh;
+                m.local_lo[i] += __ldcg(m.delta_lo + i);
+                m.local_hi[i] += __ldcg(m.delta_hi + i);
                 m.delta_lo[i] = 0;
                 m.delta_hi[i] = 0;
             }

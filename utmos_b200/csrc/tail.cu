@@ -19,11 +19,16 @@
 // re-compacted by a streaming filter pass, so dead entries never dominate.
 //
 // Reference semantics: utmos/select.py:24-53 (scores, mask, weights, argmax, zero stop) and :91-112.
+#include <cooperative_groups.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace utmos {
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -271,6 +276,10 @@ struct TailCfg {
     int off_lo, off_hi, off_w, off_mask, off_loff, off_llen, off_live;   // byte offsets, counts at 0
     int live_words;      // > 0: live mask held in shared memory
     unsigned int min_recompact;   // do not bother re-compacting below this many live entries
+    unsigned int single_rows;     // cluster flavour: hand over to the single-CTA flavour once a pick covers fewer rows
+    uint32_t *live_priv;          // cluster flavour with the live mask in global memory: [CL][colPitchW] private copies
+    int off_stage;                // staging area for the carrier lists of the rows a pick newly covers
+    unsigned int stage_cap;       // ... capacity in chunks (16 bytes = 8 carriers; AF flavours: + 16 bytes of limbs)
 };
 
 // integer argmax for count mode without weights: key = gain count of a selectable sample (0 otherwise);
@@ -284,13 +293,25 @@ __device__ __forceinline__ uint2 warp_argmax_u32(unsigned int key, unsigned int 
 
 // ESTRIDE 1: count entries; 2: AF flavours (second uint4 = fixed-point AF limbs of the row).
 // FAST: count mode without weights -> integer keys (two REDUX per reduction level instead of the float64 path).
-template <int ESTRIDE, bool FAST>
+// CL: 1 = one CTA does everything.  CL > 1 = a thread-block cluster of CL CTAs, "owner computes": a shared-memory
+//     atomic costs ~2 cycles per lane, so while picks still retire thousands of carriers the decrements are the
+//     bottleneck of one SM.  Every CTA of the cluster walks the same list and keeps its own copy of the live
+//     mask (so all CTAs see the same newly covered rows without talking), but applies only the decrements of
+//     the samples it owns (s % CL == rank) and scans only those in the argmax; the CL local winners are
+//     exchanged through distributed shared memory, one hardware cluster barrier per step.
+template <int ESTRIDE, bool FAST, int CL>
 __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailCfg cfg, unsigned long long lists_total)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Cand s_red[32];
     __shared__ unsigned long long s_sum[32];
+    __shared__ uint4 s_xbest[2][16];               // CL > 1: the local winners of every CTA, double buffered by step parity
+    __shared__ unsigned long long s_xsum[16];
     constexpr bool AF = ESTRIDE == 2;
+    int crank = 0;
+    if (CL > 1) crank = (int)cg::this_cluster().block_rank();
+    int xpar = 0;
+    int want_single = 0;
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(smem);
     unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(smem + cfg.off_lo);
     unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(smem + cfg.off_hi);
@@ -299,6 +320,8 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     unsigned int *s_loff = reinterpret_cast<unsigned int *>(smem + cfg.off_loff);
     unsigned int *s_llen = reinterpret_cast<unsigned int *>(smem + cfg.off_llen);
     uint32_t *s_live = reinterpret_cast<uint32_t *>(smem + cfg.off_live);
+    uint4 *s_stage = reinterpret_cast<uint4 *>(smem + cfg.off_stage);
+    __shared__ unsigned int s_stage_n;
     const unsigned short *pool = p.pool;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool has_w = p.weights != nullptr;
@@ -314,13 +337,20 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         if (has_w) s_w[i] = p.weights[i];
     }
     for (int i = tid; i < cfg.live_words; i += blockDim.x) s_live[i] = p.live[i];
+    uint32_t *g_live = p.live;
+    if (CL > 1 && !live_smem) {                       // every CTA of the cluster clears bits in its own copy
+        g_live = cfg.live_priv + (size_t)crank * (size_t)p.colPitchW;
+        for (long long i = tid; i < p.colPitchW; i += blockDim.x) g_live[i] = p.live[i];
+    }
     long long step = st->step, tot = st->tot;
     const long long limit = st->limit;
     int stop = st->stop;
     int recompact = 0;
     int since_check = 0;
+    if (tid == 0) s_stage_n = 0;
     __syncthreads();
     long long t_arg = 0, t_walk = 0, t_mark = clock64();
+    unsigned int n_walked = 0, n_fresh = 0, n_inl = 0, n_pool = 0;       // work counters (profiling, p.dbg[5..7], [12])
 #define UT_TICK(acc) do { const long long now__ = clock64(); acc += now__ - t_mark; t_mark = now__; } while (0)
 
     while (stop == 0 && step < limit) {
@@ -328,7 +358,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         if (++since_check >= 64) {
             since_check = 0;
             unsigned long long acc = 0;
-            for (int i = tid; i < p.S; i += blockDim.x) acc += s_cnt[i];
+            for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) acc += s_cnt[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) s_sum[warp] = acc;
@@ -337,6 +367,15 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) live_now += __shfl_xor_sync(0xffffffffu, live_now, o);
             __syncthreads();
+            if (CL > 1) {                                  // every CTA holds the gains of its own samples only
+                cg::cluster_group cluster = cg::this_cluster();
+                if (tid < CL) cluster.map_shared_rank(s_xsum, tid)[crank] = live_now;
+                cluster.sync();
+                live_now = lane < CL ? s_xsum[lane] : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) live_now += __shfl_xor_sync(0xffffffffu, live_now, o);
+                cluster.sync();                            // s_xsum may be rewritten by the next check
+            }
             if (live_now >= cfg.min_recompact && live_now * 2 <= lists_total && limit - step > 128) {
                 recompact = 1;
                 break;
@@ -348,15 +387,24 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         double best_score;
         if (FAST) {
             unsigned int bk = 0, bi = 0x7fffffffu;
-            for (int i = tid; i < p.S; i += blockDim.x) {
+            for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) {
                 const unsigned int k = s_mask[i] == 1 ? s_cnt[i] : 0u;
                 if (k > bk || bi == 0x7fffffffu) { bk = k; bi = (unsigned int)i; }     // i ascends: first index kept on ties
             }
             const uint2 w = warp_argmax_u32(bk, bi);
             if (lane == 0) *reinterpret_cast<uint2 *>(&s_red[warp]) = w;
             __syncthreads();
-            const uint2 mine = *reinterpret_cast<const uint2 *>(&s_red[lane]);
-            const uint2 b = warp_argmax_u32(mine.x, mine.y);
+            uint2 mine = *reinterpret_cast<const uint2 *>(&s_red[lane]);
+            uint2 b = warp_argmax_u32(mine.x, mine.y);
+            if (CL > 1) {
+                cg::cluster_group cluster = cg::this_cluster();
+                if (tid < CL) cluster.map_shared_rank(&s_xbest[xpar][0], tid)[crank] = make_uint4(b.x, b.y, 0u, 0u);
+                cluster.sync();
+                const uint4 o = lane < CL ? s_xbest[xpar][lane] : make_uint4(0u, 0x7fffffffu, 0u, 0u);
+                xpar ^= 1;
+                mine = make_uint2(o.x, o.y);
+                b = warp_argmax_u32(mine.x, mine.y);
+            }
             const uint2 t2 = warp_argmax_u32(mine.y == b.y ? 0u : mine.x, mine.y == b.y ? 0x7fffffffu : mine.y);
             best_idx = (int)b.y;
             best_cnt = b.x;
@@ -364,7 +412,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             next_idx = t2.x > 0u ? (int)t2.y : 0x7fffffff;
         } else {
             Cand b{0u, 0u, 0x7fffffff, 0u};
-            for (int i = tid; i < p.S; i += blockDim.x) {
+            for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) {
                 const unsigned int c = s_cnt[i];
                 double g = 0.0;
                 if (s_mask[i] == 1) {
@@ -378,8 +426,17 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             b = warp_argmax(b);
             if (lane == 0) s_red[warp] = b;
             __syncthreads();
-            const Cand mine = s_red[lane];
+            Cand mine = s_red[lane];
             b = warp_argmax(mine);
+            if (CL > 1) {
+                cg::cluster_group cluster = cg::this_cluster();
+                if (tid < CL) cluster.map_shared_rank(&s_xbest[xpar][0], tid)[crank] = make_uint4(b.hi, b.lo, (unsigned int)b.idx, b.cnt);
+                cluster.sync();
+                const uint4 o = lane < CL ? s_xbest[xpar][lane] : make_uint4(0u, 0u, 0x7fffffffu, 0u);
+                xpar ^= 1;
+                mine = Cand{o.x, o.y, (int)o.z, o.w};
+                b = warp_argmax(mine);
+            }
             Cand t2 = mine;
             if (mine.idx == b.idx) { t2.hi = 0u; t2.lo = 0u; t2.idx = 0x7fffffff; }
             t2 = warp_argmax(t2);
@@ -392,11 +449,17 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             stop = UTMOS_STOP_ZERO;
             break;
         }
+        if (CL > 1 && best_cnt < cfg.single_rows) {       // light picks: one CTA without a cluster barrier is faster
+            want_single = 1;
+            break;
+        }
         if (tid == 0) {
-            p.out_idx[step] = best_idx;
-            p.out_new[step] = best_cnt;
-            p.out_score[step] = best_score;
-            if (p.dbg_time) p.out_time[step] = global_timer_ns();
+            if (crank == 0) {
+                p.out_idx[step] = best_idx;
+                p.out_new[step] = best_cnt;
+                p.out_score[step] = best_score;
+                if (p.dbg_time) p.out_time[step] = global_timer_ns();
+            }
             s_mask[best_idx] = 0;                         // utmos/select.py:100
         }
         step += 1;
@@ -432,7 +495,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     // a row appears once in a list, so nobody else clears this bit during the walk: test with a plain
                     // load (shared-memory atomics cost ~2 cycles per lane) and clear only the bits that are set
                     const uint32_t bit = 1u << (r & 31);
-                    uint32_t *lw = (live_smem ? s_live : p.live) + (r >> 5);
+                    uint32_t *lw = (live_smem ? s_live : g_live) + (r >> 5);
                     fresh = (*reinterpret_cast<volatile uint32_t *>(lw) & bit) != 0;
                     if (fresh) atomicAnd(lw, ~bit);
                 }
@@ -443,20 +506,56 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     nl = 0ull - (((unsigned long long)qv.y << 32) | qv.x);
                     nh = 0ull - (((unsigned long long)qv.w << 32) | qv.z);
                 }
+                n_walked += r != 0xffffffffu;
+                n_fresh += fresh;
                 if (fresh && n != kPooled) {
+                    n_inl += n;
                     const unsigned int c[kInline] = {e[u].y >> 16, e[u].z & 0xffffu, e[u].z >> 16, e[u].w & 0xffffu,
                                                      e[u].w >> 16};
 #pragma unroll
                     for (int j = 0; j < kInline; ++j) {
-                        if (j < (int)n) {
+                        if (j < (int)n && (CL == 1 || (int)(c[j] % CL) == crank)) {
                             atomicAdd(s_cnt + c[j], 0xffffffffu);
                             if (AF) { atomicAdd(s_lo + c[j], nl); atomicAdd(s_hi + c[j], nh); }
                         }
                     }
                 }
                 // rows with many carriers keep their carrier list (uint16, padded to 8 with 0xffff, 16-byte aligned)
-                // in the pool: the warp retires them here, four rows at a time, 8 lanes x 128-bit loads per row
-                unsigned int m = __ballot_sync(0xffffffffu, fresh && n == kPooled);
+                // in the pool.  The lists of all the rows this pick newly covers are copied into shared memory with
+                // cp.async -- every copy in flight at once, one global round trip whatever the number of rows -- and
+                // retired from there after the walk, flat over all threads.
+                const bool big = fresh && n == kPooled;
+                unsigned int m = 0;
+                if (__any_sync(0xffffffffu, big)) {
+                    const unsigned int n8 = big ? (e[u].w + 7) >> 3 : 0u;
+                    unsigned int incl = n8;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    unsigned int base0 = 0;
+                    if (lane == 31) base0 = atomicAdd(&s_stage_n, incl);
+                    base0 = __shfl_sync(0xffffffffu, base0, 31);
+                    const unsigned int my0 = base0 + incl - n8;
+                    const bool staged = big && my0 + n8 <= cfg.stage_cap;
+                    if (staged) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(pool + e[u].z);
+                        for (unsigned int k = 0; k < n8; ++k) {
+                            uint4 *dst = s_stage + (size_t)(my0 + k) * ESTRIDE;
+                            const unsigned int sa = (unsigned int)__cvta_generic_to_shared(dst);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + k) : "memory");
+                            if (AF) dst[1] = make_uint4((unsigned int)nl, (unsigned int)(nl >> 32), (unsigned int)nh, (unsigned int)(nh >> 32));
+                        }
+                    } else if (big) {
+                        // did not fit: blank the part of the reservation that lies inside the staging area
+                        for (unsigned int k = my0; k < my0 + n8 && k < cfg.stage_cap; ++k)
+                            s_stage[(size_t)k * ESTRIDE] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    }
+                    m = __ballot_sync(0xffffffffu, big && !staged);
+                }
+                // overflow (a pick that covers more carriers than the staging area holds): the warp retires the row from
+                // global memory, four rows at a time, 8 lanes x 128-bit loads per row
                 while (m) {
                     int src = -1;
 #pragma unroll
@@ -484,7 +583,8 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
-                                if (cs != 0xffffu) {
+                                if (cs != 0xffffu && (CL == 1 || (int)(cs % CL) == crank)) {
+                                    n_pool += 1;
                                     atomicAdd(s_cnt + cs, 0xffffffffu);
                                     if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
                                 }
@@ -494,32 +594,82 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                 }
             }
         }
+        // ---- retire the staged carrier lists: one 16-byte chunk (8 carriers) per thread and turn
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        {
+            const unsigned int staged_n = min(s_stage_n, cfg.stage_cap);
+            for (unsigned int c0 = tid; c0 < staged_n; c0 += blockDim.x) {
+                const uint4 v = s_stage[(size_t)c0 * ESTRIDE];
+                unsigned long long gl = 0, gh = 0;
+                if (AF) {
+                    const uint4 qv = s_stage[(size_t)c0 * ESTRIDE + 1];
+                    gl = ((unsigned long long)qv.y << 32) | qv.x;
+                    gh = ((unsigned long long)qv.w << 32) | qv.z;
+                }
+                const unsigned int ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
+                        if (cs != 0xffffu && (CL == 1 || (int)(cs % CL) == crank)) {
+                            n_pool += 1;
+                            atomicAdd(s_cnt + cs, 0xffffffffu);
+                            if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();
         // every live row of the pick is covered now: its own gain is zero (keeps sum(gains) == live list entries)
         if (tid == 0) {
+            s_stage_n = 0;                                // the next walk starts after the argmax barrier
             s_cnt[best_idx] = 0;
             if (AF) { s_lo[best_idx] = 0; s_hi[best_idx] = 0; }
         }
         UT_TICK(t_walk);
     }
 #undef UT_TICK
-    if (tid == 0 && p.dbg) { p.dbg[8] += t_arg; p.dbg[9] += t_walk; p.dbg[11] += 1; }
+    if (tid == 0 && p.dbg && crank == 0) { p.dbg[8] += t_arg; p.dbg[9] += t_walk; p.dbg[11] += 1; }
+    if (p.dbg && crank == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_walked += __shfl_xor_sync(0xffffffffu, n_walked, o);
+            n_fresh += __shfl_xor_sync(0xffffffffu, n_fresh, o);
+            n_inl += __shfl_xor_sync(0xffffffffu, n_inl, o);
+            n_pool += __shfl_xor_sync(0xffffffffu, n_pool, o);
+        }
+        if (lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(p.dbg + 5), (unsigned long long)n_walked);
+            atomicAdd(reinterpret_cast<unsigned long long *>(p.dbg + 6), (unsigned long long)n_fresh);
+            atomicAdd(reinterpret_cast<unsigned long long *>(p.dbg + 7), (unsigned long long)n_inl);
+            atomicAdd(reinterpret_cast<unsigned long long *>(p.dbg + 12), (unsigned long long)n_pool);
+        }
+    }
 
     __syncthreads();
-    for (int i = tid; i < p.S; i += blockDim.x) {
+    for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) {       // every CTA: the samples it owns
         p.gain_cnt[i] = s_cnt[i];
-        p.mask[i] = s_mask[i];
         if (AF) { p.gain_lo[i] = s_lo[i]; p.gain_hi[i] = s_hi[i]; }
     }
-    for (int i = tid; i < cfg.live_words; i += blockDim.x) p.live[i] = s_live[i];
-    if (tid == 0) {
-        st->step = step;
-        st->tot = tot;
-        st->stop = stop;
-        st->winner = -1;
-        st->regain = 0;
-        st->recompact = recompact;
+    if (crank == 0) {
+        for (int i = tid; i < p.S; i += blockDim.x) p.mask[i] = s_mask[i];
+        for (int i = tid; i < cfg.live_words; i += blockDim.x) p.live[i] = s_live[i];
+        if (CL > 1 && !live_smem)
+            for (long long i = tid; i < p.colPitchW; i += blockDim.x) p.live[i] = g_live[i];
+        if (tid == 0) {
+            st->step = step;
+            st->tot = tot;
+            st->stop = stop;
+            st->winner = -1;
+            st->regain = 0;
+            st->recompact = recompact;
+            if (want_single) st->tail_single = 1;
+        }
     }
+    if (CL > 1) cg::this_cluster().sync();           // nobody leaves while a peer may still write into its shared memory
 }
 
 int tail_layout(const SelParams &p, TailCfg *cfg, size_t *smem_bytes)
@@ -536,12 +686,19 @@ int tail_layout(const SelParams &p, TailCfg *cfg, size_t *smem_bytes)
     cfg->off_loff = take(S * 4);
     cfg->off_llen = take(S * 4);
     const size_t budget = 225 * 1024;
-    if (off + 1024 > budget) return 0;
+    if (off + 8 * 1024 > budget) return 0;
     const size_t live_bytes = (size_t)p.colPitchW * 4;
     cfg->live_words = 0;
     cfg->off_live = (int)off;
-    if (off + live_bytes + 1024 <= budget) { cfg->off_live = take(live_bytes); cfg->live_words = (int)p.colPitchW; }
+    // the live mask goes to shared memory when it leaves at least 16 KB for the staging area
+    if (off + live_bytes + 16 * 1024 <= budget) { cfg->off_live = take(live_bytes); cfg->live_words = (int)p.colPitchW; }
+    const size_t chunk = p.af ? 32 : 16;
+    size_t stage = std::min<size_t>(budget - off, 64 * 1024) / chunk;
+    cfg->off_stage = take(stage * chunk);
+    cfg->stage_cap = (unsigned int)stage;
     cfg->min_recompact = 1u << 16;
+    cfg->single_rows = 0;
+    cfg->live_priv = nullptr;
     *smem_bytes = off;
     return 1;
 }
@@ -609,22 +766,57 @@ int tail_plan(const SelParams &p, int *ok_out)
     return UTMOS_OK;
 }
 
-template <int ESTRIDE, bool FAST>
+// does the tail kernel keep the live mask of `p` in shared memory?  (else the cluster flavour needs kTailCluster
+// private copies of p.colPitchW words in global memory)
+int tail_live_in_smem(const SelParams &p)
+{
+    TailCfg cfg;
+    size_t smem = 0;
+    return tail_layout(p, &cfg, &smem) && cfg.live_words > 0;
+}
+
+template <int ESTRIDE, bool FAST, int CL>
 static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg &cfg, size_t smem, unsigned long long lists_total)
 {
-    UT_CUDA(cudaFuncSetAttribute(select_tail_kernel<ESTRIDE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    select_tail_kernel<ESTRIDE, FAST><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
+    UT_CUDA(cudaFuncSetAttribute(select_tail_kernel<ESTRIDE, FAST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CL == 1) {
+        select_tail_kernel<ESTRIDE, FAST, CL><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
+        return UTMOS_OK;
+    }
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(CL);
+    lc.blockDim = dim3(1024);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    UT_CUDA(cudaLaunchKernelEx(&lc, select_tail_kernel<ESTRIDE, FAST, CL>, p, cfg, lists_total));
     return UTMOS_OK;
 }
 
-int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, int *n_launch)
+// single_rows > 0: the cluster flavour (8 CTAs, owner computes), which returns with st->tail_single set once a pick
+// covers fewer than single_rows rows; single_rows == 0: the single-CTA flavour.
+int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int single_rows,
+                uint32_t *live_priv, int *n_launch)
 {
     TailCfg cfg;
     size_t smem = 0;
     if (!tail_layout(p, &cfg, &smem)) { set_error("tail kernel: state does not fit in shared memory"); return UTMOS_E_ARG; }
-    if (p.af) UT_TRY((launch_tail_t<2, false>(stream, p, cfg, smem, lists_total)));
-    else if (p.weights) UT_TRY((launch_tail_t<1, false>(stream, p, cfg, smem, lists_total)));
-    else UT_TRY((launch_tail_t<1, true>(stream, p, cfg, smem, lists_total)));
+    cfg.single_rows = single_rows;
+    cfg.live_priv = live_priv;
+    if (single_rows > 0 && cfg.live_words == 0 && !live_priv) { set_error("tail kernel: cluster flavour needs private live masks"); return UTMOS_E_ARG; }
+    if (single_rows > 0) {
+        if (p.af) UT_TRY((launch_tail_t<2, false, 8>(stream, p, cfg, smem, lists_total)));
+        else if (p.weights) UT_TRY((launch_tail_t<1, false, 8>(stream, p, cfg, smem, lists_total)));
+        else UT_TRY((launch_tail_t<1, true, 8>(stream, p, cfg, smem, lists_total)));
+    } else {
+        if (p.af) UT_TRY((launch_tail_t<2, false, 1>(stream, p, cfg, smem, lists_total)));
+        else if (p.weights) UT_TRY((launch_tail_t<1, false, 1>(stream, p, cfg, smem, lists_total)));
+        else UT_TRY((launch_tail_t<1, true, 1>(stream, p, cfg, smem, lists_total)));
+    }
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
