@@ -12,6 +12,7 @@
  *
  *   utmos_append_packed        utmos/select.py:272-280   np.unpackbits + .any(axis=1) filter of one .jl part
  *   utmos_append_dense_u8/f32  utmos/select.py:37        row iteration of the hdf5 'data' dataset
+ *   utmos_append_h5_chunks     utmos/select.py:250-251, :37   the same, chunks read + LZF-decoded natively
  *                              utmos/select.py:219-231   (bool, or float32 GT*AF flavour)
  *   utmos_finalize             utmos/select.py:281-284   var_count column sums; :314-320 concat / AF matrix
  *   utmos_select_begin         utmos/select.py:168-187   sample_mask / sample_weights hand-over
@@ -93,6 +94,18 @@ int utmos_append_packed_device(utmos_ctx *ctx, const uint8_t *d_rows, int64_t n_
  */
 int utmos_append_dense_u8(utmos_ctx *ctx, const uint8_t *chunk, int64_t n_rows);
 int utmos_append_dense_f32(utmos_ctx *ctx, const float *chunk, int64_t n_rows);
+
+/*
+ * hdf5 chunk streamer (utmos/select.py:250-251 re-using a --lowmem file; :37 iterating its rows): the host side
+ * (utmos_b200/h5lite.py) walks the chunk B-tree and passes the byte range of every chunk of the 'data' dataset in
+ * row order; the library reads them (pread), LZF-decodes them with `threads` host threads (0 = all cores) straight
+ * into its pinned staging buffers and overlaps decode, H2D copy and the packing kernels.  rows_per_chunk x S
+ * elements per chunk (bool bytes, or float32 GT*AF when is_f32); total_rows trims the last, partial chunk;
+ * lzf = 0 when the dataset has no filter; fmask bit 0 = this chunk is stored raw.
+ */
+int utmos_append_h5_chunks(utmos_ctx *ctx, const char *path, int64_t n_chunks, const int64_t *addr,
+                           const int64_t *nbytes, const uint32_t *fmask, int64_t rows_per_chunk, int64_t total_rows,
+                           int is_f32, int lzf, int threads);
 
 /*
  * Close ingestion: builds the sample-major copy (unless it does not fit / is disabled), the per-sample

@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle, the reference's answer keys and
 the outputs recorded from the unmodified reference.  Integer work is compared bit-exactly; --af scores
 bit-exactly against the exact-arithmetic oracle and within 1e-9 relative of the reference's float64 sums."""
+import functools
 import io
 import os
 
@@ -353,6 +354,45 @@ def test_synthetic_reduced_shape_vs_c_oracle(use_af, flags):
     assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
     dm.close()
     coh.close()
+
+
+@pytest.mark.parametrize("use_af", [False, True], ids=["count", "af"])
+@pytest.mark.parametrize("weighted", [False, True], ids=["plain", "weights"])
+@pytest.mark.parametrize("single_rows,tail_rows", [(1, 1 << 30), (64, 1 << 30), (0, 1 << 30), (32, 512)],
+                         ids=["cluster_tail_only", "cluster_then_single", "single_tail_from_step0", "cluster_late"])
+def test_tail_flavours_vs_c_oracle(use_af, weighted, single_rows, tail_rows):
+    """The list-driven tail from the very first pick (heavy picks: the staging area overflows into the direct
+    path) in its one-CTA flavour and in the 8-CTA owner-computes cluster flavour, against the exact oracle."""
+    n_vars, n_samples = 30000, 1777
+    coh = synth.DeviceCohort(3, n_vars, n_samples)
+    wts = synth.synthetic_weights(n_samples) if weighted else None
+    mask = np.ones(n_samples, np.uint8)
+    mask[5::89] = 2
+    dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE)
+    dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
+    dm.finalize()
+    dm.set_option(3, tail_rows)
+    dm.set_option(5, single_rows)
+    dm.begin(mask, wts)
+    i1, n1, s1, _ = dm.steps(150)
+    i2, n2, s2, _ = dm.steps(n_samples)
+    idx, new, score = np.concatenate([i1, i2]), np.concatenate([n1, n2]), np.concatenate([s1, s2])
+    assert dm.info()["flavour"] == 3
+    o_idx, o_new, o_score = _tail_case_oracle(use_af, weighted)
+    assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
+    dm.close()
+    coh.close()
+
+
+@functools.lru_cache(maxsize=None)
+def _tail_case_oracle(use_af, weighted):
+    n_vars, n_samples = 30000, 1777
+    gt, af = synth.mirror_rows(3, 0, n_vars, n_samples)
+    wts = synth.synthetic_weights(n_samples) if weighted else None
+    mask = np.ones(n_samples, np.uint8)
+    mask[5::89] = 2
+    o_idx, o_new, o_score, _ = orc.greedy_c(gt, n_samples, mask, wts, af if use_af else None, n_samples, exact=True)
+    return o_idx, o_new, o_score
 
 
 def test_full_shape_properties_and_mode_agreement():

@@ -77,6 +77,26 @@ def test_h5lite_reads_reference_fixtures():
         assert np.array_equal(h5["var_count"].read(), var_count)
 
 
+@pytest.mark.parametrize("name", ["tiny.hdf5", "tiny.af.hdf5"])
+def test_h5lite_chunk_table_feeds_the_native_streamer(name):
+    """The byte ranges handed to utmos_append_h5_chunks decode to exactly the blocks iter_chunks yields."""
+    with h5lite.H5File(H.fixture(name)) as h5:
+        dset = h5["data"]
+        addr, nbytes, fmask = dset.chunk_table()
+        rows, n_samples = dset.chunks
+        assert dset.has_lzf and len(addr) * rows >= dset.shape[0] and n_samples == dset.shape[1]
+        chunk_bytes = rows * n_samples * dset.dtype.itemsize
+        blocks = list(dset.iter_chunks())
+        assert len(blocks) == len(addr)
+        with open(H.fixture(name), "rb") as fh:
+            for (first, block), a, n, m in zip(blocks, addr, nbytes, fmask):
+                fh.seek(int(a))
+                raw = fh.read(int(n))
+                full = np.frombuffer(raw, np.uint8) if m & 1 else _native.lzf_decompress(raw, chunk_bytes)
+                got = full.view(dset.dtype).reshape(rows, n_samples)[:block.shape[0]]
+                assert np.array_equal(got, block), first
+
+
 @pytest.mark.parametrize("name", ["chunk0", "chunk1"])
 def test_vcf_reader_and_convert_oracle_reproduce_fixture_jl(name):
     """chunkN.vcf.gz -> GT bits and het/hom stats of chunkN.jl (AF: fixture holds the older definition)."""

@@ -19,7 +19,7 @@ E_NOGPU = -3
 # every symbol include/utmos_b200.h declares (tests check the library exports all of them)
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
-           "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_finalize", "utmos_select_begin",
+           "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_append_h5_chunks", "utmos_finalize", "utmos_select_begin",
            "utmos_select_steps", "utmos_convert_gt", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
            "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_device_alloc", "utmos_device_free",
@@ -60,6 +60,7 @@ def lib():
         "utmos_append_packed_device": (i32, [p, p, i64, i64, p]),
         "utmos_append_dense_u8": (i32, [p, p, i64]),
         "utmos_append_dense_f32": (i32, [p, p, i64]),
+        "utmos_append_h5_chunks": (i32, [p, ctypes.c_char_p, i64, p, p, p, i64, i64, i32, i32, i32]),
         "utmos_finalize": (i32, [p, ctypes.POINTER(i64), p]),
         "utmos_select_begin": (i32, [p, p, p]),
         "utmos_select_steps": (i32, [p, i64, p, p, p, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
@@ -190,6 +191,15 @@ class DeviceMatrix:
         else:
             chunk = np.ascontiguousarray(chunk).view(np.uint8)
             check(lib().utmos_append_dense_u8(self._ctx, _ptr(chunk), chunk.shape[0]))
+
+    def append_h5_chunks(self, path, addr, nbytes, fmask, rows_per_chunk, total_rows, is_f32, lzf=True, threads=0):
+        """Chunks of an hdf5 'data' dataset (byte ranges in row order), read and LZF-decoded by native host threads."""
+        addr = np.ascontiguousarray(addr, dtype=np.int64)
+        nbytes = np.ascontiguousarray(nbytes, dtype=np.int64)
+        fmask = np.ascontiguousarray(fmask, dtype=np.uint32)
+        check(lib().utmos_append_h5_chunks(self._ctx, os.fsencode(path), len(addr), _ptr(addr), _ptr(nbytes), _ptr(fmask),
+                                           int(rows_per_chunk), int(total_rows), 1 if is_f32 else 0, 1 if lzf else 0,
+                                           int(threads)))
 
     def finalize(self):
         """Close ingestion; returns var_count (int64[S])."""

@@ -9,11 +9,15 @@
 //   live0/live uint32 [colPitchW]    scoring rows at step 0 / rows not yet covered
 //   gain0_* / gain_*  [S]            per-sample gains at step 0 / current
 //   mask u8[S], weights f64[S], out_{idx,new,score}[S], SelState
+#include <fcntl.h>
 #include <math.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 
 #include "common.cuh"
 
@@ -821,6 +825,88 @@ int utmos_append_dense_f32(utmos_ctx *c, const float *chunk, int64_t n_rows)
     if (c->af_mode == UTMOS_AF_NONE) { set_error("append_dense_f32: float data needs an AF context"); return UTMOS_E_ARG; }
     UT_CUDA(cudaSetDevice(c->device));
     return append_host(c, RAW_DENSE_F32, chunk, n_rows, c->S * 4, nullptr);
+}
+
+// hdf5 chunk streamer: the chunks of the 'data' dataset are read (pread) and LZF-decoded by `threads` host threads
+// straight into the pinned staging buffers, one staging buffer of chunks at a time; the H2D copy and the packing
+// kernels of batch i run on the copy / compute streams while the host decodes batch i+1 into the other buffer.
+int utmos_append_h5_chunks(utmos_ctx *c, const char *path, int64_t n_chunks, const int64_t *addr, const int64_t *nbytes,
+                           const uint32_t *fmask, int64_t rows_per_chunk, int64_t total_rows, int is_f32, int lzf,
+                           int threads)
+{
+    if (!c || !path || n_chunks < 0 || (n_chunks > 0 && (!addr || !nbytes || !fmask)) || rows_per_chunk <= 0 || total_rows < 0) {
+        set_error("append_h5_chunks: bad arguments");
+        return UTMOS_E_ARG;
+    }
+    if (c->finalized) { set_error("append after finalize"); return UTMOS_E_ARG; }
+    if ((is_f32 != 0) != (c->af_mode != UTMOS_AF_NONE)) { set_error("append_h5_chunks: data type does not match the context's af_mode"); return UTMOS_E_ARG; }
+    if (n_chunks == 0 || total_rows == 0) return UTMOS_OK;
+    UT_CUDA(cudaSetDevice(c->device));
+    const int kind = is_f32 ? RAW_DENSE_F32 : RAW_DENSE_U8;
+    const size_t row_bytes = (size_t)c->S * (is_f32 ? 4 : 1);
+    const size_t chunk_bytes = row_bytes * (size_t)rows_per_chunk;
+    if (chunk_bytes > kStageBytes) { set_error("append_h5_chunks: one chunk exceeds the staging buffer"); return UTMOS_E_ARG; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_error(std::string("append_h5_chunks: cannot open ") + path); return UTMOS_E_ARG; }
+    const long long per_batch = (long long)(kStageBytes / chunk_bytes);
+    int rc = grow_rows(c, c->rows_upper + total_rows);
+    if (rc == UTMOS_OK) rc = ensure_stage(c, is_f32 ? per_batch * rows_per_chunk : 0, true);
+    const int nthreads = std::max(1, std::min(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), 64));
+    long long rows_left = total_rows;
+    for (long long c0 = 0; c0 < n_chunks && rc == UTMOS_OK && rows_left > 0; c0 += per_batch) {
+        const long long k = std::min(per_batch, (long long)n_chunks - c0);
+        const int b = c->stage_next;
+        c->stage_next ^= 1;
+        if (c->stage_used[b]) {
+            if (cudaEventSynchronize(c->ev_consumed[b]) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaEventSynchronize", __FILE__, __LINE__); break; }
+            cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0);
+        }
+        uint8_t *dst = (uint8_t *)c->h_stage[b];
+        std::atomic<long long> next(0);
+        std::atomic<int> bad(0);
+        auto worker = [&]() {
+            std::vector<uint8_t> raw;
+            for (;;) {
+                const long long i = next.fetch_add(1);
+                if (i >= k || bad.load()) return;
+                const long long ci = c0 + i;
+                uint8_t *out = dst + (size_t)i * chunk_bytes;
+                const bool stored_raw = !lzf || (fmask[ci] & 1u);
+                if (stored_raw) {
+                    if (nbytes[ci] != (int64_t)chunk_bytes || pread(fd, out, chunk_bytes, addr[ci]) != (ssize_t)chunk_bytes) { bad.store(1); return; }
+                } else {
+                    raw.resize((size_t)nbytes[ci]);
+                    if (pread(fd, raw.data(), raw.size(), addr[ci]) != (ssize_t)raw.size() ||
+                        utmos_lzf_decompress(raw.data(), (int64_t)raw.size(), out, (int64_t)chunk_bytes) != (int64_t)chunk_bytes) { bad.store(1); return; }
+                }
+            }
+        };
+        {
+            std::vector<std::thread> pool;
+            const int nt = (int)std::min<long long>(nthreads, k);
+            for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &t : pool) t.join();
+        }
+        if (bad.load()) { set_error("append_h5_chunks: short read or malformed LZF chunk"); rc = UTMOS_E_DATA; break; }
+        const long long n = std::min(rows_left, k * rows_per_chunk);          // the last chunk is stored full size
+        const size_t bytes = (size_t)n * row_bytes;
+        t_begin(c, T_H2D, c->copy_stream);
+        if (cudaMemcpyAsync(c->d_stage[b], dst, bytes, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync", __FILE__, __LINE__); break; }
+        t_end(c, c->copy_stream);
+        cudaEventRecord(c->ev_copied[b], c->copy_stream);
+        cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0);
+        t_begin(c, T_INGEST, c->stream);
+        rc = launch_ingest(c->stream, c->scratch, kind, c->d_stage[b], n, (long long)row_bytes, is_f32 ? c->d_af_stage[b] : nullptr,
+                           (int)c->S, c->pitchW, c->d_rows, is_f32 ? c->d_af : nullptr, c->d_nrows, &c->n_launch);
+        t_end(c, c->stream);
+        cudaEventRecord(c->ev_consumed[b], c->stream);
+        c->stage_used[b] = true;
+        c->rows_upper += n;
+        rows_left -= n;
+    }
+    close(fd);
+    return rc;
 }
 
 int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)

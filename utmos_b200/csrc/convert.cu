@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) gt_pack_af_kernel(const int8_t *__restric
 // alleles >= 2 go to a per-warp shared histogram.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCvtWarps = 8;
-constexpr size_t kCvtSmemRaw = 96 * 1024;
+constexpr size_t kCvtSmemRaw = 96 * 1024;        // largest row (2S bytes) the fast path stages
+constexpr size_t kCvtTileBytes = 40 * 1024;      // preferred tile: 5 CTAs per SM overlap their load and compute phases
 
 __device__ __forceinline__ uint32_t cvt_le32(const uint32_t *s32, unsigned int o)
 {
@@ -162,24 +163,35 @@ __global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const i
             unsigned int an = 0, zero = 0, one = 0, het = 0, hom = 0;
             bool rare = false;
             for (int s0 = lane * 8; s0 < S; s0 += 256) {
-                uint32_t w[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) w[k] = cvt_le32(s32, o + 2u * s0 + 4u * k);
                 uint32_t byte = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t pair = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-                    const int g0 = (int)(int8_t)(pair & 0xffu), g1 = (int)(int8_t)(pair >> 8);
-                    if (s0 + j < S) {
-                        if (g0 >= 0) { an += 1; if (g0 == 0) zero += 1; else if (g0 == 1) one += 1; else { rare = true; atomicAdd(&s_hist[warp][g0], 1u); } }
-                        if (g1 >= 0) { an += 1; if (g1 == 0) zero += 1; else if (g1 == 1) one += 1; else { rare = true; atomicAdd(&s_hist[warp][g1], 1u); } }
-                        const bool called = g0 >= 0 && g1 >= 0;
-                        const bool is_het = called && g0 != g1;
-                        const bool is_hom = called && g0 == g1 && g0 > 0;
-                        het += is_het ? 1u : 0u;
-                        hom += is_hom ? 1u : 0u;
-                        if (is_het || is_hom) byte |= 0x80u >> j;
+                for (int k = 0; k < 4; ++k) {
+                    // word k = samples s0+2k (bytes 0,1) and s0+2k+1 (bytes 2,3); SIMD-in-register byte compares
+                    uint32_t v = cvt_le32(s32, o + 2u * s0 + 4u * k);
+                    if (s0 + 2 * k >= S) v = 0xffffffffu;                     // past the row: missing
+                    else if (s0 + 2 * k + 1 >= S) v |= 0xffff0000u;
+                    const uint32_t called = ~v & 0x80808080u;                 // bit 7 of every called allele byte
+                    an += __popc(called);
+                    zero += __popc(__vcmpeq4(v, 0u) & 0x01010101u);
+                    one += __popc(__vcmpeq4(v, 0x01010101u) & 0x01010101u);
+                    if (__vcmpgts4(v, 0x01010101u)) {                         // alleles >= 2: rare, per-warp histogram
+                        rare = true;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int g = (int)(int8_t)(v >> (8 * e));
+                            if (g >= 2) atomicAdd(&s_hist[warp][g], 1u);
+                        }
                     }
+                    const uint32_t both = called & __byte_perm(called, 0u, 0x2301);        // both alleles of a sample called
+                    const uint32_t eq = __vcmpeq4(v, __byte_perm(v, 0u, 0x2301));          // 0xff.. where allele0 == allele1
+                    const uint32_t pos = __vcmpgts4(v, 0u);                                // 0xff where allele > 0
+                    const uint32_t het_b = both & ~eq & 0x00800080u;                       // bit 7 / bit 23: sample 2k / 2k+1
+                    const uint32_t hom_b = both & eq & pos & 0x00800080u;
+                    het += __popc(het_b);
+                    hom += __popc(hom_b);
+                    const uint32_t pr = het_b | hom_b;
+                    byte |= ((pr >> 7) & 1u) << (7 - 2 * k);
+                    byte |= ((pr >> 23) & 1u) << (6 - 2 * k);
                 }
                 out[s0 >> 3] = (uint8_t)byte;
             }
@@ -221,7 +233,8 @@ int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S,
 {
     if (V <= 0) return UTMOS_OK;
     if (ploidy == 2 && ((uintptr_t)gt & 15u) == 0 && 2ull * (size_t)S + 64 <= kCvtSmemRaw && pitch_out == (S + 7) / 8) {
-        int R = (int)std::min<size_t>(64, (kCvtSmemRaw - 64) / (2 * (size_t)S));
+        const size_t tile_budget = std::max(kCvtTileBytes, 2 * (size_t)S + 64);
+        int R = (int)std::min<size_t>(64, (tile_budget - 64) / (2 * (size_t)S));
         if (R > kCvtWarps) R = R / kCvtWarps * kCvtWarps;           // whole rounds of one row per warp
         const size_t smem = ((size_t)R * 2 * (size_t)S + 31) / 16 * 16 + 48;
         static bool configured = false;

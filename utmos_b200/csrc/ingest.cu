@@ -341,6 +341,76 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
         for (int k = tid; k < (int)total; k += kThreads) af_out[base + k] = af_in[row0 + s_src[k]];
 }
 
+// ------------------------------------------------------------------------------------------------
+// dense hdf5 rows (bool bytes, or float32 GT*AF).  Every row is kept (the file was filtered when it was written),
+// so there is nothing to compact: one thread packs 32 consecutive samples of one row into one output word,
+// neighbouring threads take neighbouring words (a warp reads 1 KB / 4 KB of contiguous input).  The float flavour
+// also recovers the row's AF (all nonzero entries of a GT*AF row are equal, select.py:222): order-preserving
+// atomicMax on the float bits, converted to float64 by a second, tiny kernel.
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_dense_kernel(const void *__restrict__ raw, long long n_rows, int S, int pitchW,
+                                                         const long long *d_nrows, uint32_t *__restrict__ rows_out,
+                                                         unsigned int *__restrict__ af_bits)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = idx / pitchW;
+    if (r >= n_rows) return;
+    const int w = (int)(idx - r * pitchW);
+    const int s0 = w * 32;
+    uint32_t word = 0;
+    if (s0 < S) {
+        const int n = min(32, S - s0);
+        if (KIND == RAW_DENSE_U8) {
+            const uint8_t *src = (const uint8_t *)raw + r * (long long)S + s0;
+            if (n == 32 && (((uintptr_t)src) & 15u) == 0) {
+                const uint4 a = ld_stream_u128(reinterpret_cast<const uint4 *>(src));
+                const uint4 b = ld_stream_u128(reinterpret_cast<const uint4 *>(src) + 1);
+                const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    // nonzero bytes -> one bit each (byte j of word k is sample 4k+j)
+                    const uint32_t nz = __vcmpne4(v[k], 0u);                 // 0xff per nonzero byte
+                    const uint32_t bits = ((nz & 0x01u)) | ((nz >> 7) & 0x02u) | ((nz >> 14) & 0x04u) | ((nz >> 21) & 0x08u);
+                    word |= bits << (4 * k);
+                }
+            } else {
+                for (int j = 0; j < n; ++j) word |= (__ldg(src + j) != 0 ? 1u : 0u) << j;
+            }
+        } else {
+            const float *src = (const float *)raw + r * (long long)S + s0;
+            float vmax = 0.0f;
+            if (n == 32 && (((uintptr_t)src) & 15u) == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 a = ld_stream_u128(reinterpret_cast<const uint4 *>(src) + k);
+                    const float f[4] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w)};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (f[j] != 0.0f) { word |= 1u << (4 * k + j); vmax = fmaxf(vmax, f[j]); }
+                    }
+                }
+            } else {
+                for (int j = 0; j < n; ++j) {
+                    const float f = __ldg(src + j);
+                    if (f != 0.0f) { word |= 1u << j; vmax = fmaxf(vmax, f); }
+                }
+            }
+            // positive floats compare like their bit patterns; negative / NaN entries make the AF check at finalize fail
+            if (word && af_bits) atomicMax(af_bits + r, __float_as_uint(vmax));
+        }
+    }
+    rows_out[(*d_nrows + r) * pitchW + w] = word;
+}
+
+__global__ void dense_af_kernel(const unsigned int *af_bits, long long n_rows, const long long *d_nrows, double *af_out)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) af_out[*d_nrows + r] = (double)__uint_as_float(af_bits[r]);
+}
+
+__global__ void bump_rows_by_kernel(long long *d_nrows, long long n) { *d_nrows += n; }
+
 __global__ void bump_rows_kernel(long long *d_nrows, const long long *d_chunk_total) { *d_nrows += *d_chunk_total; }
 
 }  // namespace
@@ -350,7 +420,7 @@ int ingest_scratch_reserve(IngestScratch &sc, long long rows, cudaStream_t strea
     if (rows <= sc.cap_rows) return UTMOS_OK;
     ingest_scratch_free(sc, stream);
     const long long nb = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
-    UT_CUDA(cudaMallocAsync(&sc.flags, (size_t)rows, stream));
+    UT_CUDA(cudaMallocAsync(&sc.flags, (size_t)rows * 4, stream));      // bytes: row flags; dense float flavour: one uint32 per row
     UT_CUDA(cudaMallocAsync(&sc.block_counts, sizeof(unsigned int) * (size_t)nb, stream));
     UT_CUDA(cudaMallocAsync(&sc.block_offsets, sizeof(unsigned int) * (size_t)nb, stream));
     UT_CUDA(cudaMallocAsync(&sc.tile_state, sizeof(unsigned long long) * (size_t)(rows + 2), stream));
@@ -412,6 +482,23 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
             rows_out, af_out);
         bump_rows_kernel<<<1, 1, 0, stream>>>(d_nrows, d_total);
         *n_launch += 2;
+        UT_CUDA(cudaGetLastError());
+        return UTMOS_OK;
+    }
+    if (kind == RAW_DENSE_U8 || kind == RAW_DENSE_F32) {
+        const long long items = n_rows * pitchW;
+        const unsigned grid = (unsigned)((items + 255) / 256);
+        if (kind == RAW_DENSE_U8) {
+            pack_dense_kernel<RAW_DENSE_U8><<<grid, 256, 0, stream>>>(raw, n_rows, S, pitchW, d_nrows, rows_out, nullptr);
+            *n_launch += 2;
+        } else {
+            unsigned int *af_bits = reinterpret_cast<unsigned int *>(sc.flags);     // scratch: >= 4 bytes per row (see reserve)
+            UT_CUDA(cudaMemsetAsync(af_bits, 0, (size_t)n_rows * 4, stream));
+            pack_dense_kernel<RAW_DENSE_F32><<<grid, 256, 0, stream>>>(raw, n_rows, S, pitchW, d_nrows, rows_out, af_bits);
+            dense_af_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(af_bits, n_rows, d_nrows, af_out);
+            *n_launch += 3;
+        }
+        bump_rows_by_kernel<<<1, 1, 0, stream>>>(d_nrows, n_rows);
         UT_CUDA(cudaGetLastError());
         return UTMOS_OK;
     }

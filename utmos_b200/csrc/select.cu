@@ -14,6 +14,7 @@
 //           K4  argmax (argmax_step_kernel, or phase A of the persistent kernel)
 //           K5  cover (cover_step_kernel, or phase B of the persistent kernel)
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -894,6 +895,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     return v;
 }
 
+template <bool CLUSTER>
+__device__ __forceinline__ bool mgpu_barrier(unsigned int *counter, unsigned int *epoch, unsigned int nblocks,
+                                             unsigned int *abort_flag, int *s_flag)
+{
+    if (CLUSTER) {
+        cg::this_cluster().sync();
+        return true;
+    }
+    return grid_barrier(counter, epoch, nblocks, abort_flag, s_flag);
+}
+
+// CLUSTER: the CTAs of this GPU form ONE thread-block cluster and meet at the hardware cluster barrier (about 1 us)
+// instead of a grid-wide barrier through L2 (about 5 us with the spin on one address); the loop has 4-5 barriers per step.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuParams m, unsigned int *bar_counter,
                                                               ArgPartial *partials)
 {
@@ -940,7 +955,7 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
             for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a.sum += s_sumw[i];
             partials[blockIdx.x] = a;
         }
-        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (!mgpu_barrier<CLUSTER>(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
         Best t{-1.0e308, 0x7fffffff, 0u};
         unsigned long long live_now = 0;
         for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x) {
@@ -985,16 +1000,17 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
         const bool regain = p.cols && p.regain_rows && b.cnt >= p.regain_rows * (unsigned int)m.world;
         if (p.V > 0)
             for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(pd, b.idx, c, lane, !regain);
-        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (!mgpu_barrier<CLUSTER>(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
         if (regain) {
             const uint4 *lv = reinterpret_cast<const uint4 *>(p.live);
             const long long n4 = p.colPitchW / 4;
-            for (int s = blockIdx.x; s < p.S; s += (int)nblocks) {
-                const uint4 *col = reinterpret_cast<const uint4 *>(p.cols + (long long)s * p.colPitchW);
+            // one warp per sample: 128-bit streaming loads of its column, shuffle reduction, no block-level sync
+            for (long long s = warp0; s < p.S; s += nwarps) {
+                const uint4 *col = reinterpret_cast<const uint4 *>(p.cols + s * p.colPitchW);
                 unsigned int alive = 0;
                 unsigned long long lo = 0, hi = 0;
                 if (p.V > 0) {
-                    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+                    for (long long i = lane; i < n4; i += 32) {
                         const uint4 c4 = ld_stream_u128(col + i);
                         const uint4 l4 = __ldcg(lv + i);
                         uint32_t w[4] = {c4.x & l4.x, c4.y & l4.y, c4.z & l4.z, c4.w & l4.w};
@@ -1018,20 +1034,12 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
                     alive += __shfl_xor_sync(0xffffffffu, alive, o);
                     if (p.af) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
                 }
-                __shared__ unsigned int s_ra[32];
-                __shared__ unsigned long long s_rl[32], s_rh[32];
-                __syncthreads();
-                if (lane == 0) { s_ra[threadIdx.x >> 5] = alive; s_rl[threadIdx.x >> 5] = lo; s_rh[threadIdx.x >> 5] = hi; }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    unsigned int a = 0;
-                    unsigned long long l = 0, h = 0;
-                    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s_ra[i]; l += s_rl[i]; h += s_rh[i]; }
-                    m.delta_cnt[s] = a - m.local_cnt[s];                 // two's complement, <= 0
-                    if (p.af) { m.delta_lo[s] = l - m.local_lo[s]; m.delta_hi[s] = h - m.local_hi[s]; }
+                if (lane == 0) {
+                    m.delta_cnt[s] = alive - __ldcg(m.local_cnt + s);     // two's complement, <= 0
+                    if (p.af) { m.delta_lo[s] = lo - __ldcg(m.local_lo + s); m.delta_hi[s] = hi - __ldcg(m.local_hi + s); }
                 }
             }
-            if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+            if (!mgpu_barrier<CLUSTER>(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
         }
         // ---- C: push the delta into every peer's inbox (NVLink P2P stores), then publish the sequence number
         seq += 1;
@@ -1046,7 +1054,7 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
             }
         }
         __threadfence_system();
-        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (!mgpu_barrier<CLUSTER>(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
         if (blockIdx.x == 0 && threadIdx.x < m.world && (int)threadIdx.x != m.rank)
             st_release_sys_u64(m.peer_flags[threadIdx.x] + m.rank, seq);
         // ---- D: wait for every peer's delta of this step, apply the sum to the replica, clear the local delta
@@ -1087,7 +1095,7 @@ __global__ void __launch_bounds__(1024, 1) select_mgpu_kernel(SelParams p, MgpuP
                 m.delta_hi[i] = 0;
             }
         }
-        if (!grid_barrier(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
+        if (!mgpu_barrier<CLUSTER>(bar_counter, &s_epoch, nblocks, &st->abort_flag, &s_flag)) return;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->step = step;
@@ -1305,27 +1313,67 @@ int launch_regain(cudaStream_t stream, const SelParams &p, int *n_launch)
 
 
 
+// grid_out < 0: |grid_out| CTAs as ONE thread-block cluster (hardware barrier); > 0: cooperative grid
 int mgpu_grid(int device, int *grid_out, int *block_out)
 {
     int n_sms = 0, per_sm = 0, coop = 0;
     UT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
     UT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    if (!coop) { set_error("device does not support cooperative launch"); return UTMOS_E_NOGPU; }
-    UT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_mgpu_kernel, 1024, 0));
-    if (per_sm < 1) { set_error("multi-GPU kernel does not fit on an SM"); return UTMOS_E_CUDA; }
-    *grid_out = n_sms < 64 ? n_sms : 64;      // few CTAs keep the grid barrier cheap; the loop is latency bound
     *block_out = 1024;
+    // UTMOS_B200_MGPU_GRID: n > 0 = cooperative grid of n CTAs, n < 0 = ONE cluster of |n| CTAs (hardware barrier).
+    // Measured on 2 x B200 (1kGP shape): the 16-CTA cluster is slower than a 64-CTA grid -- the heavy steps need the
+    // SMs (streaming recompute, retiring rows), the barrier latency is not what bounds them -- so the grid is the default.
+    const char *env = getenv("UTMOS_B200_MGPU_GRID");
+    const int want = env ? atoi(env) : 0;
+    if (want < 0 && cudaFuncSetAttribute(select_mgpu_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        const int tries[2] = {-want > 16 ? 16 : -want, 8};
+        for (int t = 0; t < 2; ++t) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(tries[t]);
+            lc.blockDim = dim3(1024);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = tries[t]; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            lc.attrs = attr;
+            lc.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, select_mgpu_kernel<true>, &lc) == cudaSuccess && n >= 1) {
+                *grid_out = -tries[t];
+                return UTMOS_OK;
+            }
+            cudaGetLastError();
+        }
+    }
+    cudaGetLastError();
+    if (!coop) { set_error("device does not support cooperative launch"); return UTMOS_E_NOGPU; }
+    UT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_mgpu_kernel<false>, 1024, 0));
+    if (per_sm < 1) { set_error("multi-GPU kernel does not fit on an SM"); return UTMOS_E_CUDA; }
+    *grid_out = n_sms < 96 ? n_sms : 96;      // measured on 2 x B200: 32 CTAs 18.4 ms, 64: 16.7, 96: 15.5, 148: 15.8 per selection
+    if (want > 0) *grid_out = want < n_sms * per_sm ? want : n_sms * per_sm;
     return UTMOS_OK;
 }
 
 int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
                 unsigned int *bar_counter, ArgPartial *partials, int *n_launch)
 {
-    UT_CUDA(cudaMemsetAsync(bar_counter, 0, sizeof(unsigned int), stream));
     SelParams pp = p;
     MgpuParams mm = m;
-    void *args[] = {&pp, &mm, &bar_counter, &partials};
-    UT_CUDA(cudaLaunchCooperativeKernel((void *)select_mgpu_kernel, dim3(grid), dim3(block), args, 0, stream));
+    if (grid < 0) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(-grid);
+        lc.blockDim = dim3(block);
+        lc.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = -grid; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        UT_CUDA(cudaLaunchKernelEx(&lc, select_mgpu_kernel<true>, pp, mm, bar_counter, partials));
+    } else {
+        UT_CUDA(cudaMemsetAsync(bar_counter, 0, sizeof(unsigned int), stream));
+        void *args[] = {&pp, &mm, &bar_counter, &partials};
+        UT_CUDA(cudaLaunchCooperativeKernel((void *)select_mgpu_kernel<false>, dim3(grid), dim3(block), args, 0, stream));
+    }
     *n_launch += 1;
     return UTMOS_OK;
 }

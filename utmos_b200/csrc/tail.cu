@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             for (int i = tid; i < lines; i += blockDim.x) prefetch_l2(l2 + (size_t)i * 8);
         }
         const int sub = lane & 7, slot = lane >> 3;
+        int staged_any = 0;
         for (int base = 0; base < len; base += 4 * (int)blockDim.x) {
             uint4 e[4];
 #pragma unroll
@@ -527,6 +528,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                 const bool big = fresh && n == kPooled;
                 unsigned int m = 0;
                 if (__any_sync(0xffffffffu, big)) {
+                    staged_any = 1;
                     const unsigned int n8 = big ? (e[u].w + 7) >> 3 : 0u;
                     unsigned int incl = n8;
 #pragma unroll
@@ -596,8 +598,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         }
         // ---- retire the staged carrier lists: one 16-byte chunk (8 carriers) per thread and turn
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        {
+        if (__syncthreads_or(staged_any)) {               // nothing staged (late tail): this barrier already ends the step
             const unsigned int staged_n = min(s_stage_n, cfg.stage_cap);
             for (unsigned int c0 = tid; c0 < staged_n; c0 += blockDim.x) {
                 const uint4 v = s_stage[(size_t)c0 * ESTRIDE];
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
         // every live row of the pick is covered now: its own gain is zero (keeps sum(gains) == live list entries)
         if (tid == 0) {
             s_stage_n = 0;                                // the next walk starts after the argmax barrier

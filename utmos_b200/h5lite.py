@@ -97,6 +97,29 @@ class Dataset:
             if rows > 0:
                 yield offs[0], block[:rows]
 
+    def chunk_table(self):
+        """(addr int64[n], nbytes int64[n], filter_mask uint32[n]) of the chunks in row order, for the native
+        chunk streamer (``DeviceMatrix.append_h5_chunks``); None when the dataset is not row-chunked."""
+        if self._layout["class"] != 2:
+            return None
+        chunk = self._layout["chunk"]
+        if any(c != s for c, s in zip(chunk[1:], self.shape[1:])):
+            return None
+        index = self._chunk_index()
+        if any(any(o != 0 for o in offs[1:]) for offs, _a, _n, _m in index):
+            return None
+        if [offs[0] for offs, _a, _n, _m in index] != list(range(0, len(index) * chunk[0], chunk[0])):
+            return None                                              # holes / unordered chunks: use iter_chunks
+        if self._filters and self._filters != [LZF_FILTER]:
+            raise H5FormatError(f"unsupported filter pipeline {self._filters}")
+        return (np.array([a for _o, a, _n, _m in index], dtype=np.int64),
+                np.array([n for _o, _a, n, _m in index], dtype=np.int64),
+                np.array([m for _o, _a, _n, m in index], dtype=np.uint32))
+
+    @property
+    def has_lzf(self):
+        return bool(self._filters)
+
     def read(self):
         """Whole dataset as one ndarray."""
         if self._layout["class"] == 1:

@@ -124,8 +124,14 @@ def _load_hdf5(path, device, flags):
             raise h5lite.H5FormatError(f"unexpected data dtype {dset.dtype}")
         af_mode = _native.AF_F32 if is_float else _native.AF_NONE
         matrix = _native.DeviceMatrix(num_samples, af_mode, rows_hint=num_rows, device=device, flags=flags)
-        for _first, block in dset.iter_chunks():
-            matrix.append_dense(block)
+        table = dset.chunk_table()
+        if table is not None and len(table[0]) * dset.chunks[0] >= num_rows:
+            # native chunk streamer: pread + LZF decode on all host cores into pinned staging, overlapped with the
+            # H2D copies and the packing kernels
+            matrix.append_h5_chunks(path, table[0], table[1], table[2], dset.chunks[0], num_rows, is_float, dset.has_lzf)
+        else:
+            for _first, block in dset.iter_chunks():
+                matrix.append_dense(block)
         samples = h5["samples"].read()
         stored_var_count = h5["var_count"].read() if "var_count" in h5 else None
     var_count = matrix.finalize()
