@@ -178,11 +178,11 @@ int utmos_debug_step_times(utmos_ctx *ctx, int64_t first, int64_t n, int64_t *ns
 int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
 
 /* Tunables.  UTMOS_OPT_REGAIN_ROWS: a pick that newly covers >= value rows triggers one streaming recompute of
- * all gains from the sample-major copy instead of per-bit subtraction (0 = never, -1 = default max(4096, V/128)). */
+ * all gains from the sample-major copy instead of per-bit subtraction (0 = never, -1 = default max(4096, V/170)). */
 #define UTMOS_OPT_REGAIN_ROWS 1
 #define UTMOS_OPT_GLOBAL_ROWS 4       /* multi-GPU: informative rows summed over all ranks; set before utmos_finalize */
 #define UTMOS_OPT_STEP_TIMES 2        /* 1: record %globaltimer per pick for utmos_debug_step_times (adds latency) */
-#define UTMOS_OPT_TAIL_ROWS 3         /* hand over to the list-driven tail kernel once a pick covers fewer rows (default 1536) */
+#define UTMOS_OPT_TAIL_ROWS 3         /* hand over to the list-driven tail kernel once a pick covers fewer rows (default 2048) */
 #define UTMOS_OPT_TAIL_SINGLE_ROWS 5  /* tail kernel: 8-CTA owner-computes cluster until a pick covers fewer rows
                                          (default 0 = single CTA only) */
 int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);

@@ -479,16 +479,46 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         }
         const int sub = lane & 7, slot = lane >> 3;
         int staged_any = 0;
-        for (int base = 0; base < len; base += 4 * (int)blockDim.x) {
+        // retire the staged carrier lists: one 16-byte chunk (8 carriers) per thread and turn
+        auto retire_staged = [&]() {
+            const unsigned int staged_n = min(s_stage_n, cfg.stage_cap);
+            for (unsigned int c0 = tid; c0 < staged_n; c0 += blockDim.x) {
+                const uint4 v = s_stage[(size_t)c0 * ESTRIDE];
+                unsigned long long gl = 0, gh = 0;
+                if (AF) {
+                    const uint4 qv = s_stage[(size_t)c0 * ESTRIDE + 1];
+                    gl = ((unsigned long long)qv.y << 32) | qv.x;
+                    gh = ((unsigned long long)qv.w << 32) | qv.z;
+                }
+                const unsigned int ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
+                        if (cs != 0xffffu && (CL == 1 || (int)(cs % CL) == crank)) {
+                            n_pool += 1;
+                            atomicAdd(s_cnt + cs, 0xffffffffu);
+                            if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
+                        }
+                    }
+                }
+            }
+        };
+        // a pick that covers very many rows is walked in smaller batches (one entry per thread instead of four) and
+        // the staging area is drained after every batch, so that it does not overflow into the slow direct path
+        const int ept = best_cnt > cfg.stage_cap / 2u ? 1 : 4;
+        const int bstride = ept * (int)blockDim.x;
+        for (int base = 0; base < len; base += bstride) {
             uint4 e[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = base + u * (int)blockDim.x + tid;
-                e[u] = i < len ? __ldg(lst + (size_t)i * ESTRIDE) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+                e[u] = (u < ept && i < len) ? __ldg(lst + (size_t)i * ESTRIDE) : make_uint4(0xffffffffu, 0u, 0u, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (base + u * (int)blockDim.x + warp * 32 >= len) break;       // warp-uniform
+                if (u >= ept || base + u * (int)blockDim.x + warp * 32 >= len) break;       // warp-uniform
                 const int i = base + u * (int)blockDim.x + tid;
                 const unsigned int r = e[u].x;
                 bool fresh = false;
@@ -529,17 +559,10 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                 unsigned int m = 0;
                 if (__any_sync(0xffffffffu, big)) {
                     staged_any = 1;
+                    // reserve chunks of the staging area (one shared-memory atomic per warp instruction: the lanes'
+                    // same-address adds are serialised by the hardware, which is cheaper than a warp scan)
                     const unsigned int n8 = big ? (e[u].w + 7) >> 3 : 0u;
-                    unsigned int incl = n8;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    unsigned int base0 = 0;
-                    if (lane == 31) base0 = atomicAdd(&s_stage_n, incl);
-                    base0 = __shfl_sync(0xffffffffu, base0, 31);
-                    const unsigned int my0 = base0 + incl - n8;
+                    const unsigned int my0 = big ? atomicAdd(&s_stage_n, n8) : 0u;
                     const bool staged = big && my0 + n8 <= cfg.stage_cap;
                     if (staged) {
                         const uint4 *src = reinterpret_cast<const uint4 *>(pool + e[u].z);
@@ -595,33 +618,20 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     }
                 }
             }
+            if (base + bstride < len) {                   // more batches follow (block-uniform): drain the staging area
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                if (__syncthreads_or(staged_any)) {
+                    retire_staged();
+                    __syncthreads();
+                    if (tid == 0) s_stage_n = 0;
+                    __syncthreads();
+                }
+                staged_any = 0;
+            }
         }
-        // ---- retire the staged carrier lists: one 16-byte chunk (8 carriers) per thread and turn
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         if (__syncthreads_or(staged_any)) {               // nothing staged (late tail): this barrier already ends the step
-            const unsigned int staged_n = min(s_stage_n, cfg.stage_cap);
-            for (unsigned int c0 = tid; c0 < staged_n; c0 += blockDim.x) {
-                const uint4 v = s_stage[(size_t)c0 * ESTRIDE];
-                unsigned long long gl = 0, gh = 0;
-                if (AF) {
-                    const uint4 qv = s_stage[(size_t)c0 * ESTRIDE + 1];
-                    gl = ((unsigned long long)qv.y << 32) | qv.x;
-                    gh = ((unsigned long long)qv.w << 32) | qv.z;
-                }
-                const unsigned int ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
-                        if (cs != 0xffffu && (CL == 1 || (int)(cs % CL) == crank)) {
-                            n_pool += 1;
-                            atomicAdd(s_cnt + cs, 0xffffffffu);
-                            if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
-                        }
-                    }
-                }
-            }
+            retire_staged();
             __syncthreads();
         }
         // every live row of the pick is covered now: its own gain is zero (keeps sum(gains) == live list entries)
