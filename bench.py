@@ -43,6 +43,17 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def traffic_from_ncu():
+    """DRAM bytes (read + write) the dominant kernel moved per selection, from the committed ncu capture
+    (profiles/r1_traffic.json; cannot be measured live).  Only meaningful for the default single-GPU workload."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)["per_selection_bytes"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason log during the timed region (B200_PROFILING.md)."""
 
@@ -293,8 +304,11 @@ def main():
                            "select_tail_kernel (head: select_cluster_kernel + regain_kernel)", "select_mgpu_kernel",
                            "select_tail_kernel replicated on every rank (head: select_mgpu_kernel, hand-over: build_edges_kernel over NVLink)"][info["flavour"]],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
-                "note": "latency-bound: %d dependent greedy steps, %.2f us per step" %
+                "traffic": traffic_from_ncu(), "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
+                "note": "latency-bound: %d dependent greedy steps, %.2f us per step; achieved = algorithmic bytes of the whole greedy loop "
+                        "(SURVEY.md 8d: newly covered rows once + per step a column probe, live-mask update and gain scan) / "
+                        "CUDA-event time of all its launches; traffic = ncu DRAM bytes of the tail kernel's launches of one "
+                        "selection (the lists replace the per-step column probe, so traffic is far below the algorithmic bytes)" %
                         (n_steps, phases["select_ms"] * 1e3 / max(n_steps, 1))}
     # one-time streaming kernels against the same peak
     row_bytes = info["num_vars"] // world * info["row_pitch_bytes"]

@@ -429,7 +429,8 @@ def test_full_shape_properties_and_mode_agreement():
 # ------------------------------------------------------------------------------------------------
 def test_convert_gt_kernel_vs_oracle():
     rng = np.random.default_rng(5)
-    for n_vars, n_samples, ploidy in [(50, 1, 2), (300, 37, 2), (200, 2504, 2), (64, 100, 1), (40, 65, 3)]:
+    for n_vars, n_samples, ploidy in [(50, 1, 2), (300, 37, 2), (200, 2504, 2), (90, 1000, 2), (70, 8, 2),
+                                        (30, 5003, 2), (64, 100, 1), (40, 65, 3)]:
         gt = rng.choice(np.array([0, 0, 0, 0, 0, 1, 1, 2, 3, -1], dtype=np.int8), size=(n_vars, n_samples, ploidy))
         gt[0] = -1                                             # nothing called -> AF NaN
         gt[1] = 0                                              # all reference

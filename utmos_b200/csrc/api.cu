@@ -1071,6 +1071,7 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
     UT_CUDA(cudaStreamSynchronize(c->stream));      // host buffers (mask, weights, st) may go away
     if ((c->flags & UTMOS_F_STEP_KERNELS) && (!c->graph_exec || had_weights != c->has_weights)) UT_TRY(build_graph(c));
     c->lists_valid = false;
+    c->lists_cur = 0;                  // the first compaction of a selection goes to the buffer sized for it (no re-allocation)
     c->mg_tail = false;
     c->selecting = true;
     return UTMOS_OK;
@@ -1165,6 +1166,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 m.peer_flags[q] = (unsigned long long *)(pb + l.off_flags);
             }
         }
+        Trace tr("select_steps");
         while (true) {
             SelParams q = make_params(c, false);
             if (c->lists_valid) {
@@ -1207,6 +1209,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             }
             UT_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
             UT_CUDA(cudaStreamSynchronize(c->stream));
+            tr.lap(c->lists_valid ? "tail launch" : "head launches");
             if (st.stop != 0 || st.step >= limit || st.abort_flag) break;
             if (tail_ok && !c->lists_valid && st.want_tail && st.live_bits <= list_budget) {
                 if (multi) {
@@ -1282,6 +1285,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                                           &c->n_launch));
                 c->lists_total = st.live_bits;
                 c->lists_valid = true;
+                tr.lap("list allocation + build launch");
             } else if (c->lists_valid && st.recompact) {
                 // re-compaction: keep the entries whose row is still live
                 const int nxt = c->lists_cur ^ 1;
@@ -1292,6 +1296,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                                            c->d_list_len[nxt], &c->n_launch));
                 c->lists_cur = nxt;
                 c->lists_total = st.live_bits;
+                tr.lap("re-compaction launch");
             }
         }
     }

@@ -99,6 +99,111 @@ __global__ void __launch_bounds__(256) gt_pack_af_kernel(const int8_t *__restric
     }
 }
 
+// One 32-bit word = two diploid samples (allele bytes g0,g1 | g0,g1).  SIMD-in-register byte compares; returns the two
+// presence bits (bit 7: first sample, bit 23: second) and accumulates the per-row counters.
+struct RowAcc {
+    unsigned int an, zero, one, het, hom;
+    bool rare;
+};
+
+__device__ __forceinline__ uint32_t gt_word(uint32_t v, RowAcc &a, unsigned int *hist)
+{
+    const uint32_t called = ~v & 0x80808080u;                 // bit 7 of every called allele byte
+    a.an += __popc(called);
+    a.zero += __popc(__vcmpeq4(v, 0u) & 0x01010101u);
+    a.one += __popc(__vcmpeq4(v, 0x01010101u) & 0x01010101u);
+    if (__vcmpgts4(v, 0x01010101u)) {                         // alleles >= 2: rare, per-warp histogram
+        a.rare = true;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int g = (int)(int8_t)(v >> (8 * e));
+            if (g >= 2) atomicAdd(&hist[g], 1u);
+        }
+    }
+    const uint32_t both = called & __byte_perm(called, 0u, 0x2301);        // both alleles of a sample called
+    const uint32_t eq = __vcmpeq4(v, __byte_perm(v, 0u, 0x2301));          // 0xff.. where allele0 == allele1
+    const uint32_t pos = __vcmpgts4(v, 0u);                                // 0xff where allele > 0
+    const uint32_t het_b = both & ~eq & 0x00800080u;
+    const uint32_t hom_b = both & eq & pos & 0x00800080u;
+    a.het += __popc(het_b);
+    a.hom += __popc(hom_b);
+    return het_b | hom_b;
+}
+
+// warp-level end of a row: reduce the counters, AF = max alt-allele count / called alleles, singleton flag
+__device__ __forceinline__ void gt_row_finish(RowAcc acc, unsigned int *hist, int lane, long long r, double *af,
+                                              uint8_t *singleton, unsigned long long &het_tot, unsigned long long &hom_tot)
+{
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+        acc.an += __shfl_xor_sync(0xffffffffu, acc.an, sh);
+        acc.zero += __shfl_xor_sync(0xffffffffu, acc.zero, sh);
+        acc.one += __shfl_xor_sync(0xffffffffu, acc.one, sh);
+        acc.het += __shfl_xor_sync(0xffffffffu, acc.het, sh);
+        acc.hom += __shfl_xor_sync(0xffffffffu, acc.hom, sh);
+    }
+    unsigned int m = acc.one;
+    if (__any_sync(0xffffffffu, acc.rare)) {
+        __syncwarp();
+        for (int a = 2 + lane; a < 128; a += 32) { m = max(m, hist[a]); hist[a] = 0; }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, sh));
+        __syncwarp();
+    }
+    if (lane == 0) {
+        // max over alleles of count/an == (max count)/an: the divide is monotone in the numerator
+        af[r] = acc.an ? (double)m / (double)acc.an : CUDART_NAN;
+        if (singleton) singleton[r] = (acc.one == 1u || acc.zero == 1u) ? 1 : 0;
+        het_tot += acc.het;
+        hom_tot += acc.hom;
+    }
+}
+
+// Rows that start on 16-byte boundaries (2S % 16 == 0, e.g. S = 2504): no staging at all -- one warp per row, a lane
+// loads 16 genotype bytes (8 samples) per turn straight from global memory with a streaming 128-bit load and emits
+// one output byte; nothing but registers between the load and the store, so many warps keep loads in flight.
+__global__ void __launch_bounds__(256) gt_pack_af_direct_kernel(const int8_t *__restrict__ gt, long long V, int S,
+                                                                uint8_t *__restrict__ packed, long long pitch,
+                                                                double *__restrict__ af, unsigned long long *het_hom,
+                                                                uint8_t *__restrict__ singleton)
+{
+    __shared__ unsigned int s_hist[8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = lane; i < 128; i += 32) s_hist[warp][i] = 0;
+    __syncwarp();
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int groups = (S + 7) >> 3;                       // 16-byte pieces per row == output bytes per row
+    unsigned long long het_tot = 0, hom_tot = 0;
+    for (long long r = warp0; r < V; r += nwarps) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(gt + r * 2ll * S);
+        uint8_t *out = packed + r * pitch;
+        RowAcc acc = {0u, 0u, 0u, 0u, 0u, false};
+#pragma unroll 2
+        for (int g = lane; g < groups; g += 32) {
+            const uint4 q = ld_stream_u128(row + g);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const int s0 = g * 8;
+            uint32_t byte = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t v = w[k];
+                if (s0 + 2 * k >= S) v = 0xffffffffu;                     // past the row (last group): missing
+                else if (s0 + 2 * k + 1 >= S) v |= 0xffff0000u;
+                const uint32_t pr = gt_word(v, acc, s_hist[warp]);
+                byte |= ((pr >> 7) & 1u) << (7 - 2 * k);
+                byte |= ((pr >> 23) & 1u) << (6 - 2 * k);
+            }
+            out[g] = (uint8_t)byte;
+        }
+        gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, het_tot, hom_tot);
+    }
+    if (lane == 0) {
+        if (het_tot) atomicAdd(het_hom + 0, het_tot);
+        if (hom_tot) atomicAdd(het_hom + 1, hom_tot);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // diploid fast path.  A CTA stages a tile of consecutive rows (one contiguous byte range of R * 2S genotype
 // bytes) in shared memory with aligned 128-bit streaming loads, then one warp per row: a lane takes 8 samples
@@ -160,64 +265,22 @@ __global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const i
             const long long r = row0 + i;
             const unsigned int o = mis + (unsigned int)(i * row_bytes);
             uint8_t *out = packed + r * pitch;
-            unsigned int an = 0, zero = 0, one = 0, het = 0, hom = 0;
-            bool rare = false;
+            RowAcc acc = {0u, 0u, 0u, 0u, 0u, false};
             for (int s0 = lane * 8; s0 < S; s0 += 256) {
                 uint32_t byte = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    // word k = samples s0+2k (bytes 0,1) and s0+2k+1 (bytes 2,3); SIMD-in-register byte compares
+                    // word k = samples s0+2k (bytes 0,1) and s0+2k+1 (bytes 2,3)
                     uint32_t v = cvt_le32(s32, o + 2u * s0 + 4u * k);
                     if (s0 + 2 * k >= S) v = 0xffffffffu;                     // past the row: missing
                     else if (s0 + 2 * k + 1 >= S) v |= 0xffff0000u;
-                    const uint32_t called = ~v & 0x80808080u;                 // bit 7 of every called allele byte
-                    an += __popc(called);
-                    zero += __popc(__vcmpeq4(v, 0u) & 0x01010101u);
-                    one += __popc(__vcmpeq4(v, 0x01010101u) & 0x01010101u);
-                    if (__vcmpgts4(v, 0x01010101u)) {                         // alleles >= 2: rare, per-warp histogram
-                        rare = true;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int g = (int)(int8_t)(v >> (8 * e));
-                            if (g >= 2) atomicAdd(&s_hist[warp][g], 1u);
-                        }
-                    }
-                    const uint32_t both = called & __byte_perm(called, 0u, 0x2301);        // both alleles of a sample called
-                    const uint32_t eq = __vcmpeq4(v, __byte_perm(v, 0u, 0x2301));          // 0xff.. where allele0 == allele1
-                    const uint32_t pos = __vcmpgts4(v, 0u);                                // 0xff where allele > 0
-                    const uint32_t het_b = both & ~eq & 0x00800080u;                       // bit 7 / bit 23: sample 2k / 2k+1
-                    const uint32_t hom_b = both & eq & pos & 0x00800080u;
-                    het += __popc(het_b);
-                    hom += __popc(hom_b);
-                    const uint32_t pr = het_b | hom_b;
+                    const uint32_t pr = gt_word(v, acc, s_hist[warp]);
                     byte |= ((pr >> 7) & 1u) << (7 - 2 * k);
                     byte |= ((pr >> 23) & 1u) << (6 - 2 * k);
                 }
                 out[s0 >> 3] = (uint8_t)byte;
             }
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) {
-                an += __shfl_xor_sync(0xffffffffu, an, sh);
-                zero += __shfl_xor_sync(0xffffffffu, zero, sh);
-                one += __shfl_xor_sync(0xffffffffu, one, sh);
-                het += __shfl_xor_sync(0xffffffffu, het, sh);
-                hom += __shfl_xor_sync(0xffffffffu, hom, sh);
-            }
-            unsigned int m = one;
-            if (__any_sync(0xffffffffu, rare)) {
-                __syncwarp();
-                for (int a = 2 + lane; a < 128; a += 32) { m = max(m, s_hist[warp][a]); s_hist[warp][a] = 0; }
-#pragma unroll
-                for (int sh = 16; sh > 0; sh >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, sh));
-                __syncwarp();
-            }
-            if (lane == 0) {
-                // max over alleles of count/an == (max count)/an: the divide is monotone in the numerator
-                af[r] = an ? (double)m / (double)an : CUDART_NAN;
-                if (singleton) singleton[r] = (one == 1u || zero == 1u) ? 1 : 0;
-                het_tot += het;
-                hom_tot += hom;
-            }
+            gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, het_tot, hom_tot);
         }
     }
     if (lane == 0) {
@@ -232,6 +295,14 @@ int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S,
                       long long pitch_out, double *af, unsigned long long *het_hom, uint8_t *singleton, int *n_launch)
 {
     if (V <= 0) return UTMOS_OK;
+    if (ploidy == 2 && ((uintptr_t)gt & 15u) == 0 && (2ll * S) % 16 == 0 && pitch_out == (S + 7) / 8) {
+        const long long warps = V;
+        const unsigned grid = (unsigned)std::min<long long>((warps + 7) / 8, 148ll * 16);
+        gt_pack_af_direct_kernel<<<grid, 256, 0, stream>>>(gt, V, S, packed, pitch_out, af, het_hom, singleton);
+        *n_launch += 1;
+        UT_CUDA(cudaGetLastError());
+        return UTMOS_OK;
+    }
     if (ploidy == 2 && ((uintptr_t)gt & 15u) == 0 && 2ull * (size_t)S + 64 <= kCvtSmemRaw && pitch_out == (S + 7) / 8) {
         const size_t tile_budget = std::max(kCvtTileBytes, 2 * (size_t)S + 64);
         int R = (int)std::min<size_t>(64, (tile_budget - 64) / (2 * (size_t)S));

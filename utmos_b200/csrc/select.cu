@@ -48,14 +48,18 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 
 __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__restrict__ rows, long long V,
                                                              int pitchW, int S32, uint32_t *__restrict__ cols,
-                                                             long long colPitchW)
+                                                             long long colPitchW, int col_tiles)
 {
     extern __shared__ __align__(16) uint32_t t_smem[];
     uint32_t *s_in = t_smem;                                   // [kTRows][kTInPitch]
     uint32_t *s_out = t_smem + kTRows * kTInPitch;             // [1024][kTOutPitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long r0 = (long long)blockIdx.x * kTRows;
-    const int w0 = blockIdx.y * kTWords;
+    // 1-D grid, column tile fastest: the CTAs that share the 128-byte lines of the same rows run back to back, so the
+    // second 64-byte half of every line comes from L2 instead of DRAM (ncu: 707 MB read for 353 MB before this)
+    const long long row_tile = blockIdx.x / col_tiles;
+    const int col_tile = (int)(blockIdx.x - row_tile * col_tiles);
+    const long long r0 = row_tile * kTRows;
+    const int w0 = col_tile * kTWords;
 
     for (int i = threadIdx.x; i < kTRows * (kTWords / 4); i += 256) {
         const int row = i / (kTWords / 4), q = i % (kTWords / 4);
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__r
         const int s = w0 * 32 + sl;
         if (s >= S32) continue;
         const uint32_t *o = s_out + sl * kTOutPitch;
-        uint4 *dst = reinterpret_cast<uint4 *>(cols + (long long)s * colPitchW + (long long)blockIdx.x * (kTRows / 32));
+        uint4 *dst = reinterpret_cast<uint4 *>(cols + (long long)s * colPitchW + row_tile * (kTRows / 32));
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
@@ -1128,14 +1132,14 @@ int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int
     // colPitchW is a multiple of 8 words and covers ceil(V/32); one tile = 256 rows = 8 words
     const long long row_tiles = colPitchW / (kTRows / 32);
     const int col_tiles = (pitchW + kTWords - 1) / kTWords;
-    if (row_tiles > 0x7fffffffll || col_tiles > 65535) { set_error("transpose: matrix too large"); return UTMOS_E_ARG; }
+    if (row_tiles * col_tiles > 0x7fffffffll) { set_error("transpose: matrix too large"); return UTMOS_E_ARG; }
     static bool configured = false;
     if (!configured) {
         UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
         configured = true;
     }
-    dim3 grid((unsigned)row_tiles, (unsigned)col_tiles);
-    transpose_bits_kernel<<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW);
+    const unsigned grid = (unsigned)(row_tiles * col_tiles);
+    transpose_bits_kernel<<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW, col_tiles);
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
