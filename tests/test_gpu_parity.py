@@ -395,6 +395,36 @@ def _tail_case_oracle(use_af, weighted):
     return o_idx, o_new, o_score
 
 
+@pytest.mark.parametrize("mode", ["count", "weights", "af"])
+@pytest.mark.parametrize("tail_rows", [1 << 30, 64], ids=["tail_from_step0", "cluster_head_then_tail"])
+def test_wide_cohort_more_than_65535_samples(mode, tail_rows):
+    """S > 65,535: 32-bit carriers and per-sample state sliced over a thread-block cluster (the state of 70k samples
+    does not fit one SM); against the exact oracle, and against the cluster-only kernels."""
+    n_vars, n_samples, steps = 5000, 70001, 250
+    coh = synth.DeviceCohort(11, n_vars, n_samples)
+    gt, af = coh.to_host()
+    use_af = mode == "af"
+    wts = synth.synthetic_weights(n_samples) if mode == "weights" else None
+    mask = np.ones(n_samples, np.uint8)
+    mask[7::101] = 2
+    results = []
+    for flags in (0, _native.F_NO_TAIL):
+        dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE, flags=flags)
+        dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
+        dm.finalize()
+        dm.set_option(3, tail_rows)
+        dm.begin(mask, wts)
+        i1, n1, s1, _ = dm.steps(100)
+        i2, n2, s2, _ = dm.steps(steps - 100)
+        results.append((np.concatenate([i1, i2]), np.concatenate([n1, n2]), np.concatenate([s1, s2]), dm.info()["flavour"]))
+        dm.close()
+    coh.close()
+    assert results[0][3] == 3 and results[1][3] != 3
+    o_idx, o_new, o_score, _ = orc.greedy_c(gt, n_samples, mask, wts, af if use_af else None, steps, exact=True)
+    for idx, new, score, _ in results:
+        assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
+
+
 def test_full_shape_properties_and_mode_agreement():
     """1kGP chr22 shape (2,504 x 1,103,547), --count -1: invariants the greedy loop must satisfy at any size,
     and all four kernel flavours must give the same ordering."""

@@ -56,7 +56,9 @@ struct Trace {
 };
 constexpr size_t kStageBytes = 64ull << 20;      // per staging buffer (two pinned host + two device)
 constexpr int kGraphSteps = 32;                  // step pairs per CUDA graph replay
-constexpr unsigned long long kListBudget = 1ull << 24;   // edge-list entries (16 B each; 32 B for AF flavours)
+constexpr unsigned long long kListBudget = 1ull << 24;       // edge-list entries (16 B each; 32 B for AF flavours)
+constexpr unsigned long long kListBudgetWide = 1ull << 28;   // S > 65,535: the rare variants of a 100k-sample cohort alone
+                                                             // hold more than 2^24 bits, and the head costs ~20-100 us per step
 enum { T_H2D = 0, T_INGEST = 1, T_TRANSPOSE = 2, T_GAIN = 3, T_SELECT = 4, T_COUNT = 5 };
 
 struct Pending {
@@ -494,7 +496,7 @@ void free_select_state(utmos_ctx *c)
     for (int i = 0; i < kMaxRanks; ++i) c->mg_peer[i] = nullptr;     // mappings stay in the process-wide cache
     if (c->mg_block) { mg_block_release(c->mg_block); c->mg_block = nullptr; }
     dev_free(c, c->d_pool_cursor, 16);
-    big_free(c, c->d_pool, c->pool_cap * 2);
+    big_free(c, c->d_pool, c->pool_cap * (c->S > 65535 ? 4 : 2));
     c->pool_cap = 0;
     c->lists_valid = false;
     dev_free(c, c->d_dbg_score, S * 8);
@@ -509,6 +511,7 @@ struct MgLayout {
 };
 MgLayout mg_layout(size_t S, int world, bool af, unsigned long long list_cap, long long merged_rows)
 {
+    const size_t pool_elem = S > 65535 ? 4 : 2;           // carrier ids: uint16, or uint32 for wide cohorts
     MgLayout l;
     size_t off = 0;
     auto take = [&](size_t b) { const size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
@@ -521,7 +524,7 @@ MgLayout mg_layout(size_t S, int world, bool af, unsigned long long list_cap, lo
     l.pool_cap = list_cap ? (size_t)(mgpu_pool_share(list_cap) + 64ull * (size_t)world) : 0;
     l.off_live = take(l.live_words * 4);
     l.off_lists = take((size_t)list_cap * (af ? 32 : 16));
-    l.off_pool = take(l.pool_cap * 2);
+    l.off_pool = take(l.pool_cap * pool_elem);
     l.bytes = off;
     return l;
 }
@@ -1123,7 +1126,9 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         // waiting for the live part of the matrix to become sparse, launches are kept short so the host can switch
         // as soon as the per-sample live-row lists fit the budget.
         // Tail: one CTA runs all remaining steps from the lists (on every rank, identically, when multi-GPU).
-        const unsigned long long list_budget = multi ? c->mg_list_cap - 64 : kListBudget;
+        const bool wide = c->S > 65535;
+        const size_t pool_elem = wide ? 4 : 2;
+        const unsigned long long list_budget = multi ? c->mg_list_cap - 64 : (wide ? kListBudgetWide : kListBudget);
         const size_t estride = af ? 2 : 1;
         c->tail_budget = tail_ok ? list_budget : 0;
         auto reserve_lists = [&](int which, unsigned long long entries) -> int {
@@ -1171,10 +1176,11 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             SelParams q = make_params(c, false);
             if (c->lists_valid) {
                 // heavy picks: cluster of 8 CTAs, each applying the decrements of the samples it owns; light picks: one CTA
-                unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
+                const unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
+                const bool cluster = wide || single_rows > 0;
                 uint32_t *live_priv = nullptr;
-                if (single_rows > 0 && !tail_live_in_smem(q)) {
-                    const size_t need = (size_t)kTailCluster * (size_t)q.colPitchW * 4;
+                if (cluster && !tail_live_in_smem(q, cluster)) {
+                    const size_t need = (size_t)tail_cluster_size(q, cluster) * (size_t)q.colPitchW * 4;
                     if (need > c->live_priv_bytes) {
                         dev_free(c, c->d_live_priv, c->live_priv_bytes);
                         UT_TRY(dev_alloc(c, (void **)&c->d_live_priv, need));
@@ -1182,7 +1188,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                     }
                     live_priv = c->d_live_priv;
                 }
-                UT_TRY(launch_tail(c->stream, q, c->lists_total, single_rows, live_priv, &c->n_launch));
+                UT_TRY(launch_tail(c->stream, q, c->lists_total, cluster, single_rows, live_priv, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 c->flavour_used = multi ? 5 : 3;
             } else if (multi) {
@@ -1257,7 +1263,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                     if (chk.abort_flag) { st.abort_flag = chk.abort_flag; break; }
                     if (!c->lists_external) {
                         big_free(c, c->d_lists[0], c->lists_cap[0] * 16);
-                        big_free(c, c->d_pool, c->pool_cap * 2);
+                        big_free(c, c->d_pool, c->pool_cap * pool_elem);
                     }
                     c->d_lists[0] = (uint4 *)(mine + l.off_lists);
                     c->lists_cap[0] = (size_t)c->mg_list_cap * estride;
@@ -1275,9 +1281,9 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 // pooled carrier lists are padded to 8 entries per row (rows with >= 7 carriers): <= 15/7 per live bit
                 const size_t pool_need = (size_t)mgpu_pool_share(st.live_bits);
                 if (pool_need > c->pool_cap) {
-                    big_free(c, c->d_pool, c->pool_cap * 2);
+                    big_free(c, c->d_pool, c->pool_cap * pool_elem);
                     c->pool_cap = pool_need;
-                    UT_TRY(big_alloc(c, (void **)&c->d_pool, c->pool_cap * 2));
+                    UT_TRY(big_alloc(c, (void **)&c->d_pool, c->pool_cap * pool_elem));
                 }
                 q = make_params(c, false);
                 UT_TRY(launch_build_lists(c->stream, q, c->d_lists[c->lists_cur], c->d_list_off[c->lists_cur],
@@ -1373,9 +1379,9 @@ int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
     // merged edge lists for the replicated tail: as many entries as the tail hand-over budget allows (utmos_set_gains0
     // has stored the set bits of all ranks' scoring rows); every rank computes the same capacity
     c->mg_list_cap = 0;
-    if (c->mg_allow_tail && c->mg_merged_rows > 0 && c->mg_merged_rows < 0xffffffffll && c->S <= 65535 &&
+    if (c->mg_allow_tail && c->mg_merged_rows > 0 && c->mg_merged_rows < 0xffffffffll &&
         !(c->flags & (UTMOS_F_NO_TAIL | UTMOS_F_NO_TRANSPOSE)))
-        c->mg_list_cap = std::min<unsigned long long>(kListBudget, c->total_bits) + 64;
+        c->mg_list_cap = std::min<unsigned long long>(c->S > 65535 ? kListBudgetWide : kListBudget, c->total_bits) + 64;
     const MgLayout l = mg_layout(S, world, af, c->mg_list_cap, c->mg_merged_rows);
     cudaIpcMemHandle_t h;
     UT_TRY(mg_block_acquire(c->device, l.bytes, &c->mg_block, &h));

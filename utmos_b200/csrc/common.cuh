@@ -262,10 +262,10 @@ int launch_gather_offsets(cudaStream_t stream, const GatherParams &g, unsigned i
 int launch_gather_live(cudaStream_t stream, const GatherParams &g, const uint32_t *live, int *n_launch);
 int launch_gather_done(cudaStream_t stream, const GatherParams &g, int *n_launch);
 unsigned long long mgpu_pool_share(unsigned long long live_bits);
-constexpr int kTailCluster = 8;     // CTAs of the owner-computes flavour of the tail kernel
-int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int single_rows,
-                uint32_t *live_priv, int *n_launch);
-int tail_live_in_smem(const SelParams &p);
+int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, bool cluster,
+                unsigned int single_rows, uint32_t *live_priv, int *n_launch);
+int tail_live_in_smem(const SelParams &p, bool cluster);
+int tail_cluster_size(const SelParams &p, bool cluster);
 int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
                 unsigned int *bar_counter, ArgPartial *partials, int *n_launch);
 int mgpu_grid(int device, int *grid_out, int *block_out);

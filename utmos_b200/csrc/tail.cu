@@ -97,21 +97,17 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(const unsigned int *
     }
 }
 
-__device__ __forceinline__ uint4 pack_entry(unsigned int r, unsigned int n, const unsigned short *c)
-{
-    return make_uint4(r, n | ((unsigned int)c[0] << 16), (unsigned int)c[1] | ((unsigned int)c[2] << 16),
-                      (unsigned int)c[3] | ((unsigned int)c[4] << 16));
-}
-
 // First compaction, from the bit matrix: one warp per live row.  A row with k carriers yields k entries, one
 // in the list of each carrier.  ESTRIDE = 1 (count) or 2 (AF flavours: second uint4 = fixed-point AF limbs).
 // EdgeDst says where the entries go: single GPU = this context's buffers; multi-GPU = the SAME slots of every
 // rank's merged buffers (peer pointers, NVLink stores), so all ranks end up with byte-identical lists.
-template <int ESTRIDE>
+template <int ESTRIDE, bool WIDE>
 __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d, unsigned int *cursor,
                                                           unsigned int *pool_cursor)
 {
-    __shared__ unsigned short s_car[8][8];
+    constexpr int kInl = WIDE ? 2 : kInline;           // other carriers stored inline in an entry
+    constexpr int kPerChunk = WIDE ? 4 : 8;            // pool elements per 16-byte chunk
+    __shared__ unsigned int s_car[8][8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -134,24 +130,27 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
             const unsigned long long ql = p.q_lo[r], qh = p.q_hi[r];
             tailq = make_uint4((unsigned int)ql, (unsigned int)(ql >> 32), (unsigned int)qh, (unsigned int)(qh >> 32));
         }
-        if (total - 1 <= kInline) {
+        if (total - 1 <= kInl) {
             int pos = incl - mine;
             for (int k = lane; k < p.nW; k += 32) {
                 uint32_t x = __ldg(row + k);
                 while (x) {
-                    s_car[wib][pos++] = (unsigned short)((k << 5) + (__ffs(x) - 1));
+                    s_car[wib][pos++] = (unsigned int)((k << 5) + (__ffs(x) - 1));
                     x &= x - 1;
                 }
             }
             __syncwarp();
             if (lane < total) {
-                unsigned short others[kInline] = {0, 0, 0, 0, 0};
+                unsigned int others[kInline] = {0, 0, 0, 0, 0};
                 int m = 0;
                 for (int j = 0; j < total; ++j)
                     if (j != lane) others[m++] = s_car[wib][j];
                 const unsigned int s = s_car[wib][lane];
                 const size_t slot = ((size_t)d.slot_base[s] + atomicAdd(cursor + s, 1u)) * ESTRIDE;
-                const uint4 e0 = pack_entry(rg, (unsigned int)(total - 1), others);
+                uint4 e0;
+                if (WIDE) e0 = make_uint4(rg, (unsigned int)(total - 1), others[0], others[1]);
+                else e0 = make_uint4(rg, (unsigned int)(total - 1) | (others[0] << 16), others[1] | (others[2] << 16),
+                                     others[3] | (others[4] << 16));
                 for (int q = 0; q < d.world; ++q) {
                     d.lists[q][slot] = e0;
                     if (ESTRIDE == 2) d.lists[q][slot + 1] = tailq;
@@ -160,13 +159,17 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
             __syncwarp();
         } else {
             // carriers of this row go to the pool once; every carrier's entry points at them
-            // (padded to a multiple of 8 entries with 0xffff so the tail kernel can use aligned 128-bit loads)
-            const int padded = (total + 7) & ~7;
+            // (padded to whole 16-byte chunks with all-ones so the tail kernel can use aligned 128-bit copies)
+            const int padded = (total + kPerChunk - 1) / kPerChunk * kPerChunk;
             unsigned int base = 0;
             if (lane == 0) base = pool_base + atomicAdd(pool_cursor, (unsigned int)padded);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (lane < padded - total)
-                for (int q = 0; q < d.world; ++q) d.pool[q][base + total + lane] = (unsigned short)0xffffu;
+            if (lane < padded - total) {
+                for (int q = 0; q < d.world; ++q) {
+                    if (WIDE) reinterpret_cast<unsigned int *>(d.pool[q])[base + total + lane] = 0xffffffffu;
+                    else d.pool[q][base + total + lane] = (unsigned short)0xffffu;
+                }
+            }
             int pos = incl - mine;
             for (int k = lane; k < p.nW; k += 32) {
                 uint32_t x = __ldg(row + k);
@@ -174,9 +177,10 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
                     const unsigned int s = (unsigned int)((k << 5) + (__ffs(x) - 1));
                     x &= x - 1;
                     const size_t slot = ((size_t)d.slot_base[s] + atomicAdd(cursor + s, 1u)) * ESTRIDE;
-                    const uint4 e0 = make_uint4(rg, kPooled, base, (unsigned int)total);
+                    const uint4 e0 = make_uint4(rg, WIDE ? 0xffffffffu : kPooled, base, (unsigned int)total);
                     for (int q = 0; q < d.world; ++q) {
-                        d.pool[q][base + pos] = (unsigned short)s;
+                        if (WIDE) reinterpret_cast<unsigned int *>(d.pool[q])[base + pos] = s;
+                        else d.pool[q][base + pos] = (unsigned short)s;
                         d.lists[q][slot] = e0;
                         if (ESTRIDE == 2) d.lists[q][slot + 1] = tailq;
                     }
@@ -279,7 +283,7 @@ struct TailCfg {
     unsigned int single_rows;     // cluster flavour: hand over to the single-CTA flavour once a pick covers fewer rows
     uint32_t *live_priv;          // cluster flavour with the live mask in global memory: [CL][colPitchW] private copies
     int off_stage;                // staging area for the carrier lists of the rows a pick newly covers
-    unsigned int stage_cap;       // ... capacity in chunks (16 bytes = 8 carriers; AF flavours: + 16 bytes of limbs)
+    unsigned int stage_cap;       // ... capacity in chunks (16 bytes of carriers; AF flavours: + 16 bytes of limbs)
 };
 
 // integer argmax for count mode without weights: key = gain count of a selectable sample (0 otherwise);
@@ -293,21 +297,28 @@ __device__ __forceinline__ uint2 warp_argmax_u32(unsigned int key, unsigned int 
 
 // ESTRIDE 1: count entries; 2: AF flavours (second uint4 = fixed-point AF limbs of the row).
 // FAST: count mode without weights -> integer keys (two REDUX per reduction level instead of the float64 path).
-// CL: 1 = one CTA does everything.  CL > 1 = a thread-block cluster of CL CTAs, "owner computes": a shared-memory
-//     atomic costs ~2 cycles per lane, so while picks still retire thousands of carriers the decrements are the
-//     bottleneck of one SM.  Every CTA of the cluster walks the same list and keeps its own copy of the live
-//     mask (so all CTAs see the same newly covered rows without talking), but applies only the decrements of
-//     the samples it owns (s % CL == rank) and scans only those in the argmax; the CL local winners are
-//     exchanged through distributed shared memory, one hardware cluster barrier per step.
-template <int ESTRIDE, bool FAST, int CL>
+// WIDE: more than 65,535 samples -> 32-bit carriers (two inline per entry, four per pooled 16-byte chunk).
+// CL: 1 = one CTA does everything.  CL > 1 = a thread-block cluster of CL CTAs, "owner computes": every CTA of the
+//     cluster walks the same list and keeps its own copy of the live mask (so all CTAs see the same newly covered
+//     rows without talking), but keeps only the state of the samples it owns (s % CL == rank, local index s / CL),
+//     applies only their decrements and scans only them in the argmax; the CL local winners (with the position of
+//     their lists) are exchanged through distributed shared memory, one hardware cluster barrier per step.  This
+//     is what makes S > 65,535 fit (the per-sample state of 100,000 samples does not fit one SM), and it divides
+//     the shared-memory atomics of heavy picks by CL.
+template <int ESTRIDE, bool FAST, int CL, bool WIDE>
 __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailCfg cfg, unsigned long long lists_total)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Cand s_red[32];
     __shared__ unsigned long long s_sum[32];
     __shared__ uint4 s_xbest[2][16];               // CL > 1: the local winners of every CTA, double buffered by step parity
+    __shared__ uint2 s_xlist[2][16];               //         ... and where their edge lists are (offset, length)
     __shared__ unsigned long long s_xsum[16];
+    __shared__ unsigned int s_stage_n;
     constexpr bool AF = ESTRIDE == 2;
+    constexpr int kInl = WIDE ? 2 : kInline;       // carriers inline in an entry
+    constexpr int kPerChunk = WIDE ? 4 : 8;        // carriers per 16-byte pool chunk
+    constexpr unsigned int kPad = WIDE ? 0xffffffffu : 0xffffu;
     int crank = 0;
     if (CL > 1) crank = (int)cg::this_cluster().block_rank();
     int xpar = 0;
@@ -317,24 +328,27 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(smem + cfg.off_hi);
     double *s_w = reinterpret_cast<double *>(smem + cfg.off_w);
     uint8_t *s_mask = smem + cfg.off_mask;
-    unsigned int *s_loff = reinterpret_cast<unsigned int *>(smem + cfg.off_loff);
+    unsigned int *s_loff = reinterpret_cast<unsigned int *>(smem + cfg.off_loff);     // CL == 1 only
     unsigned int *s_llen = reinterpret_cast<unsigned int *>(smem + cfg.off_llen);
     uint32_t *s_live = reinterpret_cast<uint32_t *>(smem + cfg.off_live);
     uint4 *s_stage = reinterpret_cast<uint4 *>(smem + cfg.off_stage);
-    __shared__ unsigned int s_stage_n;
-    const unsigned short *pool = p.pool;
+    const uint4 *pool16 = reinterpret_cast<const uint4 *>(p.pool);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool has_w = p.weights != nullptr;
     const bool live_smem = cfg.live_words > 0;
     SelState *st = p.st;
+    // samples this CTA owns: s = crank + CL * li, li = 0 .. n_own-1
+    const int n_own = p.S > crank ? (p.S - crank + CL - 1) / CL : 0;
+#define UT_OWNED(s) (CL == 1 || (int)((s) % CL) == crank)
+#define UT_LI(s) (CL == 1 ? (s) : (s) / CL)
 
-    for (int i = tid; i < p.S; i += blockDim.x) {
-        s_cnt[i] = p.gain_cnt[i];
-        s_mask[i] = p.mask[i];
-        s_loff[i] = p.list_off[i];
-        s_llen[i] = p.list_len[i];
-        if (AF) { s_lo[i] = p.gain_lo[i]; s_hi[i] = p.gain_hi[i]; }
-        if (has_w) s_w[i] = p.weights[i];
+    for (int li = tid; li < n_own; li += blockDim.x) {
+        const int i = crank + CL * li;
+        s_cnt[li] = p.gain_cnt[i];
+        s_mask[li] = p.mask[i];
+        if (CL == 1) { s_loff[li] = p.list_off[i]; s_llen[li] = p.list_len[i]; }
+        if (AF) { s_lo[li] = p.gain_lo[i]; s_hi[li] = p.gain_hi[i]; }
+        if (has_w) s_w[li] = p.weights[i];
     }
     for (int i = tid; i < cfg.live_words; i += blockDim.x) s_live[i] = p.live[i];
     uint32_t *g_live = p.live;
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         if (++since_check >= 64) {
             since_check = 0;
             unsigned long long acc = 0;
-            for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) acc += s_cnt[i];
+            for (int li = tid; li < n_own; li += blockDim.x) acc += s_cnt[li];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) s_sum[warp] = acc;
@@ -382,25 +396,33 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             }
         }
         // ---- argmax over all samples (shared memory, np.argmax order)
-        int best_idx, next_idx;             // the pick, and the best of the other warps' winners (a likely next pick)
+        int best_idx, next_idx;             // the pick, and the best of the other warps' / CTAs' winners (a likely next pick)
         unsigned int best_cnt;
         double best_score;
+        unsigned int best_off = 0, best_len = 0, next_off = 0, next_len = 0;
         if (FAST) {
             unsigned int bk = 0, bi = 0x7fffffffu;
-            for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) {
-                const unsigned int k = s_mask[i] == 1 ? s_cnt[i] : 0u;
-                if (k > bk || bi == 0x7fffffffu) { bk = k; bi = (unsigned int)i; }     // i ascends: first index kept on ties
+            for (int li = tid; li < n_own; li += blockDim.x) {
+                const unsigned int k = s_mask[li] == 1 ? s_cnt[li] : 0u;
+                if (k > bk || bi == 0x7fffffffu) { bk = k; bi = (unsigned int)(crank + CL * li); }     // ascending: first index kept on ties
             }
             const uint2 w = warp_argmax_u32(bk, bi);
             if (lane == 0) *reinterpret_cast<uint2 *>(&s_red[warp]) = w;
             __syncthreads();
             uint2 mine = *reinterpret_cast<const uint2 *>(&s_red[lane]);
             uint2 b = warp_argmax_u32(mine.x, mine.y);
+            uint2 olist = make_uint2(0u, 0u);
             if (CL > 1) {
                 cg::cluster_group cluster = cg::this_cluster();
-                if (tid < CL) cluster.map_shared_rank(&s_xbest[xpar][0], tid)[crank] = make_uint4(b.x, b.y, 0u, 0u);
+                if (tid < CL) {
+                    uint2 ll = make_uint2(0u, 0u);
+                    if (b.y != 0x7fffffffu) ll = make_uint2(__ldg(p.list_off + b.y), __ldg(p.list_len + b.y));
+                    cluster.map_shared_rank(&s_xbest[xpar][0], tid)[crank] = make_uint4(b.x, b.y, 0u, 0u);
+                    cluster.map_shared_rank(&s_xlist[xpar][0], tid)[crank] = ll;
+                }
                 cluster.sync();
                 const uint4 o = lane < CL ? s_xbest[xpar][lane] : make_uint4(0u, 0x7fffffffu, 0u, 0u);
+                olist = lane < CL ? s_xlist[xpar][lane] : make_uint2(0u, 0u);
                 xpar ^= 1;
                 mine = make_uint2(o.x, o.y);
                 b = warp_argmax_u32(mine.x, mine.y);
@@ -410,17 +432,24 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             best_cnt = b.x;
             best_score = (double)b.x;
             next_idx = t2.x > 0u ? (int)t2.y : 0x7fffffff;
+            if (CL > 1) {
+                const int src_b = b.y != 0x7fffffffu ? (int)(b.y % CL) : 0, src_n = next_idx != 0x7fffffff ? next_idx % CL : 0;
+                best_off = __shfl_sync(0xffffffffu, olist.x, src_b);
+                best_len = __shfl_sync(0xffffffffu, olist.y, src_b);
+                next_off = __shfl_sync(0xffffffffu, olist.x, src_n);
+                next_len = __shfl_sync(0xffffffffu, olist.y, src_n);
+            }
         } else {
             Cand b{0u, 0u, 0x7fffffff, 0u};
-            for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) {
-                const unsigned int c = s_cnt[i];
+            for (int li = tid; li < n_own; li += blockDim.x) {
+                const unsigned int c = s_cnt[li];
                 double g = 0.0;
-                if (s_mask[i] == 1) {
-                    g = AF ? fixed_to_double(s_lo[i], s_hi[i], p.L, p.scale) : (double)c;
-                    if (has_w) g *= s_w[i];
+                if (s_mask[li] == 1) {
+                    g = AF ? fixed_to_double(s_lo[li], s_hi[li], p.L, p.scale) : (double)c;
+                    if (has_w) g *= s_w[li];
                 }
                 const unsigned long long k = score_key(g);
-                Cand c2{(unsigned int)(k >> 32), (unsigned int)k, i, c};
+                Cand c2{(unsigned int)(k >> 32), (unsigned int)k, crank + CL * li, c};
                 if (cand_better(c2, b)) b = c2;
             }
             b = warp_argmax(b);
@@ -428,11 +457,18 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             __syncthreads();
             Cand mine = s_red[lane];
             b = warp_argmax(mine);
+            uint2 olist = make_uint2(0u, 0u);
             if (CL > 1) {
                 cg::cluster_group cluster = cg::this_cluster();
-                if (tid < CL) cluster.map_shared_rank(&s_xbest[xpar][0], tid)[crank] = make_uint4(b.hi, b.lo, (unsigned int)b.idx, b.cnt);
+                if (tid < CL) {
+                    uint2 ll = make_uint2(0u, 0u);
+                    if (b.idx != 0x7fffffff) ll = make_uint2(__ldg(p.list_off + b.idx), __ldg(p.list_len + b.idx));
+                    cluster.map_shared_rank(&s_xbest[xpar][0], tid)[crank] = make_uint4(b.hi, b.lo, (unsigned int)b.idx, b.cnt);
+                    cluster.map_shared_rank(&s_xlist[xpar][0], tid)[crank] = ll;
+                }
                 cluster.sync();
                 const uint4 o = lane < CL ? s_xbest[xpar][lane] : make_uint4(0u, 0u, 0x7fffffffu, 0u);
+                olist = lane < CL ? s_xlist[xpar][lane] : make_uint2(0u, 0u);
                 xpar ^= 1;
                 mine = Cand{o.x, o.y, (int)o.z, o.w};
                 b = warp_argmax(mine);
@@ -444,6 +480,13 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             best_cnt = b.cnt;
             best_score = key_score(b.hi, b.lo);
             next_idx = (t2.idx != 0x7fffffff && key_score(t2.hi, t2.lo) > 0.0) ? t2.idx : 0x7fffffff;
+            if (CL > 1) {
+                const int src_b = best_idx != 0x7fffffff ? best_idx % CL : 0, src_n = next_idx != 0x7fffffff ? next_idx % CL : 0;
+                best_off = __shfl_sync(0xffffffffu, olist.x, src_b);
+                best_len = __shfl_sync(0xffffffffu, olist.y, src_b);
+                next_off = __shfl_sync(0xffffffffu, olist.x, src_n);
+                next_len = __shfl_sync(0xffffffffu, olist.y, src_n);
+            }
         }
         if (p.S == 0 || best_score == 0.0) {              // utmos/select.py:51-52
             stop = UTMOS_STOP_ZERO;
@@ -453,6 +496,11 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             want_single = 1;
             break;
         }
+        if (CL == 1) {
+            best_off = s_loff[best_idx];
+            best_len = s_llen[best_idx];
+            if (next_idx != 0x7fffffff) { next_off = s_loff[next_idx]; next_len = s_llen[next_idx]; }
+        }
         if (tid == 0) {
             if (crank == 0) {
                 p.out_idx[step] = best_idx;
@@ -460,7 +508,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                 p.out_score[step] = best_score;
                 if (p.dbg_time) p.out_time[step] = global_timer_ns();
             }
-            s_mask[best_idx] = 0;                         // utmos/select.py:100
+            if (UT_OWNED(best_idx)) s_mask[UT_LI(best_idx)] = 0;      // utmos/select.py:100
         }
         step += 1;
         tot += best_cnt;
@@ -470,16 +518,29 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         }
         UT_TICK(t_arg);
         // ---- stream the winner's list; a live bit that we clear marks a newly covered row
-        const uint4 *lst = p.lists + (size_t)s_loff[best_idx] * ESTRIDE;
-        const int len = (int)s_llen[best_idx];
+        const uint4 *lst = p.lists + (size_t)best_off * ESTRIDE;
+        const int len = (int)best_len;
         if (next_idx != 0x7fffffff) {                     // warm L2 with the runner-up's list
-            const uint4 *l2 = p.lists + (size_t)s_loff[next_idx] * ESTRIDE;
-            const int lines = ((int)s_llen[next_idx] * ESTRIDE + 7) >> 3;    // 128-byte lines
+            const uint4 *l2 = p.lists + (size_t)next_off * ESTRIDE;
+            const int lines = ((int)next_len * ESTRIDE + 7) >> 3;    // 128-byte lines
             for (int i = tid; i < lines; i += blockDim.x) prefetch_l2(l2 + (size_t)i * 8);
         }
         const int sub = lane & 7, slot = lane >> 3;
         int staged_any = 0;
-        // retire the staged carrier lists: one 16-byte chunk (8 carriers) per thread and turn
+        // subtract one pooled chunk (16 bytes of carriers) from the gains this CTA owns
+        auto retire_chunk = [&](const uint4 &v, unsigned long long gl, unsigned long long gh) {
+            const unsigned int ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < kPerChunk; ++q) {
+                const unsigned int cs = WIDE ? ww[q] : ((q & 1) ? ww[q >> 1] >> 16 : ww[q >> 1] & 0xffffu);
+                if (cs != kPad && UT_OWNED(cs)) {
+                    n_pool += 1;
+                    atomicAdd(s_cnt + UT_LI(cs), 0xffffffffu);
+                    if (AF) { atomicAdd(s_lo + UT_LI(cs), gl); atomicAdd(s_hi + UT_LI(cs), gh); }
+                }
+            }
+        };
+        // retire the staged carrier lists: one chunk per thread and turn
         auto retire_staged = [&]() {
             const unsigned int staged_n = min(s_stage_n, cfg.stage_cap);
             for (unsigned int c0 = tid; c0 < staged_n; c0 += blockDim.x) {
@@ -490,19 +551,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     gl = ((unsigned long long)qv.y << 32) | qv.x;
                     gh = ((unsigned long long)qv.w << 32) | qv.z;
                 }
-                const unsigned int ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
-                        if (cs != 0xffffu && (CL == 1 || (int)(cs % CL) == crank)) {
-                            n_pool += 1;
-                            atomicAdd(s_cnt + cs, 0xffffffffu);
-                            if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
-                        }
-                    }
-                }
+                retire_chunk(v, gl, gh);
             }
         };
         // a pick that covers very many rows is walked in smaller batches (one entry per thread instead of four) and
@@ -530,7 +579,10 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     fresh = (*reinterpret_cast<volatile uint32_t *>(lw) & bit) != 0;
                     if (fresh) atomicAnd(lw, ~bit);
                 }
-                const unsigned int n = e[u].y & 0xffffu;
+                // narrow entry: {row, n | c0 << 16, c1 | c2 << 16, c3 | c4 << 16}; wide entry: {row, n, c0, c1};
+                // pooled (n == all ones): {row, pooled, first pool element, carriers}
+                const unsigned int n = WIDE ? e[u].y : (e[u].y & 0xffffu);
+                const bool pooled = WIDE ? n == 0xffffffffu : n == kPooled;
                 unsigned long long nl = 0, nh = 0;
                 if (AF && fresh) {
                     const uint4 qv = __ldg(lst + (size_t)i * ESTRIDE + 1);
@@ -539,33 +591,34 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                 }
                 n_walked += r != 0xffffffffu;
                 n_fresh += fresh;
-                if (fresh && n != kPooled) {
+                if (fresh && !pooled) {
                     n_inl += n;
-                    const unsigned int c[kInline] = {e[u].y >> 16, e[u].z & 0xffffu, e[u].z >> 16, e[u].w & 0xffffu,
-                                                     e[u].w >> 16};
+                    unsigned int c[kInline];
+                    if (WIDE) { c[0] = e[u].z; c[1] = e[u].w; c[2] = c[3] = c[4] = 0; }
+                    else { c[0] = e[u].y >> 16; c[1] = e[u].z & 0xffffu; c[2] = e[u].z >> 16; c[3] = e[u].w & 0xffffu; c[4] = e[u].w >> 16; }
 #pragma unroll
-                    for (int j = 0; j < kInline; ++j) {
-                        if (j < (int)n && (CL == 1 || (int)(c[j] % CL) == crank)) {
-                            atomicAdd(s_cnt + c[j], 0xffffffffu);
-                            if (AF) { atomicAdd(s_lo + c[j], nl); atomicAdd(s_hi + c[j], nh); }
+                    for (int j = 0; j < kInl; ++j) {
+                        if (j < (int)n && UT_OWNED(c[j])) {
+                            atomicAdd(s_cnt + UT_LI(c[j]), 0xffffffffu);
+                            if (AF) { atomicAdd(s_lo + UT_LI(c[j]), nl); atomicAdd(s_hi + UT_LI(c[j]), nh); }
                         }
                     }
                 }
-                // rows with many carriers keep their carrier list (uint16, padded to 8 with 0xffff, 16-byte aligned)
-                // in the pool.  The lists of all the rows this pick newly covers are copied into shared memory with
+                // rows with many carriers keep their carrier list (padded to whole 16-byte chunks, 16-byte aligned) in
+                // the pool.  The lists of all the rows this pick newly covers are copied into shared memory with
                 // cp.async -- every copy in flight at once, one global round trip whatever the number of rows -- and
                 // retired from there after the walk, flat over all threads.
-                const bool big = fresh && n == kPooled;
+                const bool big = fresh && pooled;
                 unsigned int m = 0;
                 if (__any_sync(0xffffffffu, big)) {
                     staged_any = 1;
                     // reserve chunks of the staging area (one shared-memory atomic per warp instruction: the lanes'
                     // same-address adds are serialised by the hardware, which is cheaper than a warp scan)
-                    const unsigned int n8 = big ? (e[u].w + 7) >> 3 : 0u;
+                    const unsigned int n8 = big ? (e[u].w + kPerChunk - 1) / kPerChunk : 0u;
                     const unsigned int my0 = big ? atomicAdd(&s_stage_n, n8) : 0u;
                     const bool staged = big && my0 + n8 <= cfg.stage_cap;
                     if (staged) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(pool + e[u].z);
+                        const uint4 *src = pool16 + e[u].z / kPerChunk;
                         for (unsigned int k = 0; k < n8; ++k) {
                             uint4 *dst = s_stage + (size_t)(my0 + k) * ESTRIDE;
                             const unsigned int sa = (unsigned int)__cvta_generic_to_shared(dst);
@@ -597,24 +650,13 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     const unsigned int cnt = src < 0 ? 0u : cnt_from;
                     unsigned long long gl = 0, gh = 0;
                     if (AF) { gl = __shfl_sync(0xffffffffu, nl, from); gh = __shfl_sync(0xffffffffu, nh, from); }
-                    const uint4 *pl = reinterpret_cast<const uint4 *>(pool + pbase);
-                    const unsigned int n8 = (cnt + 7) >> 3;
+                    const uint4 *pl = pool16 + pbase / kPerChunk;
+                    const unsigned int n8 = (cnt + kPerChunk - 1) / kPerChunk;
                     for (unsigned int k0 = sub; k0 < n8; k0 += 16) {
                         const uint4 v0 = __ldg(pl + k0);
                         const uint4 v1 = k0 + 8 < n8 ? __ldg(pl + k0 + 8) : make_uint4(~0u, ~0u, ~0u, ~0u);
-                        const unsigned int ww[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const unsigned int cs = h ? ww[q] >> 16 : ww[q] & 0xffffu;
-                                if (cs != 0xffffu && (CL == 1 || (int)(cs % CL) == crank)) {
-                                    n_pool += 1;
-                                    atomicAdd(s_cnt + cs, 0xffffffffu);
-                                    if (AF) { atomicAdd(s_lo + cs, gl); atomicAdd(s_hi + cs, gh); }
-                                }
-                            }
-                        }
+                        retire_chunk(v0, gl, gh);
+                        retire_chunk(v1, gl, gh);
                     }
                 }
             }
@@ -637,8 +679,10 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         // every live row of the pick is covered now: its own gain is zero (keeps sum(gains) == live list entries)
         if (tid == 0) {
             s_stage_n = 0;                                // the next walk starts after the argmax barrier
-            s_cnt[best_idx] = 0;
-            if (AF) { s_lo[best_idx] = 0; s_hi[best_idx] = 0; }
+            if (UT_OWNED(best_idx)) {
+                s_cnt[UT_LI(best_idx)] = 0;
+                if (AF) { s_lo[UT_LI(best_idx)] = 0; s_hi[UT_LI(best_idx)] = 0; }
+            }
         }
         UT_TICK(t_walk);
     }
@@ -661,12 +705,13 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     }
 
     __syncthreads();
-    for (int i = crank + CL * tid; i < p.S; i += CL * (int)blockDim.x) {       // every CTA: the samples it owns
-        p.gain_cnt[i] = s_cnt[i];
-        if (AF) { p.gain_lo[i] = s_lo[i]; p.gain_hi[i] = s_hi[i]; }
+    for (int li = tid; li < n_own; li += blockDim.x) {       // every CTA: the samples it owns
+        const int i = crank + CL * li;
+        p.gain_cnt[i] = s_cnt[li];
+        p.mask[i] = s_mask[li];
+        if (AF) { p.gain_lo[i] = s_lo[li]; p.gain_hi[i] = s_hi[li]; }
     }
     if (crank == 0) {
-        for (int i = tid; i < p.S; i += blockDim.x) p.mask[i] = s_mask[i];
         for (int i = tid; i < cfg.live_words; i += blockDim.x) p.live[i] = s_live[i];
         if (CL > 1 && !live_smem)
             for (long long i = tid; i < p.colPitchW; i += blockDim.x) p.live[i] = g_live[i];
@@ -680,22 +725,26 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             if (want_single) st->tail_single = 1;
         }
     }
+#undef UT_OWNED
+#undef UT_LI
     if (CL > 1) cg::this_cluster().sync();           // nobody leaves while a peer may still write into its shared memory
 }
 
-int tail_layout(const SelParams &p, TailCfg *cfg, size_t *smem_bytes)
+// CL: CTAs that share the per-sample state (1 = everything in one CTA)
+int tail_layout(const SelParams &p, int CL, TailCfg *cfg, size_t *smem_bytes)
 {
-    if (p.S > 65535 || p.V >= 0xffffffffll) return 0;       // carriers are uint16 (0xffff = padding), rows uint32
+    if (p.V >= 0xffffffffll || p.S <= 0) return 0;          // rows are uint32 in the edge lists
+    if (p.S > 65535 && CL == 1) return 0;                   // 16-bit carriers; wide cohorts need the cluster flavour
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int)o; };
-    const size_t S = (size_t)p.S;
+    const size_t S = ((size_t)p.S + CL - 1) / CL;           // samples whose state one CTA keeps
     take(S * 4);
     cfg->off_lo = take(p.af ? S * 8 : 0);
     cfg->off_hi = take(p.af ? S * 8 : 0);
     cfg->off_w = take(p.weights ? S * 8 : 0);
     cfg->off_mask = take(S);
-    cfg->off_loff = take(S * 4);
-    cfg->off_llen = take(S * 4);
+    cfg->off_loff = take(CL == 1 ? S * 4 : 0);              // cluster flavour: list positions travel with the winners
+    cfg->off_llen = take(CL == 1 ? S * 4 : 0);
     const size_t budget = 225 * 1024;
     if (off + 8 * 1024 > budget) return 0;
     const size_t live_bytes = (size_t)p.colPitchW * 4;
@@ -750,8 +799,11 @@ int launch_build_edges(cudaStream_t stream, const SelParams &p, const EdgeDst &d
     long long blocks = (p.V + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (p.af) build_edges_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
-    else build_edges_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    const bool wide = p.S > 65535;
+    if (p.af && wide) build_edges_kernel<2, true><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    else if (p.af) build_edges_kernel<2, false><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    else if (wide) build_edges_kernel<1, true><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    else build_edges_kernel<1, false><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
@@ -769,31 +821,41 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
     return UTMOS_OK;
 }
 
+// CTAs of the tail kernel for this problem: wide cohorts (S > 65,535) always run the cluster flavour (8 CTAs, 16 for
+// the AF flavours whose per-sample state is larger); otherwise 8 when the caller asks for the cluster flavour, else 1
+int tail_cluster_size(const SelParams &p, bool cluster)
+{
+    if (p.S > 65535) return p.af ? 16 : 8;
+    return cluster ? 8 : 1;
+}
+
 int tail_plan(const SelParams &p, int *ok_out)
 {
     TailCfg cfg;
     size_t smem = 0;
-    *ok_out = p.cols != nullptr && p.S > 0 && tail_layout(p, &cfg, &smem);
+    *ok_out = p.cols != nullptr && p.S > 0 && tail_layout(p, tail_cluster_size(p, false), &cfg, &smem);
     return UTMOS_OK;
 }
 
-// does the tail kernel keep the live mask of `p` in shared memory?  (else the cluster flavour needs kTailCluster
-// private copies of p.colPitchW words in global memory)
-int tail_live_in_smem(const SelParams &p)
+// does the tail kernel keep the live mask of `p` in shared memory?  (else the cluster flavour needs one private copy
+// of p.colPitchW words per CTA in global memory)
+int tail_live_in_smem(const SelParams &p, bool cluster)
 {
     TailCfg cfg;
     size_t smem = 0;
-    return tail_layout(p, &cfg, &smem) && cfg.live_words > 0;
+    return tail_layout(p, tail_cluster_size(p, cluster), &cfg, &smem) && cfg.live_words > 0;
 }
 
-template <int ESTRIDE, bool FAST, int CL>
+template <int ESTRIDE, bool FAST, int CL, bool WIDE>
 static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg &cfg, size_t smem, unsigned long long lists_total)
 {
-    UT_CUDA(cudaFuncSetAttribute(select_tail_kernel<ESTRIDE, FAST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = select_tail_kernel<ESTRIDE, FAST, CL, WIDE>;
+    UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CL == 1) {
-        select_tail_kernel<ESTRIDE, FAST, CL><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
+        kernel<<<1, 1024, smem, stream>>>(p, cfg, lists_total);
         return UTMOS_OK;
     }
+    if (CL > 8) UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(CL);
     lc.blockDim = dim3(1024);
@@ -804,29 +866,35 @@ static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg 
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    UT_CUDA(cudaLaunchKernelEx(&lc, select_tail_kernel<ESTRIDE, FAST, CL>, p, cfg, lists_total));
+    UT_CUDA(cudaLaunchKernelEx(&lc, kernel, p, cfg, lists_total));
     return UTMOS_OK;
 }
 
-// single_rows > 0: the cluster flavour (8 CTAs, owner computes), which returns with st->tail_single set once a pick
-// covers fewer than single_rows rows; single_rows == 0: the single-CTA flavour.
-int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int single_rows,
-                uint32_t *live_priv, int *n_launch)
+// cluster: the owner-computes cluster flavour (always for wide cohorts); it returns with st->tail_single set once a
+// pick covers fewer than single_rows rows (0 = never hand over, the only choice for wide cohorts).
+int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, bool cluster,
+                unsigned int single_rows, uint32_t *live_priv, int *n_launch)
 {
     TailCfg cfg;
     size_t smem = 0;
-    if (!tail_layout(p, &cfg, &smem)) { set_error("tail kernel: state does not fit in shared memory"); return UTMOS_E_ARG; }
-    cfg.single_rows = single_rows;
+    const bool wide = p.S > 65535;
+    const int CL = tail_cluster_size(p, cluster);
+    if (!tail_layout(p, CL, &cfg, &smem)) { set_error("tail kernel: state does not fit in shared memory"); return UTMOS_E_ARG; }
+    cfg.single_rows = wide ? 0u : single_rows;
     cfg.live_priv = live_priv;
-    if (single_rows > 0 && cfg.live_words == 0 && !live_priv) { set_error("tail kernel: cluster flavour needs private live masks"); return UTMOS_E_ARG; }
-    if (single_rows > 0) {
-        if (p.af) UT_TRY((launch_tail_t<2, false, 8>(stream, p, cfg, smem, lists_total)));
-        else if (p.weights) UT_TRY((launch_tail_t<1, false, 8>(stream, p, cfg, smem, lists_total)));
-        else UT_TRY((launch_tail_t<1, true, 8>(stream, p, cfg, smem, lists_total)));
+    if (CL > 1 && cfg.live_words == 0 && !live_priv) { set_error("tail kernel: cluster flavour needs private live masks"); return UTMOS_E_ARG; }
+    if (wide) {
+        if (p.af) UT_TRY((launch_tail_t<2, false, 16, true>(stream, p, cfg, smem, lists_total)));
+        else if (p.weights) UT_TRY((launch_tail_t<1, false, 8, true>(stream, p, cfg, smem, lists_total)));
+        else UT_TRY((launch_tail_t<1, true, 8, true>(stream, p, cfg, smem, lists_total)));
+    } else if (CL > 1) {
+        if (p.af) UT_TRY((launch_tail_t<2, false, 8, false>(stream, p, cfg, smem, lists_total)));
+        else if (p.weights) UT_TRY((launch_tail_t<1, false, 8, false>(stream, p, cfg, smem, lists_total)));
+        else UT_TRY((launch_tail_t<1, true, 8, false>(stream, p, cfg, smem, lists_total)));
     } else {
-        if (p.af) UT_TRY((launch_tail_t<2, false, 1>(stream, p, cfg, smem, lists_total)));
-        else if (p.weights) UT_TRY((launch_tail_t<1, false, 1>(stream, p, cfg, smem, lists_total)));
-        else UT_TRY((launch_tail_t<1, true, 1>(stream, p, cfg, smem, lists_total)));
+        if (p.af) UT_TRY((launch_tail_t<2, false, 1, false>(stream, p, cfg, smem, lists_total)));
+        else if (p.weights) UT_TRY((launch_tail_t<1, false, 1, false>(stream, p, cfg, smem, lists_total)));
+        else UT_TRY((launch_tail_t<1, true, 1, false>(stream, p, cfg, smem, lists_total)));
     }
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
