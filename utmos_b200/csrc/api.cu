@@ -1231,19 +1231,26 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                     g.live_words = (c->V + 31) / 32;
                     EdgeDst d;
                     memset(&d, 0, sizeof(d));
-                    d.world = c->mg_world;
+                    d.world = 1;                      // entries are built locally, whole segments are pushed afterwards
                     for (int r = 0; r < c->mg_world; ++r) {
                         char *blk = r == c->mg_rank ? (char *)c->mg_block : (char *)c->mg_peer[r];
                         g.peer_inbox_cnt[r] = (unsigned int *)(blk + l.off_cnt);
                         g.peer_flags[r] = (unsigned long long *)(blk + l.off_flags);
                         g.live_dst[r] = (uint32_t *)(blk + l.off_live);
-                        d.lists[r] = (uint4 *)(blk + l.off_lists);
-                        d.pool[r] = (unsigned short *)(blk + l.off_pool);
+                        g.lists_dst[r] = (uint4 *)(blk + l.off_lists);
+                        g.pool_dst[r] = (unsigned char *)(blk + l.off_pool);
                     }
+                    char *mine = (char *)c->mg_block;
+                    d.lists[0] = (uint4 *)(mine + l.off_lists);
+                    d.pool[0] = (unsigned short *)(mine + l.off_pool);
                     d.slot_base = c->d_my_base;
                     d.pool_base = c->d_pool_base;
                     d.row_base = c->mg_row_base;
-                    char *mine = (char *)c->mg_block;
+                    g.my_base = c->d_my_base;
+                    g.pool_base = c->d_pool_base;
+                    g.pool_cursor = c->d_pool_cursor;
+                    g.estride = (int)estride;
+                    g.pool_elem = (int)pool_elem;
                     // my merged live mask: zero the padding words; the ranks fill their own word ranges
                     UT_CUDA(cudaMemsetAsync(mine + l.off_live, 0, l.live_words * 4, c->stream));
                     UT_TRY(launch_live_counts(c->stream, q, c->d_lcnt, &c->n_launch));
@@ -1252,6 +1259,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                     UT_TRY(launch_gather_offsets(c->stream, g, c->d_list_off[0], c->d_list_len[0], c->d_my_base, c->d_cursor,
                                                  c->d_pool_base, &c->n_launch));
                     UT_TRY(launch_build_edges(c->stream, q, d, c->d_cursor, c->d_pool_cursor, &c->n_launch));
+                    UT_TRY(launch_gather_push(c->stream, g, &c->n_launch));
                     UT_TRY(launch_gather_live(c->stream, g, q.live, &c->n_launch));
                     g.seq = st.mgpu_seq + 2;       // (b) everybody's entries have landed everywhere
                     UT_TRY(launch_gather_done(c->stream, g, &c->n_launch));

@@ -131,6 +131,13 @@ struct GatherParams {
     unsigned int *peer_inbox_cnt[kMaxRanks];
     unsigned long long *peer_flags[kMaxRanks];
     uint32_t *live_dst[kMaxRanks];             // merged live masks of every rank
+    uint4 *lists_dst[kMaxRanks];               // merged edge lists of every rank (own entry = local pointer)
+    unsigned char *pool_dst[kMaxRanks];        // merged carrier pools of every rank (bytes)
+    const unsigned int *my_base;               // [S] first merged slot of this rank's entries of sample s
+    const unsigned int *pool_base;             // device scalar: first pool element of this rank
+    const unsigned int *pool_cursor;           // device scalar: pool elements this rank used (after build_edges_kernel)
+    int estride;                               // uint4 per entry (1, or 2 for AF flavours)
+    int pool_elem;                             // bytes per pool element (2, or 4 for wide cohorts)
     long long live_word0;                      // first word of this rank's rows in the merged mask
     long long live_words;                      // words this rank contributes (ceil(V/32))
     SelState *st;
@@ -260,6 +267,7 @@ int launch_gather_counts(cudaStream_t stream, const GatherParams &g, int *n_laun
 int launch_gather_offsets(cudaStream_t stream, const GatherParams &g, unsigned int *list_off, unsigned int *list_len,
                           unsigned int *my_base, unsigned int *cursor, unsigned int *pool_base, int *n_launch);
 int launch_gather_live(cudaStream_t stream, const GatherParams &g, const uint32_t *live, int *n_launch);
+int launch_gather_push(cudaStream_t stream, const GatherParams &g, int *n_launch);
 int launch_gather_done(cudaStream_t stream, const GatherParams &g, int *n_launch);
 unsigned long long mgpu_pool_share(unsigned long long live_bits);
 int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, bool cluster,
