@@ -92,3 +92,32 @@ def test_two_gpus_match_single_gpu_and_reference(use_af):
     i1, n1, s1, _ = dm.steps(100)
     dm.close()
     assert out["synth"][0] == i1.tolist() and out["synth"][1] == n1.tolist() and out["synth"][2] == s1.tolist()
+
+
+CLI_CASES = [
+    ("select_af.txt", ["-c", "20", "--af", "chunk0.jl", "chunk1.jl"]),
+    ("select_exclude.txt", ["-c", "20", "--exclude", "NA21117", "chunk0.jl", "chunk1.jl"]),
+    ("select_first.txt", ["--maxmem", "1", "tiny.hdf5"]),
+    ("select_af_h5.txt", ["--maxmem", "1", "-c", "20", "--lowmem", "tiny.af.hdf5"]),
+]
+
+
+@pytest.mark.parametrize("key,argv", CLI_CASES, ids=[c[0] + ":" + " ".join(c[1]) for c in CLI_CASES])
+def test_cli_under_torchrun_reproduces_answer_keys(key, argv, tmp_path):
+    """`torchrun --nproc-per-node 2 -m utmos_b200 select ...`: rows of every input sharded over two GPUs, rank 0
+    writes the report; byte-identical to the reference's answer keys."""
+    if _native.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "report.txt"
+    args = [a if not a.endswith((".jl", ".hdf5")) else H.fixture(a) for a in argv]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), "-m", "utmos_b200", "select", "-o", str(out)] + args
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=240, check=False)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert out.read_text() == H.answer_key(key)

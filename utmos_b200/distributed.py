@@ -82,6 +82,10 @@ class ShardedMatrix:
     def append_dense(self, chunk):
         self.local.append_dense(chunk)
 
+    def append_h5_chunks(self, *args, **kwargs):
+        self.local.append_h5_chunks(*args, **kwargs)
+
+
     def finalize(self):
         comm = self.comm
         kept = self.local.rows()

@@ -114,7 +114,23 @@ class LoadedData(dict):
             self["data"].close()
 
 
-def _load_hdf5(path, device, flags):
+def _new_matrix(num_samples, af_mode, rows_hint, device, flags, comm):
+    """One GPU: DeviceMatrix.  Under torchrun (comm given): this rank's shard of the rows (distributed.ShardedMatrix)."""
+    if comm is None:
+        return _native.DeviceMatrix(num_samples, af_mode, rows_hint=rows_hint, device=device, flags=flags)
+    from utmos_b200.distributed import ShardedMatrix  # pylint: disable=import-outside-toplevel
+    return ShardedMatrix(num_samples, af_mode, rows_hint=rows_hint // comm.world + 1, device=device, flags=flags, comm=comm)
+
+
+def _my_rows(n_rows, comm):
+    """[begin, end) of the rows of one input part this rank ingests (all of them on one GPU)."""
+    if comm is None:
+        return 0, n_rows
+    from utmos_b200.distributed import shard_bounds  # pylint: disable=import-outside-toplevel
+    return shard_bounds(n_rows, comm.rank, comm.world)
+
+
+def _load_hdf5(path, device, flags, comm=None):
     """Stream an existing utmos hdf5 (utmos/select.py:250-251) chunk by chunk into HBM."""
     with h5lite.H5File(path) as h5:
         dset = h5["data"]
@@ -123,15 +139,21 @@ def _load_hdf5(path, device, flags):
         if is_float and dset.dtype != np.float32:
             raise h5lite.H5FormatError(f"unexpected data dtype {dset.dtype}")
         af_mode = _native.AF_F32 if is_float else _native.AF_NONE
-        matrix = _native.DeviceMatrix(num_samples, af_mode, rows_hint=num_rows, device=device, flags=flags)
+        matrix = _new_matrix(num_samples, af_mode, num_rows, device, flags, comm)
         table = dset.chunk_table()
         if table is not None and len(table[0]) * dset.chunks[0] >= num_rows:
             # native chunk streamer: pread + LZF decode on all host cores into pinned staging, overlapped with the
-            # H2D copies and the packing kernels
-            matrix.append_h5_chunks(path, table[0], table[1], table[2], dset.chunks[0], num_rows, is_float, dset.has_lzf)
+            # H2D copies and the packing kernels; under torchrun every rank streams its own run of chunks
+            c_begin, c_end = _my_rows(len(table[0]), comm)
+            rows_here = max(0, min(num_rows - c_begin * dset.chunks[0], (c_end - c_begin) * dset.chunks[0]))
+            matrix.append_h5_chunks(path, table[0][c_begin:c_end], table[1][c_begin:c_end], table[2][c_begin:c_end],
+                                    dset.chunks[0], rows_here, is_float, dset.has_lzf)
         else:
-            for _first, block in dset.iter_chunks():
-                matrix.append_dense(block)
+            r_begin, r_end = _my_rows(num_rows, comm)
+            for first, block in dset.iter_chunks():
+                lo, hi = max(first, r_begin), min(first + block.shape[0], r_end)
+                if lo < hi:
+                    matrix.append_dense(block[lo - first:hi - first])
         samples = h5["samples"].read()
         stored_var_count = h5["var_count"].read() if "var_count" in h5 else None
     var_count = matrix.finalize()
@@ -141,7 +163,7 @@ def _load_hdf5(path, device, flags):
     return LoadedData(samples=samples, data=matrix, var_count=var_count)
 
 
-def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, flags=0):
+def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, flags=0, comm=None):
     """
     Load and concatenate multiple files into one HBM-resident matrix (utmos/select.py:241-321).
     if lowmem is a filename, the concatenated informative rows are also written to that hdf5 file
@@ -151,7 +173,7 @@ def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, fla
     """
     logging.info(f"Loading {len(in_files)} files")
     if lowmem == 1:
-        return _load_hdf5(in_files[0], device, flags)
+        return _load_hdf5(in_files[0], device, flags, comm)
 
     samples = None
     matrix = None
@@ -171,11 +193,11 @@ def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, fla
 
         if samples is None:
             samples = np.asarray(dat["samples"]).astype("S")
-            matrix = _native.DeviceMatrix(len(samples), af_mode, rows_hint=dat["GT"].shape[0] * len(in_files),
-                                          device=device, flags=flags)
-            if lowmem is not None:
-                writer = h5lite.H5Writer(lowmem, samples, float_data=calc_af)
-        matrix.append_packed(dat["GT"], dat["AF"] if calc_af else None)
+            matrix = _new_matrix(len(samples), af_mode, dat["GT"].shape[0] * len(in_files), device, flags, comm)
+            if lowmem is not None and (comm is None or comm.rank == 0):
+                writer = h5lite.H5Writer(lowmem, samples, float_data=calc_af)     # rank 0 writes the whole file
+        r_begin, r_end = _my_rows(dat["GT"].shape[0], comm)                       # under torchrun: this rank's rows
+        matrix.append_packed(dat["GT"][r_begin:r_end], np.asarray(dat["AF"])[r_begin:r_end] if calc_af else None)
         if writer is not None:
             writer.append_packed(dat["GT"], dat["AF"])
         load_row_count += dat["GT"].shape[0]
@@ -282,7 +304,20 @@ def select_main(cmdargs):
     global MAXMEM  # pylint: disable=global-statement
     args = parse_args(cmdargs)
 
-    data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device)
+    # `torchrun --nproc-per-node N -m utmos_b200 select ...`: one process per GPU, the rows of every input are
+    # sharded over the ranks; every rank computes the same report, rank 0 writes it
+    comm = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+        from utmos_b200.distributed import HostCollectives  # pylint: disable=import-outside-toplevel
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        comm = HostCollectives()
+        args.device = int(os.environ.get("LOCAL_RANK", str(comm.rank)))
+        if comm.rank != 0:
+            args.out = os.devnull
+
+    data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device, comm=comm)
     if data["data"].dtype == bool and args.af:
         logging.critical("HDF5 file doesn't appear to be created with --af weighted scores, remove --af or recreate hdf5")
         sys.exit(1)
