@@ -397,10 +397,12 @@ def _tail_case_oracle(use_af, weighted):
 
 @pytest.mark.parametrize("mode", ["count", "weights", "af"])
 @pytest.mark.parametrize("tail_rows", [1 << 30, 64], ids=["tail_from_step0", "cluster_head_then_tail"])
-def test_wide_cohort_more_than_65535_samples(mode, tail_rows):
+@pytest.mark.parametrize("n_samples", [70001, 30011], ids=["wide_32bit_carriers", "midsize_sliced_state"])
+def test_cohorts_whose_state_does_not_fit_one_sm(mode, tail_rows, n_samples):
     """S > 65,535: 32-bit carriers and per-sample state sliced over a thread-block cluster (the state of 70k samples
-    does not fit one SM); against the exact oracle, and against the cluster-only kernels."""
-    n_vars, n_samples, steps = 5000, 70001, 250
+    does not fit one SM); 30k samples: 16-bit carriers, but the state still has to be sliced.  Against the exact
+    oracle, and against the cluster-only kernels."""
+    n_vars, steps = 5000, 250
     coh = synth.DeviceCohort(11, n_vars, n_samples)
     gt, af = coh.to_host()
     use_af = mode == "af"

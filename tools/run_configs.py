@@ -90,52 +90,77 @@ def config_c3(args):
 
 
 def config_c4(args):
+    """hdf5 streaming.  Under torchrun every rank streams its own run of chunks of the same file (rank 0 writes it)."""
     n_samples = args.samples or 50_000
     n_vars = args.vars or 200_000
     from utmos_b200 import h5lite
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        from utmos_b200.distributed import HostCollectives
+        comm = HostCollectives()
     names = synth.sample_names(n_samples).astype("S")
     path = os.path.join(args.tmp or tempfile.gettempdir(), f"utmos_c4_{n_samples}x{n_vars}.hdf5")
     mask = np.ones(n_samples, dtype=np.uint8)
     count = usel.resolve_select_count(args.count, n_samples)
-    out = {"config": "c4", "samples": n_samples, "variants": n_vars, "dense_bytes": n_samples * n_vars, "count": args.count}
-    # the cohort: generated in HBM, mirrored to the host as packed .jl rows
-    cohort = synth.DeviceCohort(args.seed, n_vars, n_samples)
-    gt, af = cohort.to_host()
-    cohort.close()
-    # (1) reference point: the same cohort ingested from packed rows
-    dm = _native.DeviceMatrix(n_samples, _native.AF_NONE, rows_hint=n_vars)
-    dm.append_packed(gt)
-    var_count = dm.finalize()
-    idx2, new2, score2, stop2, sel2_ms = timed_selection(dm, mask, None, count)
-    out["packed"] = {"select_ms": sel2_ms, "timings": dm.timings(), "flavour": dm.info()["flavour"]}
-    dm.close()
-    # (2) write the hdf5 file of the utmos dialect (bool 'data', LZF chunks of max(1, int(1e6/4/S)) rows)
-    t0 = time.perf_counter()
-    writer = h5lite.H5Writer(path, names, float_data=False)
-    block = max(1, (256 << 20) // n_samples)
-    for r0 in range(0, n_vars, block):
-        writer.append_packed(gt[r0:r0 + block], af[r0:r0 + block])
-    writer.close(var_count)
-    out["write_s"] = time.perf_counter() - t0
-    out["hdf5_bytes"] = os.path.getsize(path)
+    out = {"config": "c4", "samples": n_samples, "variants": n_vars, "dense_bytes": n_samples * n_vars, "count": args.count,
+           "n_gpus": world}
+    idx2 = new2 = stop2 = None
+    if rank == 0:
+        # the cohort: generated in HBM, mirrored to the host as packed .jl rows
+        cohort = synth.DeviceCohort(args.seed, n_vars, n_samples, device=local_rank)
+        gt, af = cohort.to_host()
+        cohort.close()
+        # (1) reference point: the same cohort ingested from packed rows on one GPU
+        dm = _native.DeviceMatrix(n_samples, _native.AF_NONE, rows_hint=n_vars, device=local_rank)
+        dm.append_packed(gt)
+        var_count = dm.finalize()
+        idx2, new2, score2, stop2, sel2_ms = timed_selection(dm, mask, None, count)
+        out["packed"] = {"select_ms": sel2_ms, "timings": dm.timings(), "flavour": dm.info()["flavour"]}
+        dm.close()
+        # (2) write the hdf5 file of the utmos dialect (bool 'data', LZF chunks of max(1, int(1e6/4/S)) rows)
+        t0 = time.perf_counter()
+        writer = h5lite.H5Writer(path, names, float_data=False)
+        block = max(1, (256 << 20) // n_samples)
+        for r0 in range(0, n_vars, block):
+            writer.append_packed(gt[r0:r0 + block], af[r0:r0 + block])
+        writer.close(var_count)
+        out["write_s"] = time.perf_counter() - t0
+        out["hdf5_bytes"] = os.path.getsize(path)
+        del gt, af
+    if comm is not None:
+        comm.barrier()
     # (3) the --lowmem path: stream the file chunk by chunk (LZF decode on the host, pinned staging, side stream)
-    _native.timer_start(0)
+    _native.timer_start(local_rank)
     t0 = time.perf_counter()
-    data = usel.load_files([path], lowmem=1)
+    data = usel.load_files([path], lowmem=1, device=local_rank, comm=comm)
     load_wall = time.perf_counter() - t0
-    load_ms = _native.timer_stop(0)
+    load_ms = _native.timer_stop(local_rank)
     dm = data["data"]
-    assert np.array_equal(np.asarray(data["var_count"]), var_count)
-    idx, new, score, stop, sel_ms = timed_selection(dm, mask, None, count)
-    out["hdf5"] = check_run(idx, new, score, stop, mask, dm.num_vars)
-    out["hdf5"].update({"load_wall_s": load_wall, "load_device_ms": load_ms, "select_ms": sel_ms, "timings": dm.timings(),
-                        "dense_GBps_streamed": n_samples * n_vars / 1e9 / load_wall, "flavour": dm.info()["flavour"]})
+    local = dm.local if comm is not None else dm
+    _native.timer_start(local_rank)
+    dm.begin(mask, None)
+    idx, new, score, stop = dm.steps(count)
+    sel_ms = _native.timer_stop(local_rank)
+    if rank == 0:
+        assert np.array_equal(np.asarray(data["var_count"]), var_count)
+        out["hdf5"] = check_run(idx, new, score, stop, mask, dm.shape[0])
+        out["hdf5"].update({"load_wall_s": load_wall, "load_device_ms": load_ms, "select_ms": sel_ms, "timings": local.timings(),
+                            "dense_GBps_streamed": n_samples * n_vars / 1e9 / load_wall, "flavour": local.info()["flavour"]})
+        out["hdf5_and_packed_agree_bit_for_bit"] = bool(np.array_equal(idx, idx2) and np.array_equal(new, new2) and stop == stop2)
+        assert out["hdf5_and_packed_agree_bit_for_bit"]
     data.close()
-    out["hdf5_and_packed_agree_bit_for_bit"] = bool(np.array_equal(idx, idx2) and np.array_equal(new, new2) and stop == stop2)
-    assert out["hdf5_and_packed_agree_bit_for_bit"]
-    if not args.keep:
+    if comm is not None:
+        comm.barrier()
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    if rank == 0 and not args.keep:
         os.unlink(path)
-    return out
+    return out if rank == 0 else None
 
 
 def config_c5(args):

@@ -1177,7 +1177,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             if (c->lists_valid) {
                 // heavy picks: cluster of 8 CTAs, each applying the decrements of the samples it owns; light picks: one CTA
                 const unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
-                const bool cluster = wide || single_rows > 0;
+                const bool cluster = single_rows > 0 || tail_cluster_size(q, false) != 1;     // wide / mid-size cohorts: sliced state
                 uint32_t *live_priv = nullptr;
                 if (cluster && !tail_live_in_smem(q, cluster)) {
                     const size_t need = (size_t)tail_cluster_size(q, cluster) * (size_t)q.colPitchW * 4;
@@ -1387,7 +1387,7 @@ int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
     // merged edge lists for the replicated tail: as many entries as the tail hand-over budget allows (utmos_set_gains0
     // has stored the set bits of all ranks' scoring rows); every rank computes the same capacity
     c->mg_list_cap = 0;
-    if (c->mg_allow_tail && c->mg_merged_rows > 0 && c->mg_merged_rows < 0xffffffffll &&
+    if (c->mg_allow_tail && c->mg_merged_rows > 0 && c->mg_merged_rows < 0xffffffffll && tail_possible(c->S, af ? 1 : 0) &&
         !(c->flags & (UTMOS_F_NO_TAIL | UTMOS_F_NO_TRANSPOSE)))
         c->mg_list_cap = std::min<unsigned long long>(c->S > 65535 ? kListBudgetWide : kListBudget, c->total_bits) + 64;
     const MgLayout l = mg_layout(S, world, af, c->mg_list_cap, c->mg_merged_rows);

@@ -274,6 +274,7 @@ int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long list
                 unsigned int single_rows, uint32_t *live_priv, int *n_launch);
 int tail_live_in_smem(const SelParams &p, bool cluster);
 int tail_cluster_size(const SelParams &p, bool cluster);
+int tail_possible(long long S, int af);
 int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, int grid, int block,
                 unsigned int *bar_counter, ArgPartial *partials, int *n_launch);
 int mgpu_grid(int device, int *grid_out, int *block_out);

@@ -821,19 +821,37 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
     return UTMOS_OK;
 }
 
-// CTAs of the tail kernel for this problem: wide cohorts (S > 65,535) always run the cluster flavour (8 CTAs, 16 for
-// the AF flavours whose per-sample state is larger); otherwise 8 when the caller asks for the cluster flavour, else 1
+// CTAs of the tail kernel for this problem: 1 when the per-sample state fits one SM (and the caller does not ask for
+// the owner-computes cluster flavour); otherwise the state is sliced over a cluster of 8, or 16, CTAs.  Wide cohorts
+// (S > 65,535) always need the cluster.  0 = no configuration fits.
 int tail_cluster_size(const SelParams &p, bool cluster)
 {
-    if (p.S > 65535) return p.af ? 16 : 8;
-    return cluster ? 8 : 1;
+    TailCfg cfg;
+    size_t smem = 0;
+    if (!cluster && tail_layout(p, 1, &cfg, &smem)) return 1;
+    if (tail_layout(p, 8, &cfg, &smem)) return 8;
+    if (tail_layout(p, 16, &cfg, &smem)) return 16;
+    return 0;
+}
+
+// can the tail kernel run for S samples whatever the weights / live-mask size?  (multi-GPU: decided before the
+// selection starts, identically on every rank)
+int tail_possible(long long S, int af)
+{
+    SelParams p;
+    memset(&p, 0, sizeof(p));
+    p.S = (int)S;
+    p.V = 1;
+    p.af = af;
+    p.colPitchW = 1ll << 30;                          // worst case: live mask in global memory
+    static const double one = 1.0;
+    p.weights = &one;                                 // worst case: weights present
+    return tail_cluster_size(p, false) > 0;
 }
 
 int tail_plan(const SelParams &p, int *ok_out)
 {
-    TailCfg cfg;
-    size_t smem = 0;
-    *ok_out = p.cols != nullptr && p.S > 0 && tail_layout(p, tail_cluster_size(p, false), &cfg, &smem);
+    *ok_out = p.cols != nullptr && p.S > 0 && tail_cluster_size(p, false) > 0;
     return UTMOS_OK;
 }
 
@@ -843,7 +861,8 @@ int tail_live_in_smem(const SelParams &p, bool cluster)
 {
     TailCfg cfg;
     size_t smem = 0;
-    return tail_layout(p, tail_cluster_size(p, cluster), &cfg, &smem) && cfg.live_words > 0;
+    const int CL = tail_cluster_size(p, cluster);
+    return CL > 0 && tail_layout(p, CL, &cfg, &smem) && cfg.live_words > 0;
 }
 
 template <int ESTRIDE, bool FAST, int CL, bool WIDE>
@@ -879,23 +898,23 @@ int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long list
     size_t smem = 0;
     const bool wide = p.S > 65535;
     const int CL = tail_cluster_size(p, cluster);
-    if (!tail_layout(p, CL, &cfg, &smem)) { set_error("tail kernel: state does not fit in shared memory"); return UTMOS_E_ARG; }
-    cfg.single_rows = wide ? 0u : single_rows;
+    if (CL == 0 || !tail_layout(p, CL, &cfg, &smem)) { set_error("tail kernel: state does not fit in shared memory"); return UTMOS_E_ARG; }
+    // hand-over to the single-CTA flavour only when that flavour exists for this problem
+    cfg.single_rows = (CL > 1 && tail_cluster_size(p, false) == 1) ? single_rows : 0u;
     cfg.live_priv = live_priv;
     if (CL > 1 && cfg.live_words == 0 && !live_priv) { set_error("tail kernel: cluster flavour needs private live masks"); return UTMOS_E_ARG; }
+#define UT_TAIL(E, F, C, W) UT_TRY((launch_tail_t<E, F, C, W>(stream, p, cfg, smem, lists_total)))
     if (wide) {
-        if (p.af) UT_TRY((launch_tail_t<2, false, 16, true>(stream, p, cfg, smem, lists_total)));
-        else if (p.weights) UT_TRY((launch_tail_t<1, false, 8, true>(stream, p, cfg, smem, lists_total)));
-        else UT_TRY((launch_tail_t<1, true, 8, true>(stream, p, cfg, smem, lists_total)));
-    } else if (CL > 1) {
-        if (p.af) UT_TRY((launch_tail_t<2, false, 8, false>(stream, p, cfg, smem, lists_total)));
-        else if (p.weights) UT_TRY((launch_tail_t<1, false, 8, false>(stream, p, cfg, smem, lists_total)));
-        else UT_TRY((launch_tail_t<1, true, 8, false>(stream, p, cfg, smem, lists_total)));
+        if (CL == 16) { if (p.af) UT_TAIL(2, false, 16, true); else if (p.weights) UT_TAIL(1, false, 16, true); else UT_TAIL(1, true, 16, true); }
+        else { if (p.af) UT_TAIL(2, false, 8, true); else if (p.weights) UT_TAIL(1, false, 8, true); else UT_TAIL(1, true, 8, true); }
+    } else if (CL == 16) {
+        if (p.af) UT_TAIL(2, false, 16, false); else if (p.weights) UT_TAIL(1, false, 16, false); else UT_TAIL(1, true, 16, false);
+    } else if (CL == 8) {
+        if (p.af) UT_TAIL(2, false, 8, false); else if (p.weights) UT_TAIL(1, false, 8, false); else UT_TAIL(1, true, 8, false);
     } else {
-        if (p.af) UT_TRY((launch_tail_t<2, false, 1, false>(stream, p, cfg, smem, lists_total)));
-        else if (p.weights) UT_TRY((launch_tail_t<1, false, 1, false>(stream, p, cfg, smem, lists_total)));
-        else UT_TRY((launch_tail_t<1, true, 1, false>(stream, p, cfg, smem, lists_total)));
+        if (p.af) UT_TAIL(2, false, 1, false); else if (p.weights) UT_TAIL(1, false, 1, false); else UT_TAIL(1, true, 1, false);
     }
+#undef UT_TAIL
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
