@@ -1141,7 +1141,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             }
             return UTMOS_OK;
         };
-        MgLayout l;
+        MgLayout l = {};
         MgpuParams m;
         memset(&m, 0, sizeof(m));
         if (multi) {
