@@ -1208,7 +1208,12 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                         UT_TRY(launch_persistent(c->stream, q, c->grid, c->block, c->d_bar, c->d_partials, &c->n_launch));
                         c->flavour_used = 1;
                     }
-                    if (!q.regain_rows) break;
+                    if (!q.regain_rows) {
+                        // no recompute configured (no sample-major copy): still refresh st->live_bits, the host decides
+                        // the hand-over to the tail from it
+                        UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                        break;
+                    }
                     UT_TRY(launch_regain(c->stream, q, &c->n_launch));
                     UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 }

@@ -851,7 +851,8 @@ int tail_possible(long long S, int af)
 
 int tail_plan(const SelParams &p, int *ok_out)
 {
-    *ok_out = p.cols != nullptr && p.S > 0 && tail_cluster_size(p, false) > 0;
+    // (the sample-major copy is not needed: the lists are built from the variant-major rows)
+    *ok_out = p.rows != nullptr && p.S > 0 && tail_cluster_size(p, false) > 0;
     return UTMOS_OK;
 }
 
