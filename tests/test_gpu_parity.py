@@ -427,6 +427,29 @@ def test_cohorts_whose_state_does_not_fit_one_sm(mode, tail_rows, n_samples):
         assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
 
 
+@pytest.mark.timeout(60)
+def test_hand_over_without_gain_recompute_on_a_large_input():
+    """Regression: with the streaming gain recompute disabled (or no sample-major copy) the host must still see
+    live_bits shrink, else it waits for the hand-over to the tail forever once the input holds more than 2^24 bits."""
+    n_vars, n_samples = 250_000, 2504
+    coh = synth.DeviceCohort(2, n_vars, n_samples)
+    results = []
+    for regain, flags in ((-1, 0), (0, 0), (0, _native.F_NO_TRANSPOSE)):
+        dm = _native.DeviceMatrix(n_samples, _native.AF_NONE, rows_hint=n_vars, flags=flags)
+        dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, 0)
+        vc = dm.finalize()
+        assert int(vc.sum()) > 1 << 24                              # more set bits than the list budget
+        dm.set_regain_rows(regain)
+        dm.begin(np.ones(n_samples, np.uint8))
+        idx, new, _score, stop = dm.steps(n_samples)
+        results.append((idx, new, stop, dm.info()["flavour"]))
+        dm.close()
+    coh.close()
+    for idx, new, stop, flavour in results:
+        assert flavour == 3
+        assert np.array_equal(idx, results[0][0]) and np.array_equal(new, results[0][1]) and stop == results[0][2]
+
+
 def test_full_shape_properties_and_mode_agreement():
     """1kGP chr22 shape (2,504 x 1,103,547), --count -1: invariants the greedy loop must satisfy at any size,
     and all four kernel flavours must give the same ordering."""
