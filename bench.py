@@ -304,7 +304,7 @@ def main():
                            "select_tail_kernel (head: select_cluster_kernel + regain_kernel)", "select_mgpu_kernel",
                            "select_tail_kernel replicated on every rank (head: select_mgpu_kernel, hand-over: build_edges_kernel over NVLink)"][info["flavour"]],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic_from_ncu(), "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
+                "traffic": traffic_from_ncu() if world == 1 and n_vars == N_VARS else None, "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
                 "note": "latency-bound: %d dependent greedy steps, %.2f us per step; achieved = algorithmic bytes of the whole greedy loop "
                         "(SURVEY.md 8d: newly covered rows once + per step a column probe, live-mask update and gain scan) / "
                         "CUDA-event time of all its launches; traffic = ncu DRAM bytes of the tail kernel's launches of one "
