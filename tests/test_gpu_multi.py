@@ -49,6 +49,21 @@ def _worker(rank, world, port, queue, use_af):
     out["synth"] = (np.concatenate([i1, i2]).tolist(), np.concatenate([n1, n2]).tolist(),
                     np.concatenate([s1, s2]).tolist())
     sm.close()
+    # (3) a cohort beyond 65,535 samples: 32-bit carriers, sliced cluster tail on the merged lists
+    n_vars, n_samples = 6000, 70001
+    coh = synth.DeviceCohort(13, n_vars, n_samples, device=rank)
+    gt, af = coh.to_host()
+    coh.close()
+    mask = np.ones(n_samples, np.uint8)
+    mask[3::211] = 2
+    sm = ShardedMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE, device=rank, comm=comm)
+    b, e = shard_bounds(n_vars, rank, world)
+    sm.append_packed(gt[b:e], af[b:e])
+    sm.finalize()
+    sm.begin(mask)
+    i1, n1, s1, _ = sm.steps(300)
+    out["wide"] = (i1.tolist(), n1.tolist(), s1.tolist(), sm.info()["flavour"])
+    sm.close()
     if rank == 0:
         queue.put(out)
     dist.destroy_process_group()
@@ -92,6 +107,20 @@ def test_two_gpus_match_single_gpu_and_reference(use_af):
     i1, n1, s1, _ = dm.steps(100)
     dm.close()
     assert out["synth"][0] == i1.tolist() and out["synth"][1] == n1.tolist() and out["synth"][2] == s1.tolist()
+    # single-GPU run of the wide cohort
+    n_vars, n_samples = 6000, 70001
+    coh = synth.DeviceCohort(13, n_vars, n_samples)
+    mask = np.ones(n_samples, np.uint8)
+    mask[3::211] = 2
+    dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE)
+    dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
+    dm.finalize()
+    dm.begin(mask)
+    i1, n1, s1, _ = dm.steps(300)
+    dm.close()
+    coh.close()
+    assert out["wide"][3] == 5
+    assert out["wide"][0] == i1.tolist() and out["wide"][1] == n1.tolist() and out["wide"][2] == s1.tolist()
 
 
 CLI_CASES = [
