@@ -19,6 +19,7 @@
  *   utmos_select_steps         utmos/select.py:24-53     calculate_scores (scores, mask, weights, argmax)
  *                              utmos/select.py:91-112    greedy_select loop and its three stop rules
  *   utmos_convert_gt           utmos/convert.py:57-87    is_het|is_hom_alt, het/hom totals, max-alt AF, packbits
+ *   utmos_vcf_parse_gt (+ gz)  utmos/convert.py:50-53    allel.read_vcf genotype parse (host threads, BGZF aware)
  */
 #ifndef UTMOS_B200_H
 #define UTMOS_B200_H
@@ -208,6 +209,19 @@ int utmos_timer_stop(int device, double *ms_out);
  * decompress: returns decoded length or -1; compress: returns encoded length or 0 if it does not fit. */
 int64_t utmos_lzf_decompress(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_cap);
 int64_t utmos_lzf_compress(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_cap);
+
+/* ---- host-side VCF text path of `utmos convert` (no device work; csrc/vcfio.cu) ----
+ * Stands in for scikit-allel's parser, allel.read_vcf(fields=["calldata/GT","samples"]) (utmos/convert.py:50-53):
+ * the int8 GT[V][S][2] tensor these produce is what utmos_convert_gt (K1) consumes.
+ *   utmos_gz_size      uncompressed size of a gzip / BGZF buffer (exact for BGZF; ISIZE for one plain member), -1 if not gzip
+ *   utmos_gz_inflate   inflate a whole buffer; BGZF blocks in parallel on `threads` host threads (0 = all cores)
+ *   utmos_vcf_parse_gt tokenise up to max_variants data lines ('#' and empty lines skipped) into gt_out (missing = -1,
+ *                      ploidy 2, phasing ignored, ploidy > 2 truncated, FORMAT without GT = all missing); *consumed_out
+ *                      ends on a line boundary; a last line without newline is taken only when `final` is set */
+int64_t utmos_gz_size(const uint8_t *src, int64_t len, int *is_bgzf_out);
+int utmos_gz_inflate(const uint8_t *src, int64_t len, uint8_t *dst, int64_t dst_cap, int64_t *dst_len_out, int threads);
+int utmos_vcf_parse_gt(const char *text, int64_t len, int64_t n_samples, int8_t *gt_out, int64_t max_variants,
+                       int64_t *n_out, int64_t *consumed_out, int final, int threads);
 
 /* ---- synthetic benchmark / test input generated in HBM (utmos_b200/synth.py holds the NumPy mirror) ----
  * Raw device buffers for the resident-input benchmark leg, and a deterministic cohort generator:

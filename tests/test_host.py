@@ -125,6 +125,92 @@ def test_vcf_gt_token_forms():
     assert vcf._parse_gt("0/1/1") == (0, 1)
 
 
+def _bgzf(data, block=700):
+    """Minimal BGZF writer (test helper): independent gzip members with the 'BC' extra subfield + EOF block."""
+    import struct
+    import zlib
+    out = []
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i:i + block]
+        comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = comp.compress(chunk) + comp.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+                   + body + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    return b"".join(out)
+
+
+def test_native_gz_inflate_bgzf_plain_and_multimember():
+    import gzip
+    rng = np.random.default_rng(3)
+    data = bytes(rng.integers(0, 4, 50_000, dtype=np.uint8) + 48) + b"tail\n"
+    for blob in (_bgzf(data), gzip.compress(data), gzip.compress(data[:1000]) + gzip.compress(data[1000:])):
+        assert _native.gz_inflate(blob).tobytes() == data
+    assert _native.gz_inflate(_bgzf(b"")).tobytes() == b""
+    with pytest.raises(ValueError):
+        _native.gz_inflate(b"plain text, not gzip at all")
+    broken = bytearray(_bgzf(data))
+    broken[40] ^= 0xff
+    with pytest.raises(_native.NativeError):
+        _native.gz_inflate(bytes(broken))
+
+
+VCF_HEAD = "##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC\tD\n"
+VCF_LINES = [
+    "1\t10\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1/1\t./.\t0|0",
+    "1\t11\t.\tA\tC,G\t.\t.\t.\tGT:DP\t0/2:7\t.|1:3\t1:9\t0/1/2:4",          # haploid call, ploidy 3, '.|1'
+    "1\t12\t.\tA\tC\t.\t.\t.\tDP:GT\t7:0|1\t3:1|1\t9\t4:.",                    # GT second; a call without that subfield
+    "1\t13\t.\tA\tC\t.\t.\t.\tDP\t7\t3\t9\t4",                                 # no GT in FORMAT -> all missing
+    "1\t14\t.\tA\t<X>\t.\t.\t.\tGT\t10|12\t0/x\t|\t/1",                        # two-digit alleles, junk tokens
+    "1\t15\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1|0",                                    # fewer sample columns than the header
+    "1\t16\t.\tA\tC\t.\t.\t.\tGT\t0/1|1\t1|0/1\t0|1|2\t0",                    # mixed separators
+]
+
+
+@pytest.mark.parametrize("ending", ["\n", "", "\r\n"], ids=["newline", "no_final_newline", "crlf"])
+@pytest.mark.parametrize("container", ["plain", "gzip", "bgzf"])
+def test_native_vcf_tokenizer_matches_python_restatement(tmp_path, ending, container):
+    """csrc/vcfio.cu against vcf.read_vcf_genotypes_py on genotype forms the fixtures do not contain."""
+    import gzip
+    sep = "\r\n" if ending == "\r\n" else "\n"
+    text = (VCF_HEAD + sep.join(VCF_LINES) + ending).encode()
+    path = tmp_path / ("t.vcf" if container == "plain" else "t.vcf.gz")
+    path.write_bytes(text if container == "plain" else gzip.compress(text) if container == "gzip" else _bgzf(text, 97))
+    want = list(vcf.read_vcf_genotypes_py(str(path), 3))
+    for slab in (1 << 20, 150):                                  # 150-byte slabs: lines straddle slab boundaries
+        got = list(vcf.read_vcf_genotypes(str(path), 3, threads=3, slab_bytes=slab))
+        assert list(got[0][0]) == list(want[0][0])
+        a, b = np.concatenate([g for _, g in got]), np.concatenate([g for _, g in want])
+        assert a.shape == b.shape == (len(VCF_LINES), 4, 2) and np.array_equal(a, b)
+        assert all(g.shape[0] <= 3 for _, g in got)
+
+
+def test_native_vcf_tokenizer_rejects_what_it_cannot_represent(tmp_path):
+    bad = VCF_HEAD + "1\t10\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1/1\t./.\t0|0\t1|1\n"          # five calls, four samples
+    (tmp_path / "a.vcf").write_text(bad)
+    with pytest.raises(_native.NativeError):
+        list(vcf.read_vcf_genotypes(str(tmp_path / "a.vcf")))
+    big = VCF_HEAD + "1\t10\t.\tA\tC\t.\t.\t.\tGT\t0|200\t1/1\t./.\t0|0\n"                  # allele 200 does not fit int8
+    (tmp_path / "b.vcf").write_text(big)
+    with pytest.raises(_native.NativeError):
+        list(vcf.read_vcf_genotypes(str(tmp_path / "b.vcf")))
+    (tmp_path / "c.vcf").write_text("##only meta\n")
+    with pytest.raises(ValueError):
+        list(vcf.read_vcf_genotypes(str(tmp_path / "c.vcf")))
+    (tmp_path / "d.vcf").write_text(VCF_HEAD)                    # header only: one empty block
+    blocks = list(vcf.read_vcf_genotypes(str(tmp_path / "d.vcf")))
+    assert len(blocks) == 1 and blocks[0][1].shape == (0, 4, 2)
+
+
+@pytest.mark.parametrize("name", ["chunk0", "chunk1"])
+def test_native_vcf_reader_equals_python_reader_on_fixtures(name):
+    path = H.fixture(name + ".vcf.gz")
+    want = np.concatenate([g for _, g in vcf.read_vcf_genotypes_py(path, 500)])
+    for slab in (256 << 20, 90_000):
+        got = np.concatenate([g for _, g in vcf.read_vcf_genotypes(path, 333, slab_bytes=slab)])
+        assert np.array_equal(got, want)
+
+
 def test_convert_oracle_edge_genotypes():
     gt = np.array([[[0, 0], [0, 1], [1, 1], [-1, 1], [2, 1], [-1, -1], [2, 2], [1, -1]]], dtype=np.int8)
     out = orc.convert_gt_c(gt)

@@ -22,7 +22,7 @@ SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_hos
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_append_h5_chunks", "utmos_finalize", "utmos_select_begin",
            "utmos_select_steps", "utmos_convert_gt", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
            "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
-           "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_device_alloc", "utmos_device_free",
+           "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_gz_size", "utmos_gz_inflate", "utmos_vcf_parse_gt", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
 
 
@@ -82,6 +82,9 @@ def lib():
         "utmos_timer_stop": (i32, [i32, ctypes.POINTER(ctypes.c_double)]),
         "utmos_lzf_decompress": (i64, [p, i64, p, i64]),
         "utmos_lzf_compress": (i64, [p, i64, p, i64]),
+        "utmos_gz_size": (i64, [p, i64, ctypes.POINTER(i32)]),
+        "utmos_gz_inflate": (i32, [p, i64, p, i64, ctypes.POINTER(i64), i32]),
+        "utmos_vcf_parse_gt": (i32, [p, i64, i64, p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), i32, i32]),
         "utmos_device_alloc": (i32, [i32, pp, i64]),
         "utmos_device_free": (i32, [i32, p]),
         "utmos_device_to_host": (i32, [i32, p, p, i64]),
@@ -342,6 +345,44 @@ def convert_kernel_ms():
     ms = ctypes.c_double(0.0)
     check(lib().utmos_convert_kernel_ms(ctypes.byref(ms)))
     return ms.value
+
+
+def gz_inflate(data, threads=0):
+    """gzip / BGZF bytes -> uint8 array (BGZF blocks are inflated in parallel by native host threads)."""
+    src = np.frombuffer(data, dtype=np.uint8)
+    is_bgzf = ctypes.c_int(0)
+    size = lib().utmos_gz_size(_ptr(src), len(src), ctypes.byref(is_bgzf))
+    if size < 0:
+        raise ValueError("not a gzip stream")
+    if is_bgzf.value:
+        dst = np.empty(max(size, 1), dtype=np.uint8)
+        got = ctypes.c_int64(0)
+        check(lib().utmos_gz_inflate(_ptr(src), len(src), _ptr(dst), len(dst), ctypes.byref(got), int(threads)))
+        return dst[:got.value]
+    import zlib  # pylint: disable=import-outside-toplevel
+    # plain gzip: the trailer's ISIZE is only the size modulo 2^32 and members may be concatenated -> stream it
+    out, dec, view = [], zlib.decompressobj(31), memoryview(data)
+    while len(view):
+        out.append(dec.decompress(view))
+        view = memoryview(dec.unused_data)
+        if dec.eof and len(view):
+            dec = zlib.decompressobj(31)
+        elif not dec.eof:
+            break
+    return np.frombuffer(b"".join(out), dtype=np.uint8)
+
+
+def vcf_parse_gt(text, offset, n_samples, max_variants, final=True, threads=0):
+    """Tokenise up to max_variants data lines of VCF text (uint8 array) starting at `offset` ->
+    (int8 GT[n, S, 2], bytes consumed)."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    gt = np.empty((max(int(max_variants), 1), int(n_samples), 2), dtype=np.int8)
+    n = ctypes.c_int64(0)
+    used = ctypes.c_int64(0)
+    view = text[offset:]
+    check(lib().utmos_vcf_parse_gt(_ptr(view), len(view), int(n_samples), _ptr(gt), int(max_variants), ctypes.byref(n),
+                                   ctypes.byref(used), 1 if final else 0, int(threads)))
+    return gt[:n.value], used.value
 
 
 def lzf_decompress(data, out_len):

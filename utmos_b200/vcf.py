@@ -35,8 +35,103 @@ def _parse_gt(token):
     return a0, a1
 
 
-def read_vcf_genotypes(path, chunk_length=2000):
-    """Yield (samples ndarray[str], int8 GT [n<=chunk_length, S, 2]) blocks in file order."""
+SLAB_BYTES = 256 << 20          # uncompressed text handled at a time (a 1kGP chromosome VCF is ~11 GB of text)
+
+
+def _bgzf_batches(raw, slab_bytes):
+    """Split BGZF bytes into runs of whole blocks that inflate to about slab_bytes each; None if not BGZF."""
+    out, pos, start, size = [], 0, 0, 0
+    n = len(raw)
+    while pos < n:
+        if pos + 18 > n or raw[pos:pos + 3] != b"\x1f\x8b\x08" or not raw[pos + 3] & 4:
+            return None
+        xlen = raw[pos + 10] | (raw[pos + 11] << 8)
+        q, xend, bsize = pos + 12, pos + 12 + xlen, -1
+        while q + 4 <= xend:
+            slen = raw[q + 2] | (raw[q + 3] << 8)
+            if raw[q:q + 2] == b"BC" and slen == 2:
+                bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1
+            q += 4 + slen
+        if bsize < 0 or pos + bsize > n:
+            return None
+        size += int.from_bytes(raw[pos + bsize - 4:pos + bsize], "little")
+        pos += bsize
+        if size >= slab_bytes:
+            out.append((start, pos))
+            start, size = pos, 0
+    if pos > start:
+        out.append((start, pos))
+    return out
+
+
+def _text_slabs(path, threads, slab_bytes):
+    """Yield (uint8 text, is_last) pieces of the uncompressed file, in order."""
+    from utmos_b200 import _native  # pylint: disable=import-outside-toplevel
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    if raw[:2] != b"\x1f\x8b":
+        yield np.frombuffer(raw, dtype=np.uint8), True
+        return
+    batches = _bgzf_batches(raw, slab_bytes)
+    if batches is None:                                   # plain gzip: one sequential stream
+        yield _native.gz_inflate(raw, threads), True
+        return
+    view = memoryview(raw)
+    for k, (b, e) in enumerate(batches):
+        yield _native.gz_inflate(view[b:e], threads), k == len(batches) - 1
+    if not batches:
+        yield np.zeros(0, dtype=np.uint8), True
+
+
+def read_vcf_genotypes(path, chunk_length=2000, threads=0, slab_bytes=SLAB_BYTES):
+    """Yield (samples ndarray[str], int8 GT [n<=chunk_length, S, 2]) blocks in file order.
+
+    The text work is native (csrc/vcfio.cu): BGZF blocks are inflated in parallel, a slab of text at a time, and the
+    data lines are tokenised by all host cores straight into the int8 tensor.  ``read_vcf_genotypes_py`` below is
+    the pure-Python restatement of the same semantics that the tests pin the native path to."""
+    from utmos_b200 import _native  # pylint: disable=import-outside-toplevel
+    samples = None
+    carry = np.zeros(0, dtype=np.uint8)
+    emitted = False
+    for slab, is_last in _text_slabs(path, threads, slab_bytes):
+        text = np.concatenate([carry, slab]) if len(carry) else slab
+        offset = 0
+        if samples is None:
+            blob = text.tobytes()
+            pos = 0 if blob.startswith(b"#CHROM") else blob.find(b"\n#CHROM") + 1
+            if pos == 0 and not blob.startswith(b"#CHROM"):
+                if is_last:
+                    raise ValueError(f"{path}: no #CHROM header line")
+                carry = text                               # header longer than one slab: keep reading
+                continue
+            end = blob.find(b"\n", pos)
+            if end < 0:
+                if not is_last:
+                    carry = text
+                    continue
+                end = len(blob)
+            samples = np.array(blob[pos:end].decode().split("\t")[9:])
+            if len(samples) == 0:
+                raise ValueError(f"{path}: no sample columns")
+            offset = min(end + 1, len(text))
+            del blob
+        while offset < len(text):
+            gts, used = _native.vcf_parse_gt(text, offset, len(samples), chunk_length, is_last, threads)
+            offset += used
+            if gts.shape[0]:
+                emitted = True
+                yield samples, gts
+            if used == 0:
+                break
+        carry = text[offset:].copy()                       # an incomplete last line waits for the next slab
+    if samples is None:
+        raise ValueError(f"{path}: no #CHROM header line")
+    if not emitted:
+        yield samples, np.zeros((0, len(samples), 2), dtype=np.int8)
+
+
+def read_vcf_genotypes_py(path, chunk_length=2000):
+    """Pure-Python restatement (test infrastructure for the native tokenizer; slow: ~2.6 M genotypes/s)."""
     samples = None
     rows = []
     cache = {}
@@ -56,7 +151,11 @@ def read_vcf_genotypes(path, chunk_length=2000):
             row = np.full((len(samples), 2), -1, dtype=np.int8)
             if gi >= 0:
                 for s, call in enumerate(fields[9:]):
-                    tok = call if gi == 0 and ":" not in call else call.split(":")[gi]
+                    if gi == 0 and ":" not in call:
+                        tok = call
+                    else:
+                        parts = call.split(":")
+                        tok = parts[gi] if gi < len(parts) else "."     # trailing subfields may be dropped (VCF spec)
                     got = cache.get(tok)
                     if got is None:
                         got = _parse_gt(tok)
