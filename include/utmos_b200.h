@@ -199,6 +199,13 @@ int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
  * ms[0]=h2d copies, [1]=ingest kernels, [2]=transpose, [3]=column reduce / gain init, [4]=select loop */
 int utmos_timings(utmos_ctx *ctx, double *ms, int n, int reset);
 
+/* --lowmem NEW.hdf5 writer (utmos/select.py:198-231): chunk i of the 'data' dataset = rows [i*chunk_rows, +chunk_rows)
+ * of the packed .jl rows as S bool bytes each (or S float32 GT*AF each when af != NULL), zero padded past n_rows,
+ * unpacked and LZF-compressed by `threads` host threads into dst + i*chunk_nbytes; sizes_out[i] = stored bytes,
+ * masks_out[i] = 1 when the chunk is stored raw because LZF did not shrink it (hdf5 filter_mask bit 0). */
+int utmos_h5_encode_chunks(const uint8_t *rows, int64_t n_rows, int64_t pitch, int64_t n_samples, const double *af,
+                           int64_t chunk_rows, uint8_t *dst, int64_t *sizes_out, uint32_t *masks_out, int threads);
+
 /* Device stopwatch (benchmark): start/stop synchronise the device and record a CUDA event each; *ms_out is the
  * event-to-event time, i.e. it covers every kernel and copy issued by any context on that device in between. */
 int utmos_timer_start(int device);

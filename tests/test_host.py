@@ -294,3 +294,51 @@ def test_h5writer_roundtrip_bool_float_and_multilevel_btree(tmp_path):
         assert h5["data"].chunks == (4, n_samples) and h5["data"].shape == full.shape
         assert len(h5["data"]._chunk_index()) == (full.shape[0] + 3) // 4 > 64
         assert np.array_equal(h5["data"].read(), full)
+
+
+def test_h5writer_native_chunk_encoder_matches_numpy_path(tmp_path):
+    """Native encoder (unpack + LZF on host threads, csrc/hostio.cu) against the NumPy/dense path of the writer:
+    identical files, for bool and float32 data, ragged parts, uninformative rows, threads 1 and many, and parts
+    that switch between packed and dense appends while a chunk is half full."""
+    rng = np.random.default_rng(5)
+    n_samples = 1237                                                   # 202 rows per chunk, 3 pad bits per row
+    samples = synth.sample_names(n_samples).astype("S")
+    parts = []
+    for n in (150, 1, 700, 0, 409, 33):
+        dense = rng.random((n, n_samples)) < 0.03
+        dense[::17] = False                                            # uninformative rows are dropped
+        parts.append((np.packbits(dense, axis=1), rng.random(n), dense))
+    full = np.concatenate([p[2] for p in parts])
+    full = full[full.any(axis=1)]
+    for float_data in (False, True):
+        files = []
+        for tag, threads in (("py", None), ("n1", 1), ("n8", 8)):
+            path = str(tmp_path / f"{tag}{int(float_data)}.hdf5")
+            writer = h5lite.H5Writer(path, samples, float_data=float_data)
+            for gt, af, _ in parts:
+                if threads is None:
+                    writer.append_packed_py(gt, af)
+                else:
+                    writer.append_packed(gt, af, threads=threads)
+            writer.close(full.sum(axis=0))
+            files.append(open(path, "rb").read())
+        assert files[0] == files[1] == files[2]
+        with h5lite.H5File(str(tmp_path / f"n8{int(float_data)}.hdf5")) as h5:
+            assert h5["data"].shape == full.shape
+            if float_data:
+                af_all = np.concatenate([p[1] for p in parts])[np.concatenate([p[2] for p in parts]).any(axis=1)]
+                assert np.array_equal(h5["data"].read(), (full * af_all.reshape(-1, 1)).astype(np.float32))
+            else:
+                assert np.array_equal(h5["data"].read(), full)
+    # packed, dense, packed: the dense append picks up the packed rows still waiting for their chunk
+    path = str(tmp_path / "mixed.hdf5")
+    writer = h5lite.H5Writer(path, samples)
+    writer.append_packed(parts[0][0], None)
+    extra = rng.random((300, n_samples)) < 0.02
+    extra[:, 0] = True
+    writer.append_dense(extra)
+    writer.append_packed(parts[2][0], None)
+    want = np.concatenate([parts[0][2][parts[0][2].any(axis=1)], extra, parts[2][2][parts[2][2].any(axis=1)]])
+    writer.close(want.sum(axis=0))
+    with h5lite.H5File(path) as h5:
+        assert np.array_equal(h5["data"].read(), want)

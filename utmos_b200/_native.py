@@ -22,7 +22,7 @@ SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_hos
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_append_h5_chunks", "utmos_finalize", "utmos_select_begin",
            "utmos_select_steps", "utmos_convert_gt", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
            "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
-           "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_gz_size", "utmos_gz_inflate", "utmos_vcf_parse_gt", "utmos_device_alloc", "utmos_device_free",
+           "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_h5_encode_chunks", "utmos_gz_size", "utmos_gz_inflate", "utmos_vcf_parse_gt", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
 
 
@@ -82,6 +82,7 @@ def lib():
         "utmos_timer_stop": (i32, [i32, ctypes.POINTER(ctypes.c_double)]),
         "utmos_lzf_decompress": (i64, [p, i64, p, i64]),
         "utmos_lzf_compress": (i64, [p, i64, p, i64]),
+        "utmos_h5_encode_chunks": (i32, [p, i64, i64, i64, p, i64, p, p, p, i32]),
         "utmos_gz_size": (i64, [p, i64, ctypes.POINTER(i32)]),
         "utmos_gz_inflate": (i32, [p, i64, p, i64, ctypes.POINTER(i64), i32]),
         "utmos_vcf_parse_gt": (i32, [p, i64, i64, p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64), i32, i32]),
@@ -403,6 +404,24 @@ def lzf_compress(data):
     if got <= 0:
         return None
     return dst[:got].tobytes()
+
+
+def h5_encode_chunks(gt_packed, n_samples, af, chunk_rows, threads=0):
+    """Packed .jl rows -> the LZF chunks of a --lowmem 'data' dataset (bool bytes, or float32 GT*AF when af is given),
+    unpacked and compressed by native host threads.  Returns [(bytes, filter_mask)] in chunk order."""
+    gt_packed = np.ascontiguousarray(gt_packed, dtype=np.uint8)
+    n_rows, pitch = gt_packed.shape
+    if af is not None:
+        af = np.ascontiguousarray(np.asarray(af, dtype=np.float64).reshape(-1))
+    n_chunks = (n_rows + chunk_rows - 1) // chunk_rows
+    chunk_nbytes = int(chunk_rows) * int(n_samples) * (4 if af is not None else 1)
+    dst = np.empty(max(n_chunks * chunk_nbytes, 1), dtype=np.uint8)
+    sizes = np.zeros(max(n_chunks, 1), dtype=np.int64)
+    masks = np.zeros(max(n_chunks, 1), dtype=np.uint32)
+    if n_chunks:
+        check(lib().utmos_h5_encode_chunks(_ptr(gt_packed), n_rows, pitch, int(n_samples), _ptr(af), int(chunk_rows), _ptr(dst),
+                                           _ptr(sizes), _ptr(masks), int(threads)))
+    return [(dst[i * chunk_nbytes:i * chunk_nbytes + int(sizes[i])].tobytes(), int(masks[i])) for i in range(n_chunks)]
 
 
 class DeviceBuffer:

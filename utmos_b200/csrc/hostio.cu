@@ -8,6 +8,11 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 extern "C" {
@@ -88,6 +93,63 @@ int64_t utmos_lzf_compress(const uint8_t *src, int64_t n, uint8_t *dst, int64_t 
     }
     if (!flush_literals(n)) return 0;
     return op;
+}
+
+// Chunks of the 'data' dataset of a --lowmem file straight from packed .jl rows (utmos/select.py:198-231): chunk i
+// holds rows [i*chunk_rows, (i+1)*chunk_rows) as S bool bytes each, or S float32 GT*AF each when af != NULL; rows past
+// n_rows are zero (h5py pads the last chunk).  Every chunk is unpacked and LZF-compressed by one of `threads` host
+// threads into dst + i*chunk_nbytes: sizes_out[i] = compressed bytes and masks_out[i] = 0, or the raw bytes and
+// masks_out[i] = 1 when LZF does not shrink it (what the hdf5 lzf filter does).
+int utmos_h5_encode_chunks(const uint8_t *rows, int64_t n_rows, int64_t pitch, int64_t n_samples, const double *af,
+                           int64_t chunk_rows, uint8_t *dst, int64_t *sizes_out, uint32_t *masks_out, int threads)
+{
+    if (!rows || n_rows < 0 || pitch < (n_samples + 7) / 8 || n_samples <= 0 || chunk_rows <= 0 || !dst || !sizes_out || !masks_out) {
+        utmos::set_error("h5_encode_chunks: bad arguments");
+        return UTMOS_E_ARG;
+    }
+    const int64_t n_chunks = (n_rows + chunk_rows - 1) / chunk_rows;
+    const size_t item = af ? 4 : 1;
+    const size_t chunk_nbytes = (size_t)chunk_rows * (size_t)n_samples * item;
+    int hw = (int)std::thread::hardware_concurrency();
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(threads > 0 ? threads : (hw > 0 ? hw : 1), 64), n_chunks));
+    std::atomic<int64_t> next(0);
+    auto worker = [&]() {
+        std::vector<uint8_t> dense(chunk_nbytes);
+        for (;;) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= n_chunks) return;
+            memset(dense.data(), 0, chunk_nbytes);
+            for (int64_t i = 0; i < chunk_rows; ++i) {
+                const int64_t r = c * chunk_rows + i;
+                if (r >= n_rows) break;
+                const uint8_t *row = rows + (size_t)r * (size_t)pitch;
+                if (af) {
+                    float *out = reinterpret_cast<float *>(dense.data()) + (size_t)i * (size_t)n_samples;
+                    const float v = (float)af[r];                     // (bool * float64).astype(float32), select.py:222
+                    for (int64_t s = 0; s < n_samples; ++s)
+                        if (row[s >> 3] & (0x80u >> (s & 7))) out[s] = v;
+                } else {
+                    uint8_t *out = dense.data() + (size_t)i * (size_t)n_samples;
+                    for (int64_t s = 0; s < n_samples; ++s) out[s] = (row[s >> 3] >> (7 - (s & 7))) & 1u;
+                }
+            }
+            uint8_t *slot = dst + (size_t)c * chunk_nbytes;
+            const int64_t got = utmos_lzf_compress(dense.data(), (int64_t)chunk_nbytes, slot, (int64_t)chunk_nbytes - 1);
+            if (got > 0) {
+                sizes_out[c] = got;
+                masks_out[c] = 0;
+            } else {
+                memcpy(slot, dense.data(), chunk_nbytes);
+                sizes_out[c] = (int64_t)chunk_nbytes;
+                masks_out[c] = 1;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    return UTMOS_OK;
 }
 
 }  // extern "C"

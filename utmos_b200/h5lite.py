@@ -387,6 +387,15 @@ class _ChunkedDataset:
         self.chunks.append((self.rows, addr, len(comp), mask))
         self.rows += rows.shape[0]
 
+    def append_encoded(self, blobs, rows):
+        """Chunks that were encoded elsewhere (native encoder): [(bytes, filter_mask)] holding `rows` dataset rows."""
+        if self.pending is not None and self.pending.shape[0]:
+            raise H5FormatError("encoded chunks cannot follow a partial dense chunk")
+        for k, (blob, mask) in enumerate(blobs):
+            addr = self.w._write(blob)
+            self.chunks.append((self.rows + k * self.chunk_rows, addr, len(blob), mask))
+        self.rows += rows
+
     def finish(self):
         if self.pending is not None and self.pending.shape[0]:
             tail = self.pending
@@ -459,6 +468,7 @@ class H5Writer:
         self.float_data = bool(float_data)
         self._fh = open(path, "wb")
         self._pos = 0
+        self._pend_gt = self._pend_af = None                       # packed rows that do not fill a chunk yet
         self._write(b"\x00" * 96)                                  # superblock + root entry, patched in close()
         c_rows = max(1, int(1e6 / 4 / self.n_samples))             # utmos/select.py:205
         if self.float_data:
@@ -485,8 +495,44 @@ class H5Writer:
         self._fh.write(payload)
 
     # -- rows -------------------------------------------------------------------------------------
-    def append_packed(self, gt_packed, af):
-        """One .jl part: informative rows only (utmos/select.py:275-280), dense bool or float32 GT*AF (:219-223)."""
+    def append_packed(self, gt_packed, af, threads=0):
+        """One .jl part: informative rows only (utmos/select.py:275-280), dense bool or float32 GT*AF (:219-223).
+        Whole chunks are unpacked and LZF-compressed by native host threads (csrc/hostio.cu); rows that do not fill
+        a chunk wait, still packed, for the next part."""
+        gt_packed = np.ascontiguousarray(gt_packed, dtype=np.uint8)
+        af = None if af is None else np.asarray(af, dtype=np.float64).reshape(-1)
+        if self.data.pending is not None and self.data.pending.shape[0]:
+            return self.append_packed_py(gt_packed, af)          # dense rows are pending: stay on the dense path
+        keep = gt_packed.any(axis=1)                             # pad bits are zero (np.packbits)
+        gt_packed = gt_packed[keep]
+        af_kept = af[keep] if self.float_data else None
+        if self._pend_gt is not None and self._pend_gt.shape[0]:
+            gt_packed = np.concatenate([self._pend_gt, gt_packed])
+            if self.float_data:
+                af_kept = np.concatenate([self._pend_af, af_kept])
+        c_rows = self.data.chunk_rows
+        batch = max(c_rows, (256 << 20) // max(1, self.n_samples * self.data.itemsize) // c_rows * c_rows)
+        n_full = gt_packed.shape[0] // c_rows * c_rows
+        for r0 in range(0, n_full, batch):
+            r1 = min(n_full, r0 + batch)
+            blobs = _native.h5_encode_chunks(gt_packed[r0:r1], self.n_samples, af_kept[r0:r1] if self.float_data else None,
+                                             c_rows, threads)
+            self.data.append_encoded(blobs, r1 - r0)
+        self._pend_gt = gt_packed[n_full:].copy()
+        self._pend_af = af_kept[n_full:].copy() if self.float_data else None
+        return None
+
+    def _flush_packed(self):
+        """Rows that did not fill a chunk: one last, zero padded chunk (or back to the dense path)."""
+        if self._pend_gt is None or not self._pend_gt.shape[0]:
+            return
+        gt, af = self._pend_gt, self._pend_af
+        self._pend_gt = self._pend_af = None
+        blobs = _native.h5_encode_chunks(gt, self.n_samples, af if self.float_data else None, self.data.chunk_rows)
+        self.data.append_encoded(blobs, gt.shape[0])
+
+    def append_packed_py(self, gt_packed, af):
+        """NumPy restatement of append_packed (and the path taken when dense rows are pending)."""
         gt_packed = np.asarray(gt_packed)
         af = None if af is None else np.asarray(af, dtype=np.float64).reshape(-1)
         step = 8192
@@ -499,6 +545,11 @@ class H5Writer:
             self.data.append(dense)
 
     def append_dense(self, block):
+        if self._pend_gt is not None and self._pend_gt.shape[0]:
+            # packed rows are waiting for their chunk to fill: continue densely from them
+            gt, af = self._pend_gt, self._pend_af
+            self._pend_gt = self._pend_af = None
+            self.append_packed_py(gt, af if self.float_data else None)
         self.data.append(np.asarray(block, dtype=np.float32 if self.float_data else bool))
 
     # -- finish -----------------------------------------------------------------------------------
@@ -510,6 +561,7 @@ class H5Writer:
         return addr
 
     def close(self, var_count):
+        self._flush_packed()
         self.data.finish()
         width = max(1, self.samples.dtype.itemsize)
         str_type = struct.pack("<BBBBI", 0x13, 0x01, 0, 0, width)
