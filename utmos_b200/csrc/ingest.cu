@@ -7,6 +7,8 @@
 // every later kernel can use aligned 128-bit loads.
 //
 // Algorithmic bytes per chunk: read V*P (+8V AF), write V'*pitch (+8V').
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -222,6 +224,24 @@ __device__ __forceinline__ uint32_t smem_le32(const uint32_t *s32, unsigned int 
     return __funnelshift_r(s32[a], s32[a + 1], (o & 3u) * 8u);
 }
 
+// bytes [lo, hi) of the staged tile, hi - lo < 16: nonzero?
+__device__ __forceinline__ uint32_t smem_bytes_any(const uint32_t *s32, unsigned int lo, unsigned int hi)
+{
+    uint32_t any = 0;
+    for (unsigned int j = lo; j < hi; j += 4) {
+        uint32_t x = smem_le32(s32, j);
+        const unsigned int n = hi - j;
+        if (n < 4) x &= (1u << (8u * n)) - 1u;
+        any |= x;
+    }
+    return any;
+}
+
+// FLAVOUR 0: one warp ORs the words of a row (first version).  FLAVOUR 1: the load loop records which 16-byte
+// pieces are nonzero in a bitmap, one thread per row then tests the bitmap bits of the pieces that lie wholly
+// inside its row and the few bytes it shares with its neighbours; the store loop splits its unit index without
+// an integer division.
+template <int FLAVOUR>
 __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *__restrict__ raw, long long n_rows,
                                                                  long long pitch_in, const double *__restrict__ af_in,
                                                                  int S, int pitchW, int rows_per_tile, long long n_tiles,
@@ -234,6 +254,7 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
     __shared__ unsigned long long s_excl;
     __shared__ unsigned short s_src[kFastMaxRows];
     __shared__ uint8_t s_flag[kFastMaxRows];
+    __shared__ uint32_t s_nz[(kFastSmemRaw + 64) / 16 / 32 + 10];      // FLAVOUR 1: bit i = staged piece i is nonzero
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = (unsigned int)atomicAdd(state, 1ull);
     __syncthreads();
@@ -247,34 +268,84 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
     const unsigned int mis = (unsigned int)(start - a0);
     const int n16 = (int)((end - a0 + 15) >> 4);
     uint4 *s16 = reinterpret_cast<uint4 *>(f_smem);
-    for (int i = tid; i < n16 + 2; i += kThreads) {            // two extra zeroed pieces: reads past the last row stay in bounds
-        const long long off = a0 + 16ll * i;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (i < n16) {
-            if (off + 16 <= total_bytes) {
-                v = ld_stream_u128(reinterpret_cast<const uint4 *>(raw + off));
-            } else {
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
-                for (int b = 0; b < 16 && off + b < total_bytes; ++b) w[b >> 2] |= (uint32_t)__ldg(raw + off + b) << (8 * (b & 3));
-                v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        s16[i] = v;
-    }
-    __syncthreads();
     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(f_smem);
     const int nW = (S + 31) / 32;
     const uint32_t last_mask = (S & 31) ? ((1u << (S & 31)) - 1u) : 0xffffffffu;
-    for (int i = warp; i < nr; i += kThreads / 32) {
-        const unsigned int o = mis + (unsigned int)i * (unsigned int)pitch_in;
-        uint32_t any = 0;
-        for (int k = lane; k < nW; k += 32) {
-            uint32_t x = smem_le32(s32, o + 4u * k);              // bit order does not matter for "any"
-            if (k == nW - 1) x = msb_bytes_to_word(x) & last_mask;
-            any |= x;
+    if (FLAVOUR == 0) {
+        for (int i = tid; i < n16 + 2; i += kThreads) {        // two extra zeroed pieces: reads past the last row stay in bounds
+            const long long off = a0 + 16ll * i;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n16) {
+                if (off + 16 <= total_bytes) {
+                    v = ld_stream_u128(reinterpret_cast<const uint4 *>(raw + off));
+                } else {
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    for (int b = 0; b < 16 && off + b < total_bytes; ++b) w[b >> 2] |= (uint32_t)__ldg(raw + off + b) << (8 * (b & 3));
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            s16[i] = v;
         }
-        any = __ballot_sync(0xffffffffu, any != 0);
-        if (lane == 0) s_flag[i] = any ? 1 : 0;
+        __syncthreads();
+        for (int i = warp; i < nr; i += kThreads / 32) {
+            const unsigned int o = mis + (unsigned int)i * (unsigned int)pitch_in;
+            uint32_t any = 0;
+            for (int k = lane; k < nW; k += 32) {
+                uint32_t x = smem_le32(s32, o + 4u * k);          // bit order does not matter for "any"
+                if (k == nW - 1) x = msb_bytes_to_word(x) & last_mask;
+                any |= x;
+            }
+            any = __ballot_sync(0xffffffffu, any != 0);
+            if (lane == 0) s_flag[i] = any ? 1 : 0;
+        }
+    } else {
+        const uint4 *g16 = reinterpret_cast<const uint4 *>(raw + a0);
+        const int n_in = (int)min((long long)n16, (total_bytes - a0) >> 4);     // pieces that lie wholly inside the input
+        const int n_iter = (n16 + 2 + kThreads - 1) / kThreads * kThreads;      // whole warps: the ballot needs every lane
+        for (int i = tid; i < n_iter; i += kThreads) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n_in) {
+                v = ld_stream_u128(g16 + i);
+            } else if (i < n16) {                                               // the last piece of the input, byte by byte
+                const long long off = a0 + 16ll * i;
+                unsigned long long lo = 0ull, hi = 0ull;
+                for (int b = 0; b < 16 && off + b < total_bytes; ++b) {
+                    const unsigned long long x = __ldg(raw + off + b);
+                    if (b < 8) lo |= x << (8 * b);
+                    else hi |= x << (8 * (b - 8));
+                }
+                v = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+            }
+            if (i < n16 + 2) s16[i] = v;
+            const uint32_t nz = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u);
+            if (lane == 0 && i < n16 + 2) s_nz[i >> 5] = nz;
+        }
+        __syncthreads();
+        if (tid < nr) {
+            const int nbytes = (S + 7) / 8;
+            const unsigned int b0 = mis + (unsigned int)tid * (unsigned int)pitch_in;
+            unsigned int b1 = b0 + (unsigned int)nbytes;
+            uint32_t any = 0;
+            if (S & 7) {                                          // pad bits of the last byte do not count (MSB-first)
+                b1 -= 1;
+                any = (smem_le32(s32, b1) & 0xffu) & (0xff00u >> (S & 7));
+            }
+            if (!any && b0 < b1) {
+                const unsigned int m0 = min(b1, (b0 + 15u) & ~15u);       // [b0, m0): bytes shared with the row before
+                const unsigned int m1 = max(m0, b1 & ~15u);               // [m1, b1): bytes shared with the row after
+                unsigned int pa = m0 >> 4;
+                const unsigned int pb = m1 >> 4;                          // pieces [pa, pb) lie wholly inside the row
+                while (pa < pb && !any) {
+                    const unsigned int wi = pa >> 5, lo = pa & 31u;
+                    const unsigned int n = min(32u - lo, pb - pa);
+                    const uint32_t m = (n == 32u ? 0xffffffffu : ((1u << n) - 1u)) << lo;
+                    any = s_nz[wi] & m;
+                    pa += n;
+                }
+                if (!any) any = smem_bytes_any(s32, b0, m0) | smem_bytes_any(s32, m1, b1);
+            }
+            s_flag[tid] = any ? 1 : 0;
+        }
     }
     __syncthreads();
     const unsigned int keep = (tid < nr && s_flag[tid]) ? 1u : 0u;
@@ -321,8 +392,18 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
     const int q4 = pitchW >> 2;
     uint4 *out16 = reinterpret_cast<uint4 *>(rows_out + base * pitchW);
     const int units = (int)total * q4;
+    const float inv_q4 = 1.0f / (float)q4;
     for (int u = tid; u < units; u += kThreads) {
-        const int k = u / q4, q = u - k * q4;
+        int k, q;
+        if (FLAVOUR == 0) {
+            k = u / q4;
+            q = u - k * q4;
+        } else {                                                  // units < 2^20: the float quotient is off by one at most
+            k = (int)__fmul_rz((float)u, inv_q4);
+            q = u - k * q4;
+            if (q < 0) { k -= 1; q += q4; }
+            else if (q >= q4) { k += 1; q -= q4; }
+        }
         const unsigned int o = mis + (unsigned int)s_src[k] * (unsigned int)pitch_in + 16u * q;
         const unsigned int a = o >> 2, sh = (o & 3u) * 8u;
         const uint32_t r0 = s32[a], r1 = s32[a + 1], r2 = s32[a + 2], r3 = s32[a + 3], r4 = s32[a + 4];
@@ -466,20 +547,36 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
     long long *d_total = d_nrows + 1;
     if (kind == RAW_PACKED_MSB && ((uintptr_t)raw & 15u) == 0 && (size_t)pitch_in + 64 <= kFastSmemRaw &&
         n_rows * pitch_in < (1ll << 46)) {
-        const size_t tile_budget = std::max(kFastTileBytes, (size_t)pitch_in + 64);
+        static size_t tile_pref = 0;
+        if (!tile_pref) {
+            const char *env = getenv("UTMOS_B200_INGEST_TILE");   // bytes staged per CTA (A/B runs)
+            const long long want = env ? atoll(env) : 0;
+            tile_pref = want >= 1024 && (size_t)want <= kFastSmemRaw ? (size_t)want : kFastTileBytes;
+        }
+        const size_t tile_budget = std::max(tile_pref, (size_t)pitch_in + 64);
         const int R = (int)std::min<long long>(kFastMaxRows, (long long)((tile_budget - 64) / (size_t)pitch_in));
         const long long n_tiles = (n_rows + R - 1) / R;
         const size_t smem = ((size_t)R * (size_t)pitch_in + 31) / 16 * 16 + 48;
         static bool configured = false;
+        static int flavour = 1;
         if (!configured) {
-            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(kFastSmemRaw + 64)));
+            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kFastSmemRaw + 64)));
+            const char *env = getenv("UTMOS_B200_INGEST");       // 0: first version of the kernel (kept for A/B runs)
+            if (env) flavour = atoi(env) != 0;
             configured = true;
         }
         UT_CUDA(cudaMemsetAsync(sc.tile_state, 0, sizeof(unsigned long long) * (size_t)(n_tiles + 1), stream));
-        ingest_packed_kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>(
-            (const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles, sc.tile_state, d_nrows, d_total,
-            rows_out, af_out);
+        if (flavour)
+            ingest_packed_kernel<1><<<(unsigned)n_tiles, kThreads, smem, stream>>>(
+                (const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles, sc.tile_state, d_nrows, d_total,
+                rows_out, af_out);
+        else
+            ingest_packed_kernel<0><<<(unsigned)n_tiles, kThreads, smem, stream>>>(
+                (const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles, sc.tile_state, d_nrows, d_total,
+                rows_out, af_out);
         bump_rows_kernel<<<1, 1, 0, stream>>>(d_nrows, d_total);
         *n_launch += 2;
         UT_CUDA(cudaGetLastError());

@@ -46,6 +46,10 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
     return x;
 }
 
+// KEEP_L2: the 64-byte pieces are read with plain read-only loads.  A streaming (L1::no_allocate) load is looked up
+// evict-first in L2, where the whole 128-byte line is fetched: the half the neighbouring column tile needs was gone
+// again before that CTA asked for it, and DRAM read every line twice (ncu r1: 707 MB for a 353 MB matrix).
+template <bool KEEP_L2>
 __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__restrict__ rows, long long V,
                                                              int pitchW, int S32, uint32_t *__restrict__ cols,
                                                              long long colPitchW, int col_tiles)
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__r
     uint32_t *s_out = t_smem + kTRows * kTInPitch;             // [1024][kTOutPitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // 1-D grid, column tile fastest: the CTAs that share the 128-byte lines of the same rows run back to back, so the
-    // second 64-byte half of every line comes from L2 instead of DRAM (ncu: 707 MB read for 353 MB before this)
+    // second 64-byte half of every line comes from L2 instead of DRAM
     const long long row_tile = blockIdx.x / col_tiles;
     const int col_tile = (int)(blockIdx.x - row_tile * col_tiles);
     const long long r0 = row_tile * kTRows;
@@ -66,7 +70,10 @@ __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__r
         const long long r = r0 + row;
         const int w = w0 + q * 4;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < V && w < pitchW) v = ld_stream_u128(reinterpret_cast<const uint4 *>(rows + r * pitchW + w));
+        if (r < V && w < pitchW) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(rows + r * pitchW + w);
+            v = KEEP_L2 ? __ldg(src) : ld_stream_u128(src);
+        }
         uint32_t *d = s_in + row * kTInPitch + q * 4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
@@ -87,6 +94,62 @@ __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__r
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
+}
+
+// K2b, register flavour.  CTA tile = 256 rows x 32 words (1,024 samples): every row piece is one 128-byte run read by
+// eight neighbouring threads, staged in shared memory, then thread (c, g) = (tid >> 3, tid & 7) takes the 32x32 bit
+// block of word column c and row group g into 32 registers, transposes it there (5 stages of 16 masked swaps: no
+// shuffles, no second staging buffer, one barrier per tile) and stores word g of samples c*32 .. c*32+31: for a given
+// sample the eight lanes g = 0..7 write one aligned 32-byte sector.  Shared layout: row r at r*33 + (r >> 5)*4 words
+// (the staging stores and the column reads are both bank-conflict free).
+constexpr int kRRows = 256;
+constexpr int kRWords = 32;
+constexpr int kRPitch = 33;
+constexpr size_t kTransposeRegSmem = ((size_t)kRRows * kRPitch + (kRRows / 32) * 4) * 4;
+
+__global__ void __launch_bounds__(256, 5) transpose_bits_reg_kernel(const uint32_t *__restrict__ rows, long long V,
+                                                                    int pitchW, int nWS, uint32_t *__restrict__ cols,
+                                                                    long long colPitchW, int col_tiles)
+{
+    extern __shared__ __align__(16) uint32_t t_smem[];
+    const long long row_tile = blockIdx.x / col_tiles;          // column tile fastest: the CTAs that share the
+    const int col_tile = (int)(blockIdx.x - row_tile * col_tiles);   // 128-byte lines of a row run back to back (L2)
+    const long long r0 = row_tile * kRRows;
+    const int w0 = col_tile * kRWords;
+#pragma unroll
+    for (int it = 0; it < kRRows * (kRWords / 4) / 256; ++it) {
+        const int i = it * 256 + threadIdx.x;
+        const int row = i >> 3, q = i & 7;
+        const long long r = r0 + row;
+        const int w = w0 + q * 4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < V && w < pitchW) v = __ldg(reinterpret_cast<const uint4 *>(rows + r * pitchW + w));
+        uint32_t *d = t_smem + row * kRPitch + (row >> 5) * 4 + q * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    const int c = threadIdx.x >> 3, g = threadIdx.x & 7;
+    if (w0 + c >= nWS) return;                                   // word columns past the last sample
+    uint32_t a[32];
+    const uint32_t *src = t_smem + (g * 32) * kRPitch + g * 4 + c;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = src[i * kRPitch];
+    // a[i] bit j  ->  a[j] bit i  (LSB-first on both axes)
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if ((k & j) == 0) {
+                const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+                a[k] ^= t << j;
+                a[k + j] ^= t;
+            }
+        }
+    }
+    uint32_t *dst = cols + (long long)(w0 + c) * 32 * colPitchW + row_tile * (kRRows / 32) + g;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dst[(long long)j * colPitchW] = a[j];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1134,12 +1197,28 @@ int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int
     const int col_tiles = (pitchW + kTWords - 1) / kTWords;
     if (row_tiles * col_tiles > 0x7fffffffll) { set_error("transpose: matrix too large"); return UTMOS_E_ARG; }
     static bool configured = false;
+    static int flavour = 2;
     if (!configured) {
-        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
+        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
+        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
+        UT_CUDA(cudaFuncSetAttribute(transpose_bits_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeRegSmem));
+        // A/B runs: 0 = shuffle flavour with streaming loads (first version), 1 = shuffle flavour, 2 = register flavour
+        const char *env = getenv("UTMOS_B200_TRANSPOSE");
+        if (env) flavour = atoi(env);
         configured = true;
     }
-    const unsigned grid = (unsigned)(row_tiles * col_tiles);
-    transpose_bits_kernel<<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW, col_tiles);
+    if (flavour == 2) {
+        const int reg_col_tiles = (pitchW + kRWords - 1) / kRWords;
+        if (row_tiles * reg_col_tiles > 0x7fffffffll) { set_error("transpose: matrix too large"); return UTMOS_E_ARG; }
+        transpose_bits_reg_kernel<<<(unsigned)(row_tiles * reg_col_tiles), 256, kTransposeRegSmem, stream>>>(
+            rows, V, pitchW, S32 / 32, cols, colPitchW, reg_col_tiles);
+    } else {
+        const unsigned grid = (unsigned)(row_tiles * col_tiles);
+        if (flavour == 1)
+            transpose_bits_kernel<true><<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW, col_tiles);
+        else
+            transpose_bits_kernel<false><<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW, col_tiles);
+    }
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
