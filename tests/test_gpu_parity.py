@@ -521,3 +521,38 @@ def test_read_vcf_no_singleton_matches_oracle():
     assert np.array_equal(data["GT"], o["GT"])
     assert np.array_equal(data["AF"], o["AF"], equal_nan=True)
     assert data["stats"] == o["stats"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_samples,n_vars", [(517, 150_000), (40, 400_000), (9001, 20_000)],
+                         ids=["pitch65", "pitch5_many_tiles", "pitch1126"])
+def test_ingest_many_tiles_with_uninformative_runs(n_samples, n_vars):
+    """K2 over thousands of tiles (the look-back walks several windows) with runs of uninformative rows, garbage in the
+    pad bits and several appends: kept rows, their order (AF stays attached to its row) and var_count
+    (utmos/select.py:275-284) against NumPy, then greedy steps against the C oracle."""
+    rng = np.random.default_rng(n_samples)
+    dense = rng.random((n_vars, n_samples)) < (0.02 if n_samples > 100 else 0.08)
+    runs = rng.random(n_vars // 64 + 1) < 0.35                        # 64-row runs without a carrier
+    dense[np.repeat(runs, 64)[:n_vars]] = False
+    dense[rng.random(n_vars) < 0.2] = False                            # and scattered single rows
+    gt = np.packbits(dense, axis=1)
+    if n_samples & 7:                                                  # pad bits set on some rows: they carry nothing
+        noisy = rng.random(n_vars) < 0.3
+        gt[noisy, -1] |= rng.integers(0, 1 << (8 - (n_samples & 7)), int(noisy.sum())).astype(np.uint8)
+    af = rng.random(n_vars)
+    keep = dense.any(axis=1)
+    mask = np.ones(n_samples, np.uint8)
+    for af_mode, afs in ((_native.AF_NONE, None), (_native.AF_F64, af)):
+        dm = _native.DeviceMatrix(n_samples, af_mode)
+        cuts = [0, 1, n_vars // 3, n_vars // 3 + 257, n_vars]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            dm.append_packed(gt[a:b], af[a:b])
+        vc = dm.finalize()
+        assert dm.num_vars == int(keep.sum())
+        assert np.array_equal(vc, dense.sum(axis=0))
+        dm.begin(mask)
+        idx, new, score, _ = dm.steps(12)
+        clean = np.packbits(dense[keep], axis=1)
+        o_idx, o_new, o_score, _ = orc.greedy_c(clean, n_samples, mask, None, None if afs is None else afs[keep], 12, exact=True)
+        assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
+        dm.close()
