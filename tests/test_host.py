@@ -342,3 +342,47 @@ def test_h5writer_native_chunk_encoder_matches_numpy_path(tmp_path):
     writer.close(want.sum(axis=0))
     with h5lite.H5File(path) as h5:
         assert np.array_equal(h5["data"].read(), want)
+
+
+def test_vcf_text_is_streamed_from_pipes_and_large_inputs(tmp_path):
+    """`bcftools view ... | utmos convert /dev/stdin out.jl` (reference README.md:80-84): the text arrives through a
+    pipe, in every container, in bounded pieces; multi-member gzip and BGZF runs that straddle read boundaries."""
+    import gzip
+    import subprocess
+    import sys
+    rng = np.random.default_rng(11)
+    n_samples, n_lines = 40, 6000                                       # ~1 MB of text: several 64 KB reads
+    names = "\t".join(f"s{i}" for i in range(n_samples))
+    alleles = rng.integers(0, 3, (n_lines, n_samples, 2))
+    lines = ["1\t%d\t.\tA\tC,G\t.\t.\t.\tGT\t%s" % (i + 1, "\t".join(f"{a}|{b}" for a, b in row))
+             for i, row in enumerate(alleles)]
+    text = ("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + names + "\n" +
+            "\n".join(lines) + "\n").encode()
+    third = len(text) // 3
+    blobs = {"plain": text, "gzip": gzip.compress(text), "bgzf": _bgzf(text, 4000),
+             "gzip_members": gzip.compress(text[:third]) + gzip.compress(text[third:2 * third]) + gzip.compress(text[2 * third:])}
+    for name, blob in blobs.items():
+        path = tmp_path / f"{name}.bin"
+        path.write_bytes(blob)
+        for slab in (1 << 30, 100_000):
+            got = np.concatenate([g for _, g in vcf.read_vcf_genotypes(str(path), 777, slab_bytes=slab)])
+            assert np.array_equal(got, alleles), (name, slab)
+        pieces = list(vcf._text_slabs(str(path), 2, 100_000))
+        assert len(pieces) >= 8 and [last for _, last in pieces] == [False] * (len(pieces) - 1) + [True]
+        assert b"".join(p.tobytes() for p, _ in pieces) == text
+    # through a real pipe
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from utmos_b200 import vcf; "
+            "g = np.concatenate([g for _, g in vcf.read_vcf_genotypes('/dev/stdin', 500, slab_bytes=200_000)]); "
+            "sys.stdout.write('%%d %%d' %% (g.shape[0], int(g.astype(np.int64).sum())))" % ROOT)
+    for name in ("plain", "bgzf", "gzip"):
+        feeder = subprocess.Popen(["cat", str(tmp_path / f"{name}.bin")], stdout=subprocess.PIPE)
+        out = subprocess.run([sys.executable, "-c", code], stdin=feeder.stdout, capture_output=True, text=True, timeout=120, check=True)
+        feeder.wait()
+        assert out.stdout.split() == [str(n_lines), str(int(alleles.sum()))], (name, out.stderr)
+    # damaged containers fail loudly
+    (tmp_path / "cut.gz").write_bytes(blobs["gzip"][:-20])
+    with pytest.raises(ValueError):
+        list(vcf.read_vcf_genotypes(str(tmp_path / "cut.gz")))
+    (tmp_path / "cut.bgzf").write_bytes(blobs["bgzf"][:-40])
+    with pytest.raises(ValueError):
+        list(vcf.read_vcf_genotypes(str(tmp_path / "cut.bgzf")))

@@ -38,49 +38,97 @@ def _parse_gt(token):
 SLAB_BYTES = 256 << 20          # uncompressed text handled at a time (a 1kGP chromosome VCF is ~11 GB of text)
 
 
-def _bgzf_batches(raw, slab_bytes):
-    """Split BGZF bytes into runs of whole blocks that inflate to about slab_bytes each; None if not BGZF."""
-    out, pos, start, size = [], 0, 0, 0
-    n = len(raw)
-    while pos < n:
-        if pos + 18 > n or raw[pos:pos + 3] != b"\x1f\x8b\x08" or not raw[pos + 3] & 4:
+def _bgzf_run(buf, slab_bytes):
+    """(end, size): the longest run of whole BGZF blocks buf[:end] that inflates to about slab_bytes (``size`` bytes;
+    end 0: no complete block yet), or None when the bytes are not BGZF blocks."""
+    pos, size, n = 0, 0, len(buf)
+    while pos < n and size < slab_bytes:
+        if pos + 18 > n:
+            break                                          # header incomplete: wait for more bytes
+        if buf[pos:pos + 3] != b"\x1f\x8b\x08" or not buf[pos + 3] & 4:
             return None
-        xlen = raw[pos + 10] | (raw[pos + 11] << 8)
+        xlen = buf[pos + 10] | (buf[pos + 11] << 8)
         q, xend, bsize = pos + 12, pos + 12 + xlen, -1
+        if xend > n:
+            break
         while q + 4 <= xend:
-            slen = raw[q + 2] | (raw[q + 3] << 8)
-            if raw[q:q + 2] == b"BC" and slen == 2:
-                bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1
+            slen = buf[q + 2] | (buf[q + 3] << 8)
+            if buf[q:q + 2] == b"BC" and slen == 2:
+                bsize = (buf[q + 4] | (buf[q + 5] << 8)) + 1
             q += 4 + slen
-        if bsize < 0 or pos + bsize > n:
+        if bsize < 0:
             return None
-        size += int.from_bytes(raw[pos + bsize - 4:pos + bsize], "little")
+        if pos + bsize > n:
+            break
+        size += int.from_bytes(buf[pos + bsize - 4:pos + bsize], "little")
         pos += bsize
-        if size >= slab_bytes:
-            out.append((start, pos))
-            start, size = pos, 0
-    if pos > start:
-        out.append((start, pos))
-    return out
+    return pos, size
+
+
+def _text_pieces(fh, threads, slab_bytes):
+    """Uncompressed text of an open binary stream (a file or a pipe such as /dev/stdin, README.md:80-84 of the
+    reference), about slab_bytes at a time, so memory stays bounded whatever the size of the VCF."""
+    import zlib  # pylint: disable=import-outside-toplevel
+    from utmos_b200 import _native  # pylint: disable=import-outside-toplevel
+    read = max(1 << 16, slab_bytes // 4)
+    buf = fh.read(read)
+    if buf[:2] != b"\x1f\x8b":                             # plain text
+        while buf:
+            yield np.frombuffer(buf, dtype=np.uint8)
+            buf = fh.read(slab_bytes)
+        return
+    run = _bgzf_run(buf, 1)
+    while run is not None and run[0] == 0:                 # first block not complete yet
+        more = fh.read(read)
+        if not more:
+            break
+        buf += more
+        run = _bgzf_run(buf, 1)
+    if run is not None and run[0]:                         # BGZF: runs of whole blocks, inflated in parallel
+        eof = False
+        while buf:
+            run = _bgzf_run(buf, slab_bytes)
+            while run is not None and run[1] < slab_bytes and not eof:
+                more = fh.read(read)
+                eof = not more
+                buf += more
+                run = _bgzf_run(buf, slab_bytes)
+            if run is None:
+                raise ValueError("BGZF stream continues with bytes that are not a BGZF block")
+            if run[0] == 0:
+                raise ValueError("truncated BGZF block at the end of the input")
+            yield _native.gz_inflate(memoryview(buf)[:run[0]], threads)
+            buf = buf[run[0]:]
+    else:                                                  # plain gzip (possibly several members): one sequential stream
+        dec = zlib.decompressobj(wbits=31)
+        out, held = [], 0
+        while buf:
+            data = buf
+            while data:
+                if dec.eof:                                # next member
+                    dec = zlib.decompressobj(wbits=31)
+                out.append(dec.decompress(data, max(1, slab_bytes - held)))
+                held += len(out[-1])
+                data = dec.unused_data if dec.eof else dec.unconsumed_tail
+                if held >= slab_bytes:
+                    yield np.frombuffer(b"".join(out), dtype=np.uint8)
+                    out, held = [], 0
+            buf = fh.read(read)
+        if not dec.eof:
+            raise ValueError("truncated gzip stream")
+        if held:
+            yield np.frombuffer(b"".join(out), dtype=np.uint8)
 
 
 def _text_slabs(path, threads, slab_bytes):
-    """Yield (uint8 text, is_last) pieces of the uncompressed file, in order."""
-    from utmos_b200 import _native  # pylint: disable=import-outside-toplevel
+    """Yield (uint8 text, is_last) pieces of the uncompressed file, in order (one piece of look-ahead)."""
     with open(path, "rb") as fh:
-        raw = fh.read()
-    if raw[:2] != b"\x1f\x8b":
-        yield np.frombuffer(raw, dtype=np.uint8), True
-        return
-    batches = _bgzf_batches(raw, slab_bytes)
-    if batches is None:                                   # plain gzip: one sequential stream
-        yield _native.gz_inflate(raw, threads), True
-        return
-    view = memoryview(raw)
-    for k, (b, e) in enumerate(batches):
-        yield _native.gz_inflate(view[b:e], threads), k == len(batches) - 1
-    if not batches:
-        yield np.zeros(0, dtype=np.uint8), True
+        prev = None
+        for piece in _text_pieces(fh, threads, slab_bytes):
+            if prev is not None:
+                yield prev, False
+            prev = piece
+        yield (prev if prev is not None else np.zeros(0, dtype=np.uint8)), True
 
 
 def read_vcf_genotypes(path, chunk_length=2000, threads=0, slab_bytes=SLAB_BYTES):
