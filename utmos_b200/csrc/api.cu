@@ -143,6 +143,7 @@ struct utmos_ctx {
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
                                           // (measured on the 1kGP shape: not faster than one CTA, so off by default)
+    uint32_t *d_newmask = nullptr;        // rows newly covered by the pick that ended a head launch (cover_decrement_kernel)
     uint32_t *d_live_priv = nullptr;      // private live masks of the cluster flavour when they do not fit in shared memory
     size_t live_priv_bytes = 0;
     unsigned long long tail_budget = 0;   // handed to the head kernels while the tail flavour waits for sparsity
@@ -473,6 +474,7 @@ void free_select_state(utmos_ctx *c)
         c->lists_external = false;
     }
     dev_free(c, c->d_live_priv, c->live_priv_bytes);
+    dev_free(c, c->d_newmask, (size_t)c->colPitchW * 4);
     c->live_priv_bytes = 0;
     dev_free(c, c->d_local0_cnt, S * 4);
     dev_free(c, c->d_local_cnt, S * 4);
@@ -626,6 +628,7 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.tail_rows = c->mg_world > 1 ? std::min(c->tail_rows, 1536u) * (unsigned int)c->mg_world : c->tail_rows;
     p.dbg_time = c->dbg_time;
     p.dsmem_gains = (c->flags & UTMOS_F_DSMEM_GAINS) ? 1 : 0;
+    p.newmask = c->d_newmask;
     p.st = c->d_state;
     p.V = c->V;
     p.colPitchW = c->colPitchW;
@@ -1121,6 +1124,11 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         if (!multi && !(c->flags & UTMOS_F_NO_CLUSTER)) UT_TRY(cluster_plan(p, &CL));
         if (!multi && !(c->flags & UTMOS_F_NO_TAIL)) UT_TRY(tail_plan(p, &tail_ok));
         if (multi) tail_ok = c->mg_list_cap > 0;          // same decision on every rank (utmos_mgpu_export)
+        // heavy picks in count mode: subtract the newly covered rows (cover_decrement_kernel) instead of recomputing
+        // every gain from the sample-major copy (regain_kernel).  Opt-in until it has been through the full GPU suite.
+        static const bool use_decrement = getenv("UTMOS_B200_DECREMENT") && atoi(getenv("UTMOS_B200_DECREMENT")) != 0;
+        if (use_decrement && !multi && !af && c->d_cols && !c->d_newmask && !(c->flags & UTMOS_F_STEP_KERNELS))
+            UT_TRY(dev_alloc(c, (void **)&c->d_newmask, (size_t)c->colPitchW * 4));
         // Head: greedy steps by the cluster (or grid-wide, or multi-GPU) kernel; a pick that covers very many rows
         // ends the launch and the conditional regain kernel recomputes the gains.  While the tail flavour is still
         // waiting for the live part of the matrix to become sparse, launches are kept short so the host can switch
@@ -1214,7 +1222,8 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                         UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                         break;
                     }
-                    UT_TRY(launch_regain(c->stream, q, &c->n_launch));
+                    if (q.newmask) UT_TRY(launch_cover_decrement(c->stream, q, &c->n_launch));
+                    else UT_TRY(launch_regain(c->stream, q, &c->n_launch));
                     UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 }
             }

@@ -89,6 +89,8 @@ struct SelParams {
     int dbg_time;                      // 1: record %globaltimer per pick (profiling; costs latency)
     int dsmem_gains;                   // 1: cluster kernel keeps the gains in distributed shared memory
     unsigned int regain_rows;          // picks that newly cover >= this many rows trigger a gain recompute (0 = never)
+    uint32_t *newmask;                 // [colPitchW] or null: a pick that ends a head launch (st->regain) leaves the rows it
+                                       // newly covered here, for cover_decrement_kernel
 };
 
 // Multi-GPU exchange (variants sharded by rows, gains replicated on every rank).  All pointers are valid on THIS
@@ -251,6 +253,7 @@ int launch_persistent(cudaStream_t stream, const SelParams &p, int grid, int blo
                       ArgPartial *partials, int *n_launch);
 int launch_debug_scores(cudaStream_t stream, const SelParams &p, double *score_out, int *n_launch);
 int launch_regain(cudaStream_t stream, const SelParams &p, int *n_launch);
+int launch_cover_decrement(cudaStream_t stream, const SelParams &p, int *n_launch);
 int launch_sum_gains(cudaStream_t stream, const SelParams &p, int *n_launch);
 int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, unsigned int *list_off,
                        unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,

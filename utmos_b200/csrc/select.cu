@@ -14,6 +14,8 @@
 //           K4  argmax (argmax_step_kernel, or phase A of the persistent kernel)
 //           K5  cover (cover_step_kernel, or phase B of the persistent kernel)
 #include <cooperative_groups.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -295,6 +297,117 @@ __global__ void __launch_bounds__(256) regain_kernel(SelParams p)
     }
 }
 
+// K5 for a heavy pick in count mode ("incremental gain decrement", utmos/select.py:37-41 restricted to the rows the
+// pick newly covered): gain_cnt[s] -= number of those rows that carry s.  The rows are read once from the
+// variant-major matrix (N_t * pitch bytes instead of the whole sample-major copy that regain_kernel streams) and
+// counted by positional popcount: a thread owns one word column (32 samples) and adds 16 rows at a time into
+// bit-sliced counters (plane k holds bit k of the 32 counts) with a carry-save adder tree; at the end the 16 planes
+// are turned into 32 integers by one 32x32 bit transpose in registers, the slices of a CTA are summed in shared
+// memory and every sample gets one RED per CTA.  Runs only when the selection kernel left st->regain set.
+constexpr int kDecBatchWords = 64;       // mask words whose rows are listed at a time (2,048 rows)
+constexpr int kDecMaxWords = 1984;       // mask words per CTA: fewer than 65,536 rows, so 16 planes cannot overflow
+
+__device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+__global__ void __launch_bounds__(256) cover_decrement_kernel(SelParams p, int words_per_cta)
+{
+    if (p.st->regain == 0) return;
+    __shared__ unsigned int s_rows[kDecBatchWords * 32];
+    __shared__ unsigned int s_n;
+    extern __shared__ unsigned int s_dec[];                      // [cols_here * 32] decrements found by this CTA
+    const int tid = threadIdx.x;
+    const int col0 = blockIdx.y * 256;
+    const int cols_here = min(256, p.pitchW - col0);             // word columns of this CTA
+    const int slices = 256 / cols_here;                          // row slices working side by side on those columns
+    const int wc = tid % cols_here, sl = tid / cols_here;
+    const bool active = sl < slices;
+    for (int i = tid; i < cols_here * 32; i += 256) s_dec[i] = 0u;
+    uint32_t pl[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pl[k] = 0u;
+    const long long mw0 = (long long)blockIdx.x * words_per_cta;
+    const long long mw1 = min(mw0 + (long long)words_per_cta, p.colPitchW);
+    for (long long mb = mw0; mb < mw1; mb += kDecBatchWords) {
+        __syncthreads();                                         // the previous list has been consumed
+        if (tid == 0) s_n = 0u;
+        __syncthreads();
+        if (tid < kDecBatchWords && mb + tid < mw1) {
+            uint32_t x = __ldcg(p.newmask + mb + tid);
+            if (x) {
+                unsigned int at = atomicAdd(&s_n, (unsigned int)__popc(x));
+                const unsigned int r0 = (unsigned int)((mb + tid) << 5);
+                while (x) {
+                    s_rows[at++] = r0 + (unsigned int)(__ffs(x) - 1);
+                    x &= x - 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int n = (int)s_n;
+        if (!active) continue;
+        for (int i0 = sl * 16; i0 < n; i0 += slices * 16) {
+            uint32_t x[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                x[u] = i0 + u < n ? __ldg(p.rows + (long long)s_rows[i0 + u] * p.pitchW + col0 + wc) : 0u;
+            uint32_t t2a, t2b, t4a, t4b, t8a, t8b, t16;
+            csa(t2a, pl[0], pl[0], x[0], x[1]);
+            csa(t2b, pl[0], pl[0], x[2], x[3]);
+            csa(t4a, pl[1], pl[1], t2a, t2b);
+            csa(t2a, pl[0], pl[0], x[4], x[5]);
+            csa(t2b, pl[0], pl[0], x[6], x[7]);
+            csa(t4b, pl[1], pl[1], t2a, t2b);
+            csa(t8a, pl[2], pl[2], t4a, t4b);
+            csa(t2a, pl[0], pl[0], x[8], x[9]);
+            csa(t2b, pl[0], pl[0], x[10], x[11]);
+            csa(t4a, pl[1], pl[1], t2a, t2b);
+            csa(t2a, pl[0], pl[0], x[12], x[13]);
+            csa(t2b, pl[0], pl[0], x[14], x[15]);
+            csa(t4b, pl[1], pl[1], t2a, t2b);
+            csa(t8b, pl[2], pl[2], t4a, t4b);
+            csa(t16, pl[3], pl[3], t8a, t8b);
+#pragma unroll
+            for (int k = 4; k < 16; ++k) {                       // add the carry of weight 16 into the upper planes
+                const uint32_t t = pl[k] & t16;
+                pl[k] ^= t16;
+                t16 = t;
+            }
+        }
+    }
+    if (active) {
+        // 16 planes -> 32 counts: word b of the transposed 32x32 bit block has bit k = bit b of plane k
+        uint32_t a[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a[k] = k < 16 ? pl[k] : 0u;
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if ((k & j) == 0) {
+                    const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+                    a[k] ^= t << j;
+                    a[k + j] ^= t;
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 32; ++b)
+            if (a[b]) atomicAdd(&s_dec[wc * 32 + b], a[b]);
+    }
+    __syncthreads();
+    for (int i = tid; i < cols_here * 32; i += 256) {
+        const int s = col0 * 32 + i;
+        const unsigned int d = s_dec[i];
+        if (d && s < p.S) atomicSub(p.gain_cnt + s, d);
+    }
+}
+
 // K3 (variant-major source): one warp per row, one reduction per set bit.
 //   WHAT bit 0: var_count over all rows, bit 1: gain_cnt over live rows, bit 2: AF limbs over live rows
 __global__ void __launch_bounds__(256) row_gain_kernel(SelParams p, unsigned int *var_count, int what)
@@ -427,7 +540,10 @@ __device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long
         }
     }
     if (nw) __stcg(p.live + w, lv ^ nw);
-    if (!retire) return;                              // gains will be recomputed by regain_kernel
+    if (!retire) {                                    // gains will be brought up to date by the next kernel
+        if (p.newmask && w < p.colPitchW) p.newmask[w] = nw;
+        return;
+    }
     unsigned int pending = __ballot_sync(0xffffffffu, nw != 0);
     while (pending) {
         const int src = __ffs(pending) - 1;
@@ -817,7 +933,10 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
                 }
             }
             if (nw) s_live[wl] = lv ^ nw;
-            if (regain) continue;                         // warp-uniform
+            if (regain) {                                 // warp-uniform
+                if (p.newmask && w < p.colPitchW) p.newmask[w] = nw;
+                continue;
+            }
             if (nw) {
                 uint32_t m = nw;                          // warm L2 with the rows this lane found
                 while (m) {
@@ -1382,6 +1501,22 @@ int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launc
     lc.numAttrs = 1;
     UT_CUDA(cudaLaunchKernelEx(&lc, select_cluster_kernel, p, cfg));
     *n_launch += 1;
+    return UTMOS_OK;
+}
+
+int launch_cover_decrement(cudaStream_t stream, const SelParams &p, int *n_launch)
+{
+    if (p.S <= 0 || p.V <= 0 || !p.newmask || p.af) { set_error("cover_decrement: count mode with a newmask buffer only"); return UTMOS_E_ARG; }
+    const int col_passes = (p.pitchW + 255) / 256;
+    long long gx = std::max(1, 2 * 148 / col_passes);                       // about two CTAs per SM in all
+    long long wpc = (p.colPitchW + gx - 1) / gx;
+    wpc = std::min<long long>((wpc + kDecBatchWords - 1) / kDecBatchWords * kDecBatchWords, kDecMaxWords);
+    gx = (p.colPitchW + wpc - 1) / wpc;
+    if (gx > 0x7fffffffll) { set_error("cover_decrement: matrix too large"); return UTMOS_E_ARG; }
+    const size_t smem = (size_t)std::min(256, p.pitchW) * 32 * sizeof(unsigned int);
+    cover_decrement_kernel<<<dim3((unsigned)gx, (unsigned)col_passes), 256, smem, stream>>>(p, (int)wpc);
+    *n_launch += 1;
+    UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
 }
 
