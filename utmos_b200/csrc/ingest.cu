@@ -241,7 +241,7 @@ __device__ __forceinline__ uint32_t smem_bytes_any(const uint32_t *s32, unsigned
 // FLAVOUR 0: one warp ORs the words of a row (first version).  FLAVOUR 1: the load loop records which 16-byte
 // pieces are nonzero in a bitmap, one thread per row then tests the bitmap bits of the pieces that lie wholly
 // inside its row and the few bytes it shares with its neighbours; the store loop splits its unit index without
-// an integer division; the look-back reads FLAVOUR tiles per lane and round trip (window = 32 * FLAVOUR tiles).
+// an integer division; the look-back can read kLook tiles per lane and round trip (window = 32 * kLook tiles).
 template <int FLAVOUR>
 __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *__restrict__ raw, long long n_rows,
                                                                  long long pitch_in, const double *__restrict__ af_in,
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
             } else {
                 // window of 32 * kLook tiles per round trip: lane l reads the tiles at distance l*kLook .. l*kLook+kLook-1
                 // (measured: wider windows poll more and are slower -- 0.287 ms at 128 tiles against 0.261 ms at 32)
-                constexpr int kLook = FLAVOUR > 0 ? FLAVOUR : 1;
+                constexpr int kLook = 1;
                 while (true) {
                     unsigned long long v[kLook];
                     unsigned int pm, bad;
@@ -603,16 +603,12 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
             const int smem_max = (int)(kFastSmemRaw + 64);
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            const char *env = getenv("UTMOS_B200_INGEST");       // A/B runs: 0 = first version of the kernel, 2 / 4 = wider look-back
-            if (env) flavour = atoi(env);
-            if (flavour != 0 && flavour != 2 && flavour != 4) flavour = 1;
+            const char *env = getenv("UTMOS_B200_INGEST");       // A/B runs: 0 = first version of the kernel
+            if (env) flavour = atoi(env) != 0;
             configured = true;
         }
         UT_CUDA(cudaMemsetAsync(sc.tile_state, 0, sizeof(unsigned long long) * (size_t)(n_tiles + 1), stream));
-        auto kernel = flavour == 0 ? ingest_packed_kernel<0> : flavour == 2 ? ingest_packed_kernel<2>
-                    : flavour == 4 ? ingest_packed_kernel<4> : ingest_packed_kernel<1>;
+        auto kernel = flavour ? ingest_packed_kernel<1> : ingest_packed_kernel<0>;
         kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>((const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles,
                                                               sc.tile_state, d_nrows, d_total, rows_out, af_out);
         bump_rows_kernel<<<1, 1, 0, stream>>>(d_nrows, d_total);

@@ -48,10 +48,9 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
     return x;
 }
 
-// KEEP_L2: the 64-byte pieces are read with plain read-only loads.  A streaming (L1::no_allocate) load is looked up
+// The 64-byte pieces are read with plain read-only loads.  A streaming (L1::no_allocate) load is looked up
 // evict-first in L2, where the whole 128-byte line is fetched: the half the neighbouring column tile needs was gone
 // again before that CTA asked for it, and DRAM read every line twice (ncu r1: 707 MB for a 353 MB matrix).
-template <bool KEEP_L2>
 __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__restrict__ rows, long long V,
                                                              int pitchW, int S32, uint32_t *__restrict__ cols,
                                                              long long colPitchW, int col_tiles)
@@ -74,7 +73,7 @@ __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__r
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (r < V && w < pitchW) {
             const uint4 *src = reinterpret_cast<const uint4 *>(rows + r * pitchW + w);
-            v = KEEP_L2 ? __ldg(src) : ld_stream_u128(src);
+            v = __ldg(src);
         }
         uint32_t *d = s_in + row * kTInPitch + q * 4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
@@ -95,6 +94,23 @@ __global__ void __launch_bounds__(256) transpose_bits_kernel(const uint32_t *__r
         uint4 *dst = reinterpret_cast<uint4 *>(cols + (long long)s * colPitchW + row_tile * (kTRows / 32));
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// 32x32 bit block held by ONE thread, a[i] bit j -> a[j] bit i (LSB-first on both axes): 5 stages of 16 masked swaps
+__device__ __forceinline__ void transpose32_regs(uint32_t (&a)[32])
+{
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if ((k & j) == 0) {
+                const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+                a[k] ^= t << j;
+                a[k + j] ^= t;
+            }
+        }
     }
 }
 
@@ -136,19 +152,7 @@ __global__ void __launch_bounds__(256, 5) transpose_bits_reg_kernel(const uint32
     const uint32_t *src = t_smem + (g * 32) * kRPitch + g * 4 + c;
 #pragma unroll
     for (int i = 0; i < 32; ++i) a[i] = src[i * kRPitch];
-    // a[i] bit j  ->  a[j] bit i  (LSB-first on both axes)
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            if ((k & j) == 0) {
-                const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
-                a[k] ^= t << j;
-                a[k + j] ^= t;
-            }
-        }
-    }
+    transpose32_regs(a);
     uint32_t *dst = cols + (long long)(w0 + c) * 32 * colPitchW + row_tile * (kRRows / 32) + g;
 #pragma unroll
     for (int j = 0; j < 32; ++j) dst[(long long)j * colPitchW] = a[j];
@@ -384,18 +388,7 @@ __global__ void __launch_bounds__(256) cover_decrement_kernel(SelParams p, int w
         uint32_t a[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) a[k] = k < 16 ? pl[k] : 0u;
-#pragma unroll
-        for (int j = 16; j > 0; j >>= 1) {
-            const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                if ((k & j) == 0) {
-                    const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
-                    a[k] ^= t << j;
-                    a[k + j] ^= t;
-                }
-            }
-        }
+        transpose32_regs(a);
 #pragma unroll
         for (int b = 0; b < 32; ++b)
             if (a[b]) atomicAdd(&s_dec[wc * 32 + b], a[b]);
@@ -1318,12 +1311,10 @@ int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int
     static bool configured = false;
     static int flavour = 2;
     if (!configured) {
-        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
-        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
+        UT_CUDA(cudaFuncSetAttribute(transpose_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeSmem));
         UT_CUDA(cudaFuncSetAttribute(transpose_bits_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTransposeRegSmem));
-        // A/B runs: 0 = shuffle flavour with streaming loads (first version), 1 = shuffle flavour, 2 = register flavour
-        const char *env = getenv("UTMOS_B200_TRANSPOSE");
-        if (env) flavour = atoi(env);
+        const char *env = getenv("UTMOS_B200_TRANSPOSE");          // A/B runs: 1 = shuffle flavour, default = register flavour
+        if (env) flavour = atoi(env) == 1 ? 1 : 2;
         configured = true;
     }
     if (flavour == 2) {
@@ -1332,11 +1323,8 @@ int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int
         transpose_bits_reg_kernel<<<(unsigned)(row_tiles * reg_col_tiles), 256, kTransposeRegSmem, stream>>>(
             rows, V, pitchW, S32 / 32, cols, colPitchW, reg_col_tiles);
     } else {
-        const unsigned grid = (unsigned)(row_tiles * col_tiles);
-        if (flavour == 1)
-            transpose_bits_kernel<true><<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW, col_tiles);
-        else
-            transpose_bits_kernel<false><<<grid, 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols, colPitchW, col_tiles);
+        transpose_bits_kernel<<<(unsigned)(row_tiles * col_tiles), 256, kTransposeSmem, stream>>>(rows, V, pitchW, S32, cols,
+                                                                                                 colPitchW, col_tiles);
     }
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
