@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--step-times", action="store_true", help="record per-pick timestamps (profiling; slows the loop)")
     ap.add_argument("--tail-rows", type=int, default=-1, help="override the tail hand-over threshold")
+    ap.add_argument("--regain-rows", type=int, default=-1, help="override the heavy-pick threshold (UTMOS_OPT_REGAIN_ROWS)")
     ap.add_argument("--single-rows", type=int, default=-1, help="override the cluster-tail -> single-CTA-tail threshold")
     args = ap.parse_args()
 
@@ -231,6 +232,8 @@ def main():
             dm.set_option(3, args.tail_rows)
         if args.single_rows >= 0:
             dm.set_option(5, args.single_rows)
+        if args.regain_rows >= 0:
+            dm.set_option(1, args.regain_rows)
         sm.begin(mask)
         t.append(time.perf_counter())
         idx, new, score, stop = sm.steps(n_samples)

@@ -1,5 +1,21 @@
-# opt-in cover_decrement kernel: parity subset + bench line with it switched on
-UTMOS_B200_DECREMENT=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "regain_threshold or synthetic_reduced or full_orderings" > gpurun_out/s44_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/s44_pytest.log
-UTMOS_B200_DECREMENT=1 python bench.py --no-cpu > gpurun_out/bench_s44_dec.json 2> gpurun_out/bench_s44_dec.err; echo "bench rc=$?"
-python -c "
-import json;d=json.loads(open('gpurun_out/bench_s44_dec.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['phases_ms'],d['gpu_launches'])"
+#!/bin/bash
+# First GPU call of the next round (about 6 GPU-minutes): the opt-in heavy-pick kernel through the whole suite, then
+# the sweep that decides its defaults.  Everything lands in gpurun_out/.
+#   1. full parity suite with cover_decrement_kernel forced on (count mode; AF flavours keep regain_kernel)
+#   2. bench lines: default, decrement, decrement with lower thresholds (the mid picks, 1,800-4,500 rows each, then take
+#      the kernel too) and more queued head launches per host check
+UTMOS_B200_DECREMENT=1 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest_decrement.log 2>&1; echo "pytest(decrement) rc=$?"; tail -2 gpurun_out/next_pytest_decrement.log
+python bench.py --no-cpu > gpurun_out/next_bench_default.json 2> gpurun_out/next_bench_default.err
+for cfg in "4096 4" "2048 8" "1024 8" "512 16" "256 16"; do
+  set -- $cfg
+  UTMOS_B200_DECREMENT=1 UTMOS_B200_HEAD_REPS=$2 python bench.py --no-cpu --regain-rows $1 > gpurun_out/next_bench_dec_$1_$2.json 2> gpurun_out/next_bench_dec_$1_$2.err
+done
+python - <<'PY'
+import glob, json
+for f in sorted(glob.glob("gpurun_out/next_bench_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, round(d["ms_per_step"], 3), round(d["phases_ms"]["select_ms"], 3), d["gpu_launches"])
+    except Exception as e:  # noqa
+        print(f, "failed", e)
+PY

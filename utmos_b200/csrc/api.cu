@@ -1207,7 +1207,8 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             } else {
                 // a few launches are queued between host checks; once the live part is sparse enough the queued
                 // head kernels return immediately (they test st->live_bits at launch)
-                for (int rep = 0; rep < 4; ++rep) {
+                static const int head_reps = getenv("UTMOS_B200_HEAD_REPS") ? std::max(1, std::min(64, atoi(getenv("UTMOS_B200_HEAD_REPS")))) : 4;
+                for (int rep = 0; rep < head_reps; ++rep) {
                     if (CL > 0) {
                         UT_TRY(launch_cluster(c->stream, q, CL, &c->n_launch));
                         c->flavour_used = 2;
