@@ -5,6 +5,12 @@
 #   2. bench lines: default, decrement, decrement with lower thresholds (the mid picks, 1,800-4,500 rows each, then take
 #      the kernel too) and more queued head launches per host check
 UTMOS_B200_DECREMENT=1 python -m pytest tests -m gpu -x -q > gpurun_out/next_pytest_decrement.log 2>&1; echo "pytest(decrement) rc=$?"; tail -2 gpurun_out/next_pytest_decrement.log
+#   3. chained picks in the tail (select_tail_chain_kernel, exact top-K per argmax round): parity subset + bench lines
+for k in 2 4; do
+  UTMOS_B200_TAIL_CHAIN=$k python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_orderings or random_cases or synthetic_reduced or step_batches or tail_flavours or cli_answer" > gpurun_out/next_pytest_chain$k.log 2>&1; echo "pytest(chain $k) rc=$?"; tail -2 gpurun_out/next_pytest_chain$k.log
+  UTMOS_B200_TAIL_CHAIN=$k python bench.py --no-cpu > gpurun_out/next_bench_chain$k.json 2> gpurun_out/next_bench_chain$k.err
+  UTMOS_B200_TAIL_CHAIN=$k UTMOS_B200_DECREMENT=1 python bench.py --no-cpu > gpurun_out/next_bench_chain${k}_dec.json 2> gpurun_out/next_bench_chain${k}_dec.err
+done
 python bench.py --no-cpu > gpurun_out/next_bench_default.json 2> gpurun_out/next_bench_default.err
 for cfg in "4096 4" "2048 8" "1024 8" "512 16" "256 16"; do
   set -- $cfg
