@@ -11,6 +11,10 @@ for k in 2 4; do
   UTMOS_B200_TAIL_CHAIN=$k python bench.py --no-cpu > gpurun_out/next_bench_chain$k.json 2> gpurun_out/next_bench_chain$k.err
   UTMOS_B200_TAIL_CHAIN=$k UTMOS_B200_DECREMENT=1 python bench.py --no-cpu > gpurun_out/next_bench_chain${k}_dec.json 2> gpurun_out/next_bench_chain${k}_dec.err
 done
+#   4. edge lists without single-carrier rows
+UTMOS_B200_SKIP_SINGLE=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_orderings or random_cases or synthetic_reduced or step_batches or tail_flavours or cli_answer or float32_af or cohorts_whose" > gpurun_out/next_pytest_skipsingle.log 2>&1; echo "pytest(skip single) rc=$?"; tail -2 gpurun_out/next_pytest_skipsingle.log
+UTMOS_B200_SKIP_SINGLE=1 python bench.py --no-cpu > gpurun_out/next_bench_skipsingle.json 2> gpurun_out/next_bench_skipsingle.err
+UTMOS_B200_SKIP_SINGLE=1 UTMOS_B200_TAIL_CHAIN=4 UTMOS_B200_DECREMENT=1 python bench.py --no-cpu > gpurun_out/next_bench_all_optins.json 2> gpurun_out/next_bench_all_optins.err
 python bench.py --no-cpu > gpurun_out/next_bench_default.json 2> gpurun_out/next_bench_default.err
 for cfg in "4096 4" "2048 8" "1024 8" "512 16" "256 16"; do
   set -- $cfg

@@ -126,6 +126,9 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
             if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
+        // opt-in: a row that only one sample carries changes nobody else's gain when it is covered and is already
+        // counted in that sample's own gain (its new_count), so the tail never needs to see it
+        if (d.skip_single && total == 1) continue;
         uint4 tailq = make_uint4(0u, 0u, 0u, 0u);
         if (ESTRIDE == 2) {
             const unsigned long long ql = p.q_lo[r], qh = p.q_hi[r];
@@ -199,7 +202,8 @@ __global__ void __launch_bounds__(256) filter_edges_kernel(const uint32_t *__res
                                                            const unsigned int *__restrict__ old_off,
                                                            const unsigned int *__restrict__ old_len,
                                                            uint4 *__restrict__ new_lists,
-                                                           const unsigned int *__restrict__ new_off)
+                                                           const unsigned int *__restrict__ new_off,
+                                                           unsigned int *new_len_out)
 {
     __shared__ unsigned int s_cursor;
     const int s = blockIdx.x;
@@ -231,6 +235,17 @@ __global__ void __launch_bounds__(256) filter_edges_kernel(const uint32_t *__res
             }
         }
     }
+    if (new_len_out) {                  // lists without single-carrier rows: fewer entries than the gain says
+        __syncthreads();
+        if (threadIdx.x == 0) new_len_out[s] = s_cursor;
+    }
+}
+
+// lists without single-carrier rows: the length of a list is what the build wrote, not the gain
+__global__ void list_len_from_cursor_kernel(const unsigned int *cursor, unsigned int *list_len, int S)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) list_len[s] = cursor[s];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1042,6 +1057,13 @@ int launch_sum_gains(cudaStream_t stream, const SelParams &p, int *n_launch)
     return UTMOS_OK;
 }
 
+// opt-in (UTMOS_B200_SKIP_SINGLE=1, single GPU): edge lists without the rows that only one sample carries
+static bool skip_single_rows()
+{
+    static const bool on = getenv("UTMOS_B200_SKIP_SINGLE") && atoi(getenv("UTMOS_B200_SKIP_SINGLE")) != 0;
+    return on;
+}
+
 int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, unsigned int *list_off,
                        unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,
                        int *n_launch)
@@ -1054,7 +1076,14 @@ int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, un
     d.lists[0] = lists;
     d.pool[0] = pool;
     d.slot_base = list_off;
-    return launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch);
+    d.skip_single = skip_single_rows() ? 1 : 0;
+    UT_TRY(launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch));
+    if (d.skip_single) {
+        list_len_from_cursor_kernel<<<(p.S + 255) / 256, 256, 0, stream>>>(cursor, list_len, p.S);
+        *n_launch += 1;
+        UT_CUDA(cudaGetLastError());
+    }
+    return UTMOS_OK;
 }
 
 // cursor[S] must be zero; entries go to d.lists[q][slot_base[s] + k] for every q < d.world
@@ -1080,8 +1109,9 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
                         int *n_launch)
 {
     list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.S, new_off, new_len, nullptr);
-    if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off);
-    else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off);
+    unsigned int *kept = skip_single_rows() ? new_len : nullptr;
+    if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, kept);
+    else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, kept);
     *n_launch += 2;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
