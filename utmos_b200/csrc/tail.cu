@@ -866,8 +866,10 @@ __global__ void __launch_bounds__(1024, 1) select_tail_chain_kernel(SelParams p,
                 }
             } else {
                 if (best_cnt == 0u || best_idx == 0x7fffffff || step >= limit) break;
-                __syncthreads();                                  // the previous walk and tid 0's resets are complete
-                if (s_cnt[best_idx] != best_cnt) break;           // its gain moved since the argmax: run the argmax again
+                // Its gain moved since the argmax -> run the argmax again.  The previous walk ended with a barrier, so the
+                // gain is final when it is read here; the barrier inside the vote keeps every thread's read ahead of the
+                // next walk (which may lower this very gain through a pooled carrier list) and publishes tid 0's resets.
+                if (!__syncthreads_and(s_cnt[best_idx] == best_cnt)) break;
             }
             const unsigned int best_off = s_loff[best_idx], best_len = s_llen[best_idx];
             if (tid == 0) {
