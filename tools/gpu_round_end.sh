@@ -15,6 +15,14 @@ done
 UTMOS_B200_SKIP_SINGLE=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "full_orderings or random_cases or synthetic_reduced or step_batches or tail_flavours or cli_answer or float32_af or cohorts_whose" > gpurun_out/next_pytest_skipsingle.log 2>&1; echo "pytest(skip single) rc=$?"; tail -2 gpurun_out/next_pytest_skipsingle.log
 UTMOS_B200_SKIP_SINGLE=1 python bench.py --no-cpu > gpurun_out/next_bench_skipsingle.json 2> gpurun_out/next_bench_skipsingle.err
 UTMOS_B200_SKIP_SINGLE=1 UTMOS_B200_TAIL_CHAIN=4 UTMOS_B200_DECREMENT=1 python bench.py --no-cpu > gpurun_out/next_bench_all_optins.json 2> gpurun_out/next_bench_all_optins.err
+#   5. K2 ingest with batched loads (flavour 2): parity subset + streaming micro-bench A/B
+UTMOS_B200_INGEST=2 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ingest_many or ragged or empty_and or synthetic_reduced or cli_answer" > gpurun_out/next_pytest_ingest2.log 2>&1; echo "pytest(ingest 2) rc=$?"; tail -2 gpurun_out/next_pytest_ingest2.log
+: > gpurun_out/next_streaming.jsonl
+python tools/bench_streaming.py --tag ingest1 >> gpurun_out/next_streaming.jsonl
+UTMOS_B200_INGEST=2 python tools/bench_streaming.py --tag ingest2 >> gpurun_out/next_streaming.jsonl
+UTMOS_B200_INGEST=2 UTMOS_B200_INGEST_TILE=55296 python tools/bench_streaming.py --tag ingest2_tile54k >> gpurun_out/next_streaming.jsonl
+UTMOS_B200_INGEST=2 python tools/bench_streaming.py --tag ingest2_s100k --samples 100000 --vars 400000 --reps 3 >> gpurun_out/next_streaming.jsonl
+cut -c1-260 gpurun_out/next_streaming.jsonl
 python bench.py --no-cpu > gpurun_out/next_bench_default.json 2> gpurun_out/next_bench_default.err
 for cfg in "4096 4" "2048 8" "1024 8" "512 16" "256 16"; do
   set -- $cfg

@@ -303,23 +303,58 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
         const uint4 *g16 = reinterpret_cast<const uint4 *>(raw + a0);
         const int n_in = (int)min((long long)n16, (total_bytes - a0) >> 4);     // pieces that lie wholly inside the input
         const int n_iter = (n16 + 2 + kThreads - 1) / kThreads * kThreads;      // whole warps: the ballot needs every lane
-        for (int i = tid; i < n_iter; i += kThreads) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (i < n_in) {
-                v = ld_stream_u128(g16 + i);
-            } else if (i < n16) {                                               // the last piece of the input, byte by byte
-                const long long off = a0 + 16ll * i;
-                unsigned long long lo = 0ull, hi = 0ull;
-                for (int b = 0; b < 16 && off + b < total_bytes; ++b) {
-                    const unsigned long long x = __ldg(raw + off + b);
-                    if (b < 8) lo |= x << (8 * b);
-                    else hi |= x << (8 * (b - 8));
+        if (FLAVOUR == 2) {
+            // opt-in: kLoadBatch loads of a thread are issued before the first of them is used.  In FLAVOUR 1 the vote
+            // on the loaded piece sits in the load loop, so every trip waits for its own load (SASS: one LDG.128 and
+            // one VOTE per trip) -- seven dependent DRAM round trips per tile.
+            constexpr int kLoadBatch = 4;
+            for (int i0 = tid; i0 < n_iter; i0 += kLoadBatch * kThreads) {
+                uint4 v[kLoadBatch];
+#pragma unroll
+                for (int k = 0; k < kLoadBatch; ++k) {
+                    const int i = i0 + k * kThreads;
+                    v[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < n_in) v[k] = ld_stream_u128(g16 + i);
                 }
-                v = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+#pragma unroll
+                for (int k = 0; k < kLoadBatch; ++k) {
+                    const int i = i0 + k * kThreads;
+                    if (i >= n_iter) break;                                     // the same for every thread of the CTA
+                    uint4 x = v[k];
+                    if (i >= n_in && i < n16) {                                 // the last piece of the input, byte by byte
+                        const long long off = a0 + 16ll * i;
+                        unsigned long long lo = 0ull, hi = 0ull;
+                        for (int b = 0; b < 16 && off + b < total_bytes; ++b) {
+                            const unsigned long long y = __ldg(raw + off + b);
+                            if (b < 8) lo |= y << (8 * b);
+                            else hi |= y << (8 * (b - 8));
+                        }
+                        x = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+                    }
+                    if (i < n16 + 2) s16[i] = x;
+                    const uint32_t nz = __ballot_sync(0xffffffffu, (x.x | x.y | x.z | x.w) != 0u);
+                    if (lane == 0 && i < n16 + 2) s_nz[i >> 5] = nz;
+                }
             }
-            if (i < n16 + 2) s16[i] = v;
-            const uint32_t nz = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u);
-            if (lane == 0 && i < n16 + 2) s_nz[i >> 5] = nz;
+        } else {
+            for (int i = tid; i < n_iter; i += kThreads) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (i < n_in) {
+                    v = ld_stream_u128(g16 + i);
+                } else if (i < n16) {                                               // the last piece of the input, byte by byte
+                    const long long off = a0 + 16ll * i;
+                    unsigned long long lo = 0ull, hi = 0ull;
+                    for (int b = 0; b < 16 && off + b < total_bytes; ++b) {
+                        const unsigned long long x = __ldg(raw + off + b);
+                        if (b < 8) lo |= x << (8 * b);
+                        else hi |= x << (8 * (b - 8));
+                    }
+                    v = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+                }
+                if (i < n16 + 2) s16[i] = v;
+                const uint32_t nz = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u);
+                if (lane == 0 && i < n16 + 2) s_nz[i >> 5] = nz;
+            }
         }
         __syncthreads();
         if (tid < nr) {
@@ -603,12 +638,13 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
             const int smem_max = (int)(kFastSmemRaw + 64);
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-            const char *env = getenv("UTMOS_B200_INGEST");       // A/B runs: 0 = first version of the kernel
-            if (env) flavour = atoi(env) != 0;
+            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            const char *env = getenv("UTMOS_B200_INGEST");       // A/B runs: 0 = first version, 2 = batched loads (opt-in)
+            if (env) flavour = atoi(env) == 0 ? 0 : atoi(env) == 2 ? 2 : 1;
             configured = true;
         }
         UT_CUDA(cudaMemsetAsync(sc.tile_state, 0, sizeof(unsigned long long) * (size_t)(n_tiles + 1), stream));
-        auto kernel = flavour ? ingest_packed_kernel<1> : ingest_packed_kernel<0>;
+        auto kernel = flavour == 0 ? ingest_packed_kernel<0> : flavour == 2 ? ingest_packed_kernel<2> : ingest_packed_kernel<1>;
         kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>((const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles,
                                                               sc.tile_state, d_nrows, d_total, rows_out, af_out);
         bump_rows_kernel<<<1, 1, 0, stream>>>(d_nrows, d_total);
