@@ -121,7 +121,6 @@ struct EdgeDst {
     const unsigned int *slot_base;     // [S] first entry slot of sample s for THIS rank's rows
     const unsigned int *pool_base;     // device scalar: first pool slot of this rank (null = 0)
     long long row_base;                // added to local row ids (merged live mask numbering)
-    int skip_single;                   // 1: rows with exactly one carrier get no entry (nobody else's gain depends on them)
 };
 
 // Multi-GPU hand-over to the replicated tail: all-gather of the per-rank live counts and completion flags.

@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(const unsigned int *
 // in the list of each carrier.  ESTRIDE = 1 (count) or 2 (AF flavours: second uint4 = fixed-point AF limbs).
 // EdgeDst says where the entries go: single GPU = this context's buffers; multi-GPU = the SAME slots of every
 // rank's merged buffers (peer pointers, NVLink stores), so all ranks end up with byte-identical lists.
-template <int ESTRIDE, bool WIDE>
+// SKIP_SINGLE (opt-in): rows that only one sample carries get no entry.
+template <int ESTRIDE, bool WIDE, bool SKIP_SINGLE = false>
 __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d, unsigned int *cursor,
                                                           unsigned int *pool_cursor)
 {
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         // opt-in: a row that only one sample carries changes nobody else's gain when it is covered and is already
         // counted in that sample's own gain (its new_count), so the tail never needs to see it
-        if (d.skip_single && total == 1) continue;
+        if (SKIP_SINGLE && total == 1) continue;
         uint4 tailq = make_uint4(0u, 0u, 0u, 0u);
         if (ESTRIDE == 2) {
             const unsigned long long ql = p.q_lo[r], qh = p.q_hi[r];
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
 }
 
 // Re-compaction: one CTA per sample copies the entries whose row is still live (streaming filter).
-template <int ESTRIDE>
+template <int ESTRIDE, bool REPORT_LEN = false>
 __global__ void __launch_bounds__(256) filter_edges_kernel(const uint32_t *__restrict__ live,
                                                            const uint4 *__restrict__ old_lists,
                                                            const unsigned int *__restrict__ old_off,
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256) filter_edges_kernel(const uint32_t *__res
             }
         }
     }
-    if (new_len_out) {                  // lists without single-carrier rows: fewer entries than the gain says
+    if (REPORT_LEN) {                   // lists without single-carrier rows: fewer entries than the gain says
         __syncthreads();
         if (threadIdx.x == 0) new_len_out[s] = s_cursor;
     }
@@ -1078,13 +1079,14 @@ int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, un
     d.lists[0] = lists;
     d.pool[0] = pool;
     d.slot_base = list_off;
-    d.skip_single = skip_single_rows() ? 1 : 0;
-    UT_TRY(launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch));
-    if (d.skip_single) {
-        list_len_from_cursor_kernel<<<(p.S + 255) / 256, 256, 0, stream>>>(cursor, list_len, p.S);
-        *n_launch += 1;
-        UT_CUDA(cudaGetLastError());
-    }
+    if (!skip_single_rows() || p.S > 65535) return launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch);
+    UT_CUDA(cudaMemsetAsync(pool_cursor, 0, 4, stream));
+    long long blocks = std::max(1ll, std::min((p.V + 7) / 8, 148ll * 16));
+    if (p.af) build_edges_kernel<2, false, true><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    else build_edges_kernel<1, false, true><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
+    list_len_from_cursor_kernel<<<(p.S + 255) / 256, 256, 0, stream>>>(cursor, list_len, p.S);
+    *n_launch += 2;
+    UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
 }
 
@@ -1111,9 +1113,11 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
                         int *n_launch)
 {
     list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.S, new_off, new_len, nullptr);
-    unsigned int *kept = skip_single_rows() ? new_len : nullptr;
-    if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, kept);
-    else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, kept);
+    if (skip_single_rows() && p.S <= 65535) {
+        if (p.af) filter_edges_kernel<2, true><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, new_len);
+        else filter_edges_kernel<1, true><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, new_len);
+    } else if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, nullptr);
+    else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, nullptr);
     *n_launch += 2;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
