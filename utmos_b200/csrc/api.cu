@@ -628,7 +628,6 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.tail_rows = c->mg_world > 1 ? std::min(c->tail_rows, 1536u) * (unsigned int)c->mg_world : c->tail_rows;
     p.dbg_time = c->dbg_time;
     p.dsmem_gains = (c->flags & UTMOS_F_DSMEM_GAINS) ? 1 : 0;
-    p.newmask = c->d_newmask;
     p.st = c->d_state;
     p.V = c->V;
     p.colPitchW = c->colPitchW;
@@ -1127,7 +1126,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         // heavy picks in count mode: subtract the newly covered rows (cover_decrement_kernel) instead of recomputing
         // every gain from the sample-major copy (regain_kernel).  Opt-in until it has been through the full GPU suite.
         static const bool use_decrement = getenv("UTMOS_B200_DECREMENT") && atoi(getenv("UTMOS_B200_DECREMENT")) != 0;
-        if (use_decrement && !multi && !af && c->d_cols && !c->d_newmask && !(c->flags & UTMOS_F_STEP_KERNELS))
+        if (use_decrement && !multi && !af && CL > 0 && c->d_cols && !c->d_newmask && !(c->flags & UTMOS_F_STEP_KERNELS))
             UT_TRY(dev_alloc(c, (void **)&c->d_newmask, (size_t)c->colPitchW * 4));
         // Head: greedy steps by the cluster (or grid-wide, or multi-GPU) kernel; a pick that covers very many rows
         // ends the launch and the conditional regain kernel recomputes the gains.  While the tail flavour is still
@@ -1210,7 +1209,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 static const int head_reps = getenv("UTMOS_B200_HEAD_REPS") ? std::max(1, std::min(64, atoi(getenv("UTMOS_B200_HEAD_REPS")))) : 4;
                 for (int rep = 0; rep < head_reps; ++rep) {
                     if (CL > 0) {
-                        UT_TRY(launch_cluster(c->stream, q, CL, &c->n_launch));
+                        UT_TRY(launch_cluster(c->stream, q, CL, &c->n_launch, c->d_newmask));
                         c->flavour_used = 2;
                         c->cluster = CL;
                     } else {
@@ -1223,7 +1222,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                         UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                         break;
                     }
-                    if (q.newmask) UT_TRY(launch_cover_decrement(c->stream, q, &c->n_launch));
+                    if (CL > 0 && c->d_newmask) UT_TRY(launch_cover_decrement(c->stream, q, c->d_newmask, &c->n_launch));
                     else UT_TRY(launch_regain(c->stream, q, &c->n_launch));
                     UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 }

@@ -89,8 +89,6 @@ struct SelParams {
     int dbg_time;                      // 1: record %globaltimer per pick (profiling; costs latency)
     int dsmem_gains;                   // 1: cluster kernel keeps the gains in distributed shared memory
     unsigned int regain_rows;          // picks that newly cover >= this many rows trigger a gain recompute (0 = never)
-    uint32_t *newmask;                 // [colPitchW] or null: a pick that ends a head launch (st->regain) leaves the rows it
-                                       // newly covered here, for cover_decrement_kernel
 };
 
 // Multi-GPU exchange (variants sharded by rows, gains replicated on every rank).  All pointers are valid on THIS
@@ -253,7 +251,7 @@ int launch_persistent(cudaStream_t stream, const SelParams &p, int grid, int blo
                       ArgPartial *partials, int *n_launch);
 int launch_debug_scores(cudaStream_t stream, const SelParams &p, double *score_out, int *n_launch);
 int launch_regain(cudaStream_t stream, const SelParams &p, int *n_launch);
-int launch_cover_decrement(cudaStream_t stream, const SelParams &p, int *n_launch);
+int launch_cover_decrement(cudaStream_t stream, const SelParams &p, const uint32_t *newmask, int *n_launch);
 int launch_sum_gains(cudaStream_t stream, const SelParams &p, int *n_launch);
 int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, unsigned int *list_off,
                        unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,
@@ -282,7 +280,7 @@ int launch_mgpu(cudaStream_t stream, const SelParams &p, const MgpuParams &m, in
                 unsigned int *bar_counter, ArgPartial *partials, int *n_launch);
 int mgpu_grid(int device, int *grid_out, int *block_out);
 int cluster_plan(const SelParams &p, int *cluster_out);
-int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch);
+int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch, uint32_t *newmask = nullptr);
 
 // convert.cu
 int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S, int ploidy, uint8_t *packed,

@@ -318,7 +318,7 @@ __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32
     l = u ^ c;
 }
 
-__global__ void __launch_bounds__(256) cover_decrement_kernel(SelParams p, int words_per_cta)
+__global__ void __launch_bounds__(256) cover_decrement_kernel(SelParams p, const uint32_t *__restrict__ newmask, int words_per_cta)
 {
     if (p.st->regain == 0) return;
     __shared__ unsigned int s_rows[kDecBatchWords * 32];
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) cover_decrement_kernel(SelParams p, int w
         if (tid == 0) s_n = 0u;
         __syncthreads();
         if (tid < kDecBatchWords && mb + tid < mw1) {
-            uint32_t x = __ldcg(p.newmask + mb + tid);
+            uint32_t x = __ldcg(newmask + mb + tid);
             if (x) {
                 unsigned int at = atomicAdd(&s_n, (unsigned int)__popc(x));
                 const unsigned int r0 = (unsigned int)((mb + tid) << 5);
@@ -533,10 +533,7 @@ __device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long
         }
     }
     if (nw) __stcg(p.live + w, lv ^ nw);
-    if (!retire) {                                    // gains will be brought up to date by the next kernel
-        if (p.newmask && w < p.colPitchW) p.newmask[w] = nw;
-        return;
-    }
+    if (!retire) return;                              // gains will be recomputed by regain_kernel
     unsigned int pending = __ballot_sync(0xffffffffu, nw != 0);
     while (pending) {
         const int src = __ffs(pending) - 1;
@@ -744,6 +741,8 @@ struct ClusterCfg {
     int off_lo, off_hi, off_w, off_mask, off_live, off_part;   // byte offsets into dynamic smem (cnt at 0)
     int lanes_per_row;  // power of two: lanes that share one row when retiring
     int gains_l2;       // 1: gains stay in global memory (L2 atomics); 0: distributed shared memory (DSMEM atomics)
+    uint32_t *newmask;  // [colPitchW] or null: the pick that ends the launch (st->regain) leaves the rows it newly covered
+                        // here, for cover_decrement_kernel
 };
 
 
@@ -788,6 +787,8 @@ __device__ __forceinline__ void retire_row_dsmem(const SelParams &p, const Clust
     }
 }
 
+// NEWMASK (opt-in): the pick that ends the launch leaves the bitmask of its newly covered rows in cfg.newmask.
+template <bool NEWMASK>
 __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, ClusterCfg cfg)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -927,7 +928,7 @@ __global__ void __launch_bounds__(1024, 1) select_cluster_kernel(SelParams p, Cl
             }
             if (nw) s_live[wl] = lv ^ nw;
             if (regain) {                                 // warp-uniform
-                if (p.newmask && w < p.colPitchW) p.newmask[w] = nw;
+                if (NEWMASK && w < p.colPitchW) cfg.newmask[w] = nw;
                 continue;
             }
             if (nw) {
@@ -1443,7 +1444,8 @@ int cluster_plan(const SelParams &p, int *cluster_out)
     *cluster_out = 0;
     static int configured = 0;
     if (!configured) {
-        UT_CUDA(cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        UT_CUDA(cudaFuncSetAttribute(select_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        UT_CUDA(cudaFuncSetAttribute(select_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         configured = 1;
     }
     const int tries[2] = {16, 8};
@@ -1453,7 +1455,7 @@ int cluster_plan(const SelParams &p, int *cluster_out)
         size_t smem = 0;
         if (!cluster_layout(p, CL, &cfg, &smem)) continue;
         if (smem > 227 * 1024 - 1024) continue;
-        if (cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        if (cudaFuncSetAttribute(select_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess) { cudaGetLastError(); continue; }
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(CL);
@@ -1465,18 +1467,20 @@ int cluster_plan(const SelParams &p, int *cluster_out)
         lc.attrs = attr;
         lc.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, select_cluster_kernel, &lc) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cudaOccupancyMaxActiveClusters(&n, select_cluster_kernel<false>, &lc) != cudaSuccess) { cudaGetLastError(); continue; }
         if (n >= 1) { *cluster_out = CL; return UTMOS_OK; }
     }
     return UTMOS_OK;
 }
 
-int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch)
+int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch, uint32_t *newmask)
 {
     ClusterCfg cfg;
     size_t smem = 0;
     if (!cluster_layout(p, CL, &cfg, &smem)) { set_error("cluster layout failed"); return UTMOS_E_ARG; }
-    UT_CUDA(cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.newmask = newmask;
+    auto kernel = newmask ? select_cluster_kernel<true> : select_cluster_kernel<false>;
+    UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(CL);
     lc.blockDim = dim3(1024);
@@ -1487,14 +1491,14 @@ int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launc
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    UT_CUDA(cudaLaunchKernelEx(&lc, select_cluster_kernel, p, cfg));
+    UT_CUDA(cudaLaunchKernelEx(&lc, kernel, p, cfg));
     *n_launch += 1;
     return UTMOS_OK;
 }
 
-int launch_cover_decrement(cudaStream_t stream, const SelParams &p, int *n_launch)
+int launch_cover_decrement(cudaStream_t stream, const SelParams &p, const uint32_t *newmask, int *n_launch)
 {
-    if (p.S <= 0 || p.V <= 0 || !p.newmask || p.af) { set_error("cover_decrement: count mode with a newmask buffer only"); return UTMOS_E_ARG; }
+    if (p.S <= 0 || p.V <= 0 || !newmask || p.af) { set_error("cover_decrement: count mode with a newmask buffer only"); return UTMOS_E_ARG; }
     const int col_passes = (p.pitchW + 255) / 256;
     long long gx = std::max(1, 2 * 148 / col_passes);                       // about two CTAs per SM in all
     long long wpc = (p.colPitchW + gx - 1) / gx;
@@ -1502,7 +1506,7 @@ int launch_cover_decrement(cudaStream_t stream, const SelParams &p, int *n_launc
     gx = (p.colPitchW + wpc - 1) / wpc;
     if (gx > 0x7fffffffll) { set_error("cover_decrement: matrix too large"); return UTMOS_E_ARG; }
     const size_t smem = (size_t)std::min(256, p.pitchW) * 32 * sizeof(unsigned int);
-    cover_decrement_kernel<<<dim3((unsigned)gx, (unsigned)col_passes), 256, smem, stream>>>(p, (int)wpc);
+    cover_decrement_kernel<<<dim3((unsigned)gx, (unsigned)col_passes), 256, smem, stream>>>(p, newmask, (int)wpc);
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
