@@ -386,3 +386,27 @@ def test_vcf_text_is_streamed_from_pipes_and_large_inputs(tmp_path):
     (tmp_path / "cut.bgzf").write_bytes(blobs["bgzf"][:-40])
     with pytest.raises(ValueError):
         list(vcf.read_vcf_genotypes(str(tmp_path / "cut.bgzf")))
+
+
+def test_chained_pick_model_matches_plain_greedy():
+    """The scheme behind select_tail_chain_kernel (tools/simulate_tail.py): exact top-K from per-warp top-K lists, and
+    picks taken down that list while the next candidate's gain has not moved, give the plain greedy order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("simulate_tail", os.path.join(ROOT, "tools", "simulate_tail.py"))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    rng = np.random.default_rng(2)
+    for n in (1, 5, 33, 1500, 2504):
+        g = rng.integers(0, 7, n)                                   # many ties: first index must win
+        top = sim.two_level_top_k(g, 4)
+        exact = np.lexsort((np.arange(n), -g))[:4]
+        assert [t[1] for t in top if t[0] > 0] == [int(i) for i in exact if g[i] > 0]
+    gt, cols, gains0 = sim.cohort(3000, 517)
+    ref, _, _ = sim.run(gt, cols, gains0, 517, 1)
+    for k in (2, 4):
+        picks, rounds, _ = sim.run(gt, cols, gains0, 517, k)
+        assert picks == ref and len(rounds) < len(ref)
+    # and the model's order is the oracle's order
+    keep, _ = orc.filter_rows_c(gt, 517)
+    o_idx, o_new, _, _ = orc.greedy_c(gt[keep], 517, np.ones(517, np.uint8), None, None, 517, exact=True)
+    assert [p[0] for p in ref] == list(o_idx) and [p[1] for p in ref] == list(o_new)
