@@ -23,6 +23,11 @@ UTMOS_B200_INGEST=2 python tools/bench_streaming.py --tag ingest2 >> gpurun_out/
 UTMOS_B200_INGEST=2 UTMOS_B200_INGEST_TILE=55296 python tools/bench_streaming.py --tag ingest2_tile54k >> gpurun_out/next_streaming.jsonl
 UTMOS_B200_INGEST=2 python tools/bench_streaming.py --tag ingest2_s100k --samples 100000 --vars 400000 --reps 3 >> gpurun_out/next_streaming.jsonl
 cut -c1-260 gpurun_out/next_streaming.jsonl
+#   6. hdf5 chunks decoded on the GPU (lzf_unpack_bool_kernel): the hdf5 parity tests, then config C4 both ways
+UTMOS_B200_H5_GPU_LZF=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "hdf5 or lowmem or h5 or cli_answer" > gpurun_out/next_pytest_gpulzf.log 2>&1; echo "pytest(gpu lzf) rc=$?"; tail -2 gpurun_out/next_pytest_gpulzf.log
+python tools/run_configs.py c4 --vars 200000 > gpurun_out/next_c4_host_lzf.json 2> gpurun_out/next_c4_host_lzf.err
+UTMOS_B200_H5_GPU_LZF=1 python tools/run_configs.py c4 --vars 200000 > gpurun_out/next_c4_gpu_lzf.json 2> gpurun_out/next_c4_gpu_lzf.err
+tail -c 600 gpurun_out/next_c4_host_lzf.json; echo; tail -c 600 gpurun_out/next_c4_gpu_lzf.json; echo
 python bench.py --no-cpu > gpurun_out/next_bench_default.json 2> gpurun_out/next_bench_default.err
 for cfg in "4096 4" "2048 8" "1024 8" "512 16" "256 16"; do
   set -- $cfg

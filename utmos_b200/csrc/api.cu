@@ -833,6 +833,98 @@ int utmos_append_dense_f32(utmos_ctx *c, const float *chunk, int64_t n_rows)
     return append_host(c, RAW_DENSE_F32, chunk, n_rows, c->S * 4, nullptr);
 }
 
+// Opt-in flavour of the chunk streamer for bool data (UTMOS_B200_H5_GPU_LZF=1): the host threads only pread the
+// COMPRESSED chunks into pinned staging (header: offsets, lengths, stored-raw flags; then the chunk bytes), one H2D
+// copy per batch, and lzf_unpack_bool_kernel decodes and packs them on the GPU.  Every row of an hdf5 file is kept
+// (utmos/select.py:153), so the destination of a chunk's rows is known on the host when nothing was appended before.
+static int append_h5_chunks_gpu_lzf(utmos_ctx *c, int fd, int64_t n_chunks, const int64_t *addr, const int64_t *nbytes,
+                                    const uint32_t *fmask, int64_t rows_per_chunk, int64_t total_rows, int lzf, int nthreads)
+{
+    UT_TRY(grow_rows(c, total_rows));
+    UT_TRY(ensure_stage(c, 0, true));
+    int *d_bad = nullptr;
+    UT_TRY(dev_alloc(c, (void **)&d_bad, 4));
+    UT_CUDA(cudaMemsetAsync(d_bad, 0, 4, c->stream));
+    int rc = UTMOS_OK;
+    long long rows_left = total_rows, rows_done = 0;
+    for (long long c0 = 0; c0 < n_chunks && rc == UTMOS_OK && rows_left > 0;) {
+        // chunks of this batch: header + 16-byte aligned chunk bytes must fit one staging buffer
+        long long k = 0;
+        size_t data = 0;
+        while (c0 + k < n_chunks && k < 16384) {
+            const size_t sz = ((size_t)nbytes[c0 + k] + 15) / 16 * 16;
+            const size_t hdr = ((size_t)(k + 1) * 13 + 15) / 16 * 16;
+            if (hdr + data + sz > kStageBytes) break;
+            data += sz;
+            ++k;
+        }
+        if (k == 0) { set_error("append_h5_chunks: one compressed chunk exceeds the staging buffer"); rc = UTMOS_E_ARG; break; }
+        const size_t hdr = ((size_t)k * 13 + 15) / 16 * 16;
+        const int b = c->stage_next;
+        c->stage_next ^= 1;
+        if (c->stage_used[b]) {
+            if (cudaEventSynchronize(c->ev_consumed[b]) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaEventSynchronize", __FILE__, __LINE__); break; }
+            cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0);
+        }
+        uint8_t *base = (uint8_t *)c->h_stage[b];
+        long long *h_off = reinterpret_cast<long long *>(base);
+        int *h_len = reinterpret_cast<int *>(base + (size_t)k * 8);
+        uint8_t *h_raw = base + (size_t)k * 12;
+        size_t at = 0;
+        for (long long i = 0; i < k; ++i) {
+            h_off[i] = (long long)at;
+            h_len[i] = (int)nbytes[c0 + i];
+            h_raw[i] = (!lzf || (fmask[c0 + i] & 1u)) ? 1 : 0;
+            at += ((size_t)nbytes[c0 + i] + 15) / 16 * 16;
+        }
+        std::atomic<long long> next(0);
+        std::atomic<int> bad(0);
+        auto worker = [&]() {
+            for (;;) {
+                const long long i = next.fetch_add(1);
+                if (i >= k || bad.load()) return;
+                if (pread(fd, base + hdr + (size_t)h_off[i], (size_t)h_len[i], addr[c0 + i]) != (ssize_t)h_len[i]) { bad.store(1); return; }
+            }
+        };
+        {
+            std::vector<std::thread> pool;
+            const int nt = (int)std::min<long long>(nthreads, k);
+            for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &t : pool) t.join();
+        }
+        if (bad.load()) { set_error("append_h5_chunks: short read"); rc = UTMOS_E_DATA; break; }
+        const long long n = std::min(rows_left, k * (long long)rows_per_chunk);
+        t_begin(c, T_H2D, c->copy_stream);
+        if (cudaMemcpyAsync(c->d_stage[b], base, hdr + data, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "cudaMemcpyAsync", __FILE__, __LINE__); break; }
+        t_end(c, c->copy_stream);
+        cudaEventRecord(c->ev_copied[b], c->copy_stream);
+        cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0);
+        const uint8_t *d_base = (const uint8_t *)c->d_stage[b];
+        t_begin(c, T_INGEST, c->stream);
+        rc = launch_lzf_unpack_bool(c->stream, d_base + hdr, reinterpret_cast<const long long *>(d_base),
+                                    reinterpret_cast<const int *>(d_base + (size_t)k * 8), d_base + (size_t)k * 12, k,
+                                    (int)rows_per_chunk, n, (int)c->S, c->pitchW, rows_done, c->d_rows, c->d_nrows, d_bad,
+                                    &c->n_launch);
+        t_end(c, c->stream);
+        cudaEventRecord(c->ev_consumed[b], c->stream);
+        c->stage_used[b] = true;
+        c->rows_upper += n;
+        rows_done += n;
+        rows_left -= n;
+        c0 += k;
+    }
+    int h_bad = 0;
+    if (rc == UTMOS_OK) {
+        if (cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess)
+            rc = cuda_fail(cudaGetLastError(), "lzf_unpack", __FILE__, __LINE__);
+        else if (h_bad) { set_error("append_h5_chunks: malformed LZF chunk"); rc = UTMOS_E_DATA; }
+    }
+    dev_free(c, d_bad, 4);
+    return rc;
+}
+
 // hdf5 chunk streamer: the chunks of the 'data' dataset are read (pread) and LZF-decoded by `threads` host threads
 // straight into the pinned staging buffers, one staging buffer of chunks at a time; the H2D copy and the packing
 // kernels of batch i run on the copy / compute streams while the host decodes batch i+1 into the other buffer.
@@ -854,6 +946,13 @@ int utmos_append_h5_chunks(utmos_ctx *c, const char *path, int64_t n_chunks, con
     if (chunk_bytes > kStageBytes) { set_error("append_h5_chunks: one chunk exceeds the staging buffer"); return UTMOS_E_ARG; }
     const int fd = open(path, O_RDONLY);
     if (fd < 0) { set_error(std::string("append_h5_chunks: cannot open ") + path); return UTMOS_E_ARG; }
+    static const bool gpu_lzf = getenv("UTMOS_B200_H5_GPU_LZF") && atoi(getenv("UTMOS_B200_H5_GPU_LZF")) != 0;
+    if (gpu_lzf && !is_f32 && c->rows_upper == 0 && chunk_bytes / 8 + (8 << 10) + 64 <= (200u << 10)) {
+        const int nt = std::max(1, std::min(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), 64));
+        const int rc_gpu = append_h5_chunks_gpu_lzf(c, fd, n_chunks, addr, nbytes, fmask, rows_per_chunk, total_rows, lzf, nt);
+        close(fd);
+        return rc_gpu;
+    }
     const long long per_batch = (long long)(kStageBytes / chunk_bytes);
     int rc = grow_rows(c, c->rows_upper + total_rows);
     if (rc == UTMOS_OK) rc = ensure_stage(c, is_f32 ? per_batch * rows_per_chunk : 0, true);

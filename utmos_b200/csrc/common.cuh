@@ -237,6 +237,11 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
                   long long pitch_in, const double *af_in, int S, int pitchW, uint32_t *rows_out, double *af_out,
                   long long *d_nrows, int *n_launch);
 
+int launch_lzf_unpack_bool(cudaStream_t stream, const uint8_t *blob, const long long *off, const int *len,
+                           const uint8_t *stored_raw, long long n_chunks, int rows_per_chunk, long long rows_in_batch,
+                           int S, int pitchW, long long row0, uint32_t *rows_out, long long *d_nrows, int *bad,
+                           int *n_launch);
+
 // select.cu
 int launch_transpose(cudaStream_t stream, const uint32_t *rows, long long V, int pitchW, int S, uint32_t *cols,
                      long long colPitchW, int *n_launch);

@@ -559,6 +559,151 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(const void *__restrict_
     rows_out[(*d_nrows + r) * pitchW + w] = word;
 }
 
+// ------------------------------------------------------------------------------------------------
+// hdf5 bool chunks decoded ON the GPU (opt-in, UTMOS_B200_H5_GPU_LZF=1): the host only reads the compressed chunks
+// (a few KB each for sparse genotypes) and copies them over PCIe; one warp per chunk decodes the LZF stream straight
+// into a BIT buffer in shared memory -- output byte p becomes bit p (byte != 0), so the 250 KB a dense chunk would
+// occupy are never materialised -- and then writes the chunk's rows in the matrix layout.  Token logic (hostio.cu has
+// the byte decoder it mirrors; the word-level scheme was modelled in NumPy against it):
+//   literal run (<= 32 bytes): one byte per lane, the ballot is inserted at bit p;
+//   back reference, offset >= length: each lane builds one destination word with a funnel shift over the source bits;
+//   back reference, offset < length (a repeating pattern, the way runs are stored): nothing to do when the pattern is
+//   all zero (the buffer starts zeroed) -- the common case for sparse data --, else bit by bit with i % offset.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLzfCompSmem = 8 * 1024;          // compressed bytes of a chunk staged in shared memory when they fit
+
+__device__ __forceinline__ uint32_t bits_get32(const uint32_t *w, int n_words, long long sbit)
+{
+    const long long i = sbit >> 5;                         // arithmetic shift: floor for negative positions
+    const unsigned int sh = (unsigned int)(sbit & 31);
+    const uint32_t lo = (i >= 0 && i < n_words) ? w[i] : 0u;
+    const uint32_t hi = (i + 1 >= 0 && i + 1 < n_words) ? w[i + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__global__ void __launch_bounds__(32) lzf_unpack_bool_kernel(const uint8_t *__restrict__ blob, const long long *__restrict__ off,
+                                                             const int *__restrict__ len, const uint8_t *__restrict__ stored_raw,
+                                                             int rows_per_chunk, long long rows_in_batch, int S, int pitchW,
+                                                             long long row0, uint32_t *__restrict__ rows_out, int *bad)
+{
+    extern __shared__ __align__(16) uint32_t z_smem[];
+    const int lane = threadIdx.x;
+    const long long chunk = blockIdx.x;
+    const long long chunk_bytes = (long long)rows_per_chunk * S;
+    const int n_words = (int)((chunk_bytes + 31) / 32) + 2;
+    uint32_t *s_bits = z_smem;
+    uint8_t *s_comp = reinterpret_cast<uint8_t *>(z_smem + n_words);
+    for (int i = lane; i < n_words; i += 32) s_bits[i] = 0u;
+    const uint8_t *src = blob + off[chunk];
+    const int n = len[chunk];
+    const bool staged = n <= kLzfCompSmem;
+    if (staged)
+        for (int i = lane; i < n; i += 32) s_comp[i] = src[i];
+    __syncwarp();
+    auto byte_at = [&](int i) -> unsigned int { return staged ? s_comp[i] : (unsigned int)__ldg(src + i); };
+    bool ok = true;
+    if (stored_raw[chunk]) {
+        // unfiltered chunk: the bytes themselves
+        if (n != chunk_bytes) ok = false;
+        for (long long p0 = 0; ok && p0 < chunk_bytes; p0 += 32) {
+            const long long p = p0 + lane;
+            const uint32_t m = __ballot_sync(0xffffffffu, p < chunk_bytes && __ldg(src + p) != 0);
+            if (lane == 0) s_bits[p0 >> 5] = m;
+        }
+    } else {
+        int ip = 0;
+        long long p = 0;
+        while (ok && ip < n) {
+            const unsigned int ctrl = byte_at(ip++);
+            if (ctrl < 32u) {
+                const int ln = (int)ctrl + 1;
+                if (ip + ln > n || p + ln > chunk_bytes) { ok = false; break; }
+                const uint32_t m = __ballot_sync(0xffffffffu, lane < ln && byte_at(ip + lane) != 0u);
+                if (lane == 0 && m) {
+                    const int w = (int)(p >> 5), sh = (int)(p & 31);
+                    s_bits[w] |= m << sh;
+                    if (sh + ln > 32) s_bits[w + 1] |= m >> (32 - sh);
+                }
+                ip += ln;
+                p += ln;
+            } else {
+                int ln = (int)(ctrl >> 5);
+                if (ln == 7) {
+                    if (ip >= n) { ok = false; break; }
+                    ln += (int)byte_at(ip++);
+                }
+                if (ip >= n) { ok = false; break; }
+                const long long offb = (long long)(((ctrl & 31u) << 8) | byte_at(ip++)) + 1;
+                ln += 2;
+                if (offb > p || p + ln > chunk_bytes) { ok = false; break; }
+                const long long q = p - offb;
+                if (offb >= ln) {
+                    const int wd0 = (int)(p >> 5), wd1 = (int)((p + ln - 1) >> 5);
+                    const int wd = wd0 + lane;
+                    uint32_t v = 0u;
+                    if (wd <= wd1) {
+                        v = bits_get32(s_bits, n_words, (long long)wd * 32 - offb);
+                        const int lo_d = (int)(max(p, (long long)wd * 32) - (long long)wd * 32);
+                        const int hi_d = (int)(min(p + ln, (long long)wd * 32 + 32) - (long long)wd * 32);
+                        const uint32_t m = (hi_d == 32 ? 0xffffffffu : ((1u << hi_d) - 1u)) & ~((1u << lo_d) - 1u);
+                        v &= m;
+                    }
+                    __syncwarp();                              // every source word has been read
+                    if (v) s_bits[wd] |= v;
+                } else {
+                    // pattern of offb (< 264) bits repeated: is there a set bit in it at all?
+                    uint32_t any = 0u;
+                    for (long long b0 = (q >> 5) * 32 + 32ll * lane; b0 < p; b0 += 32 * 32) {
+                        uint32_t x = s_bits[b0 >> 5];
+                        if (b0 < q) x &= ~((1u << (q - b0)) - 1u);                 // bits below q
+                        if (b0 + 32 > p) x &= (1u << (p - b0)) - 1u;               // bits from p on (p - b0 < 32 here)
+                        any |= x;
+                    }
+                    if (__any_sync(0xffffffffu, any != 0u)) {
+                        bool set[9];
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int i = lane + 32 * t;
+                            const long long sb = q + (i % (int)offb);
+                            set[t] = i < ln && ((s_bits[sb >> 5] >> (sb & 31)) & 1u);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const long long d = p + lane + 32 * t;
+                            if (set[t]) atomicOr(&s_bits[d >> 5], 1u << (d & 31));
+                        }
+                    }
+                }
+                p += ln;
+            }
+            __syncwarp();
+        }
+        if (ok && p != chunk_bytes) ok = false;
+    }
+    __syncwarp();
+    if (!ok) {
+        if (lane == 0) atomicExch(bad, 1);
+        return;
+    }
+    // rows of this chunk in the matrix layout (rows past the end of the dataset are padding of the last chunk)
+    const int nW = (S + 31) / 32;
+    for (int r = 0; r < rows_per_chunk; ++r) {
+        const long long row = chunk * rows_per_chunk + r;
+        if (row >= rows_in_batch) break;
+        uint32_t *dst = rows_out + (row0 + row) * pitchW;
+        for (int w = lane; w < pitchW; w += 32) {
+            uint32_t v = 0u;
+            if (w < nW) {
+                v = bits_get32(s_bits, n_words, (long long)r * S + 32ll * w);
+                const int nb = S - w * 32;
+                if (nb < 32) v &= (1u << nb) - 1u;
+            }
+            dst[w] = v;
+        }
+    }
+}
+
 __global__ void dense_af_kernel(const unsigned int *af_bits, long long n_rows, const long long *d_nrows, double *af_out)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -684,6 +829,30 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
         set_error("launch_ingest: unknown raw kind");
         return UTMOS_E_ARG;
     }
+}
+
+// hdf5 bool chunks decoded on the GPU.  blob/off/len/stored_raw: device copies of the compressed chunks of one batch;
+// the rows go to rows_out[(row0 + chunk * rows_per_chunk + r) * pitchW] and *d_nrows grows by rows_in_batch.
+// Returns UTMOS_E_ARG when a chunk does not fit the kernel's shared-memory bit buffer (caller falls back).
+int launch_lzf_unpack_bool(cudaStream_t stream, const uint8_t *blob, const long long *off, const int *len,
+                           const uint8_t *stored_raw, long long n_chunks, int rows_per_chunk, long long rows_in_batch,
+                           int S, int pitchW, long long row0, uint32_t *rows_out, long long *d_nrows, int *bad,
+                           int *n_launch)
+{
+    const long long chunk_bytes = (long long)rows_per_chunk * S;
+    const size_t smem = ((size_t)((chunk_bytes + 31) / 32) + 2) * 4 + kLzfCompSmem;
+    if (smem > 200 * 1024 || n_chunks > 0x7fffffffll) { set_error("lzf_unpack: chunk too large for the on-chip bit buffer"); return UTMOS_E_ARG; }
+    static size_t configured = 0;
+    if (smem > configured) {
+        UT_CUDA(cudaFuncSetAttribute(lzf_unpack_bool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    lzf_unpack_bool_kernel<<<(unsigned)n_chunks, 32, smem, stream>>>(blob, off, len, stored_raw, rows_per_chunk, rows_in_batch,
+                                                                     S, pitchW, row0, rows_out, bad);
+    bump_rows_by_kernel<<<1, 1, 0, stream>>>(d_nrows, rows_in_batch);
+    *n_launch += 2;
+    UT_CUDA(cudaGetLastError());
+    return UTMOS_OK;
 }
 
 }  // namespace utmos
