@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of the next round (about 6 GPU-minutes): the opt-in heavy-pick kernel through the whole suite, then
+# First GPU call of the next round (about 11 GPU-minutes; run it with --timeout 900): the opt-in heavy-pick kernel through the whole suite, then
 # the sweep that decides its defaults.  Everything lands in gpurun_out/.
 #   1. full parity suite with cover_decrement_kernel forced on (count mode; AF flavours keep regain_kernel)
 #   2. bench lines: default, decrement, decrement with lower thresholds (the mid picks, 1,800-4,500 rows each, then take
