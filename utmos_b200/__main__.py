@@ -1,46 +1,54 @@
-#!/usr/bin/env python3
+"""Command dispatcher of the B200 build: ``python -m utmos_b200 {convert,select,version} [options]``.
+
+Behaviour follows the reference CLI (utmos/__main__.py:17-47): the first word picks the command, everything after
+it is handed to that command untouched; without any argument the overview goes to stderr and the exit status is 0.
+The sub-commands are imported on demand, so ``version`` and the overview work without loading the CUDA library.
 """
-Utmos main entrypoint (mirror of utmos/__main__.py)
-"""
-import argparse
+import importlib
 import sys
 
 from utmos_b200 import __version__
-from utmos_b200.convert import cvt_main
-from utmos_b200.select import select_main
+
+# command -> (module, function, one line for the overview)
+COMMANDS = {
+    "convert": ("utmos_b200.convert", "cvt_main", "VCF -> packed genotype presence (.jl)"),
+    "select": ("utmos_b200.select", "select_main", "greedy maximum-coverage sample selection on the GPU"),
+    "version": (None, None, "print the version"),
+}
 
 
-def version(args):  # pylint: disable=unused-argument
-    """Print the version"""
-    print(f"Utmos v{__version__}")
+def overview():
+    lines = [f"Utmos v{__version__} (B200 build): pick the samples that together carry the most variants", "",
+             "usage: utmos CMD [OPTIONS ...]", ""]
+    width = max(len(name) for name in COMMANDS)
+    lines += [f"    {name.ljust(width)}   {about}" for name, (_, _, about) in COMMANDS.items()]
+    lines += ["", "`utmos CMD -h` lists the options of a command."]
+    return "\n".join(lines) + "\n"
 
 
-TOOLS = {"convert": cvt_main, "select": select_main, "version": version}
-
-USAGE = f"""\
-Utmos v{__version__} - Maximum-coverage algorithm to select samples for validation and resequencing
-
-    CMDs:
-        convert  Extract genotypes from VCFs
-        select   Select samples
-"""
+def run(argv):
+    """argv without the program name.  Returns the process exit status."""
+    if not argv:
+        sys.stderr.write(overview())
+        return 0
+    name, rest = argv[0], argv[1:]
+    if name in ("-h", "--help"):
+        sys.stdout.write(overview())
+        return 0
+    if name not in COMMANDS:
+        sys.stderr.write(overview())
+        sys.stderr.write(f"\nutmos: error: unknown command {name!r} (choose from {', '.join(COMMANDS)})\n")
+        return 2
+    if name == "version":
+        print(f"Utmos v{__version__}")
+        return 0
+    module, function, _ = COMMANDS[name]
+    getattr(importlib.import_module(module), function)(rest)
+    return 0
 
 
 def main():
-    """
-    Main entrypoint for utmos
-    """
-    parser = argparse.ArgumentParser(prog="utmos", description=USAGE,
-                                     formatter_class=argparse.RawDescriptionHelpFormatter)
-    parser.add_argument("cmd", metavar="CMD", choices=TOOLS.keys(), type=str, default=None,
-                        help="Command to execute")
-    parser.add_argument("options", metavar="OPTIONS", nargs=argparse.REMAINDER,
-                        help="Options to pass to the command")
-    if len(sys.argv) == 1:
-        parser.print_help(sys.stderr)
-        sys.exit()
-    args = parser.parse_args()
-    TOOLS[args.cmd](args.options)
+    sys.exit(run(sys.argv[1:]))
 
 
 if __name__ == "__main__":
