@@ -410,3 +410,84 @@ def test_chained_pick_model_matches_plain_greedy():
     keep, _ = orc.filter_rows_c(gt, 517)
     o_idx, o_new, _, _ = orc.greedy_c(gt[keep], 517, np.ones(517, np.uint8), None, None, 517, exact=True)
     assert [p[0] for p in ref] == list(o_idx) and [p[1] for p in ref] == list(o_new)
+
+
+class OracleMatrix:
+    """Stand-in for _native.DeviceMatrix in CPU tests of the host code: the C oracle does the arithmetic."""
+
+    def __init__(self, n_samples, af_mode=0, rows_hint=0, device=0, flags=0):
+        self.n_samples, self.af_mode = n_samples, af_mode
+        self.parts, self.afs = [], []
+
+    def append_packed(self, gt, af=None):
+        self.parts.append(np.asarray(gt))
+        self.afs.append(None if af is None else np.asarray(af, dtype=np.float64).reshape(-1))
+
+    def finalize(self):
+        packed = np.concatenate(self.parts)
+        keep, var_count = orc.filter_rows_c(packed, self.n_samples)
+        self.packed = packed[keep]
+        self.af = None
+        if self.af_mode != _native.AF_NONE:
+            self.af = np.concatenate(self.afs)[keep]
+            if self.af_mode == _native.AF_F32:
+                self.af = self.af.astype(np.float32).astype(np.float64)
+        self.num_vars = int(keep.sum())
+        return var_count
+
+    @property
+    def shape(self):
+        return (self.num_vars, self.n_samples)
+
+    @property
+    def dtype(self):
+        return np.dtype(bool) if self.af_mode == _native.AF_NONE else np.dtype(np.float64)
+
+    def begin(self, mask, weights=None):
+        self.result = orc.greedy_c(self.packed, self.n_samples, mask, weights, self.af, self.n_samples)
+        self.pos = 0
+
+    def steps(self, max_steps):
+        idx, new, score, stop = self.result
+        a, b = self.pos, min(len(idx), self.pos + max_steps)
+        self.pos = b
+        return idx[a:b], new[a:b], score[a:b], (stop if b == len(idx) else 0)
+
+    def close(self):
+        pass
+
+
+JL_KEYED = [
+    ("select_intcnt.txt", ["--count", "10", "chunk1.jl"]),
+    ("select_floatcnt.txt", ["--count", "0.01", "chunk2.jl"]),
+    ("select_first.txt", ["chunk2.jl"]),
+    ("select_multi.txt", ["chunk0.jl", "chunk2.jl"]),
+    ("select_exclude.txt", ["-c", "20", "--exclude", "NA21117", "chunk0.jl", "chunk1.jl"]),
+    ("select_weights.txt", ["-c", "20", "--weights", "weights.txt", "chunk0.jl"]),
+    ("select_af.txt", ["-c", "20", "--af", "chunk0.jl", "chunk1.jl"]),
+    ("select_weightsaf.txt", ["-c", "5", "--af", "--weights", "weights.txt", "chunk0.jl", "chunk1.jl"]),
+    ("select_weights_subset.txt", ["--subset", "subset.txt", "-c", "5", "--weights", "weights.txt", "chunk0.jl"]),
+    ("select_af_subset.txt", ["--subset", "subset.txt", "-c", "5", "--af", "chunk0.jl"]),
+]
+
+
+@pytest.mark.parametrize("key,argv", JL_KEYED, ids=[k for k, _ in JL_KEYED])
+def test_select_main_host_code_reproduces_answer_keys(key, argv, tmp_path, monkeypatch):
+    """The host side of `utmos select` (argument rules, sample lists, weights, report writer -- utmos/select.py:327-448)
+    with the C oracle standing in for the device: byte-identical to the reference's answer keys."""
+    monkeypatch.setattr(usel._native, "DeviceMatrix", OracleMatrix)
+    out = tmp_path / "report.txt"
+    usel.select_main([H.fixture(a) if os.path.exists(H.fixture(a)) else a for a in argv] + ["-o", str(out)])
+    assert out.read_text() == H.answer_key(key)
+
+
+def test_cli_dispatcher(capsys):
+    from utmos_b200 import __main__ as cli
+    assert cli.run([]) == 0
+    assert "convert" in capsys.readouterr().err                      # overview on stderr, status 0 (utmos/__main__.py:42-44)
+    assert cli.run(["version"]) == 0
+    assert capsys.readouterr().out.strip() == "Utmos v2.2.0"
+    assert cli.run(["bogus"]) == 2
+    with pytest.raises(SystemExit) as err:
+        cli.run(["select"])                                          # no inputs: the command's own error, exit 1
+    assert err.value.code == 1

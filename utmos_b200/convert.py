@@ -16,20 +16,24 @@ from utmos_b200.logutil import setup_logging
 from utmos_b200.vcf import read_vcf_genotypes
 
 
+# option table of `utmos convert` (flags and defaults of utmos/convert.py:20-35)
+_CONVERT_OPTIONS = (
+    (("in_file",), dict(type=str, help="VCF to read (.vcf, .vcf.gz, or /dev/stdin)")),
+    (("out_file",), dict(type=str, help=".jl file to write")),
+    (("--no-singleton",), dict(action="store_true", help="drop variants whose allele 0 or allele 1 is seen exactly once")),
+    (("--lowmem",), dict(action="store_true", help="accepted for compatibility: the VCF is streamed block by block anyway")),
+    (("-B", "--buffer"), dict(type=int, default=50000, help="variants per block (%(default)s)")),
+    (("-c", "--compress"), dict(type=int, default=5, help="joblib compression level of the .jl file (%(default)s)")),
+)
+
+
 def parse_args(args):
     """
-    Pull the command line parameters (utmos/convert.py:16-40)
+    Command line of `utmos convert`
     """
-    parser = argparse.ArgumentParser(prog="convert", description=__doc__.split("\n")[0],
-                                     formatter_class=argparse.RawDescriptionHelpFormatter)
-    parser.add_argument("in_file", type=str, help="Input VCF")
-    parser.add_argument("out_file", type=str, help="Output joblib")
-    parser.add_argument("--no-singleton", action="store_true", help="Remove singleton variants")
-    parser.add_argument("--lowmem", action="store_true",
-                        help="Lower memory usage with hdf5 temporary files (%(default)s)")
-    parser.add_argument("-B", "--buffer", type=int, default=50000,
-                        help="Number of variants read at a time (%(default)s)")
-    parser.add_argument("-c", "--compress", type=int, default=5, help="joblib compress level 1-9 (%(default)s)")
+    parser = argparse.ArgumentParser(prog="convert", description="VCF genotypes -> bit-packed presence matrix (.jl)")
+    for flags, spec in _CONVERT_OPTIONS:
+        parser.add_argument(*flags, **spec)
     args = parser.parse_args(args)
     setup_logging()
     logging.info("Params:\n%s", json.dumps(vars(args), indent=4))
@@ -82,10 +86,12 @@ def read_vcf(in_file, lowmem=False, chunk_length=2000, no_singleton=False, devic
 
 def cvt_main(cmdargs):
     """
-    Main (utmos/convert.py:91-99)
+    `utmos convert`: one VCF -> one .jl (the dict of utmos/convert.py:80-87, written like :98)
     """
     args = parse_args(cmdargs)
     data = read_vcf(args.in_file, args.lowmem, args.buffer, args.no_singleton)
-    logging.info("Saving genotypes")
+    rows, n_samples = data["GT"].shape[0], len(data["samples"])
+    logging.info("Saving %d variants x %d samples (%d het, %d hom-alt calls)", rows, n_samples,
+                 int(data["stats"]["num_het"]), int(data["stats"]["num_hom"]))
     joblib.dump(data, args.out_file, compress=args.compress)
     logging.info("Finished conversion")

@@ -216,125 +216,145 @@ def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, fla
 ###################
 def parse_sample_lists(argument):
     """
-    Parse the --exclude/--subset arguments (utmos/select.py:327-340): every item is a file of names when
-    such a file exists, otherwise a comma-separated list
+    --subset / --exclude values -> flat list of sample names (contract of utmos/select.py:327-340): an item that
+    names an existing file contributes one name per line, any other item is split at commas.
     """
-    ret = []
-    if not argument:
-        return ret
-    for item in argument:
+    names = []
+    for item in argument or ():
         if os.path.exists(item):
             with open(item, "r") as fh:
-                ret.extend(line.strip() for line in fh)
+                names += [line.strip() for line in fh]
         else:
-            ret.extend(item.split(","))
-    return ret
+            names += item.split(",")
+    return names
 
 
 def parse_weights(argument):
     """
-    Parse the weights file (utmos/select.py:343-352): two tab-delimited columns, no header
+    --weights TSV (sample <tab> weight, no header) -> DataFrame indexed by sample with one column ``weight``
+    (the shape run_selection expects, utmos/select.py:343-352); None when the option was not given.
     """
     if not argument:
         return None
-    data = pd.read_csv(argument, sep="\t", header=None)
-    data.columns = ["sample", "weight"]
-    data.set_index("sample", inplace=True)
-    return data
+    names, values = [], []
+    with open(argument, "r") as fh:
+        for lineno, line in enumerate(fh, 1):
+            line = line.rstrip("\r\n")
+            if not line:
+                continue
+            fields = line.split("\t")
+            if len(fields) != 2:
+                raise ValueError(f"{argument}:{lineno}: expected `sample<TAB>weight`")
+            names.append(fields[0])
+            values.append(float(fields[1]))
+    weights = np.asarray(values, dtype=np.float64)
+    if len(weights) and np.all(weights == np.floor(weights)):
+        weights = weights.astype(np.int64)                    # integers stay integers, like a csv reader infers
+    return pd.DataFrame({"weight": weights}, index=pd.Index(names, name="sample"))
+
+
+# option table of `utmos select` (flags, defaults and meaning of utmos/select.py:359-397, plus --device)
+_SELECT_OPTIONS = (
+    ("Selection", (
+        (("-c", "--count"), dict(type=float, default=0.02,
+                                 help="how many samples: a fraction of the cohort below 1, a number from 1 up, -1 for all (%(default)s)")),
+        (("-o", "--out"), dict(type=str, default="/dev/stdout", help="report file (%(default)s)")),
+        (("--debug",), dict(action="store_true", help="log at debug level")),
+    )),
+    ("Scoring", (
+        (("--af",), dict(action="store_true", help="score a variant by its allele frequency instead of 1")),
+        (("--weights",), dict(type=str, default=None, help="TSV of sample<TAB>weight; scores are multiplied by it")),
+        (("--subset",), dict(type=str, default=None, action="append",
+                             help="only these samples can be picked: a file of names or a comma separated list (repeatable)")),
+        (("--exclude",), dict(type=str, default=None, action="append",
+                              help="these samples are never picked: a file of names or a comma separated list (repeatable)")),
+    )),
+    ("Memory", (
+        (("--lowmem",), dict(type=str, default=None, help="hdf5 file to create from the inputs, or to read when it is the only input")),
+        (("--buffer",), dict(type=int, default=32768, help="variants per block while reading VCFs (%(default)s)")),
+        (("--maxmem",), dict(type=int, default=2, help="accepted for compatibility: the matrix lives in HBM (%(default)s)")),
+    )),
+    ("Device", (
+        (("--device",), dict(type=int, default=int(os.environ.get("UTMOS_DEVICE", "0")), help="CUDA device index (%(default)s)")),
+    )),
+)
+
+
+def _fail(message, *fmt):
+    logging.error(message, *fmt)
+    sys.exit(1)
 
 
 def parse_args(args):
     """
-    Pull the command line parameters (utmos/select.py:355-418)
+    Command line of `utmos select` (options and input rules of utmos/select.py:355-418)
     """
-    parser = argparse.ArgumentParser(prog="select", description=__doc__.strip().split("\n")[0],
-                                     formatter_class=argparse.RawDescriptionHelpFormatter)
-    parser.add_argument("in_files", nargs="*", type=str, help="Input VCF or jl files")
-    parser.add_argument("-c", "--count", type=float, default=0.02,
-                        help="Number of samples to select as a percent if <1 or count if >=1 or -1 for all (%(default)s)")
-    parser.add_argument("-o", "--out", type=str, default="/dev/stdout", help="Output file (stdout)")
-    parser.add_argument("--debug", action="store_true", help="Verbose logging")
-
-    scoreg = parser.add_argument_group("Scoring Arguments")
-    scoreg.add_argument("--af", action="store_true", help="Weigh variants by allele frequency")
-    scoreg.add_argument("--weights", type=str, default=None, help="Tab-delimited file of sample weights")
-    scoreg.add_argument("--subset", type=str, default=None, action="append",
-                        help="Filename with or Comma-separated list of samples to analyze")
-    scoreg.add_argument("--exclude", type=str, default=None, action="append",
-                        help="Filename with or Comma-separated list of samples to exclude selection")
-
-    mperfg = parser.add_argument_group("Memory Arguments")
-    mperfg.add_argument("--lowmem", type=str, default=None,
-                        help="Name of concatenated hdf5 file to create/use (%(default)s)")
-    mperfg.add_argument("--buffer", type=int, default=32768,
-                        help="Number of variants to buffer during concatenation (%(default)s)")
-    mperfg.add_argument("--maxmem", type=int, default=2,
-                        help="Maximum amount of memory in (GB). 0 keeps data in hdf5 (%(default)s)")
-
-    devg = parser.add_argument_group("Device Arguments")
-    devg.add_argument("--device", type=int, default=int(os.environ.get("UTMOS_DEVICE", "0")),
-                      help="CUDA device index (%(default)s)")
-
+    parser = argparse.ArgumentParser(prog="select", description="Select fewest samples with maximum number of variants")
+    parser.add_argument("in_files", nargs="*", type=str, help="VCF (.vcf, .vcf.gz), .jl or one .hdf5 input")
+    for title, options in _SELECT_OPTIONS:
+        group = parser.add_argument_group(f"{title} options")
+        for flags, spec in options:
+            group.add_argument(*flags, **spec)
     args = parser.parse_args(args)
     setup_logging(args.debug)
-    # Validate inputs
-    if [_ for _ in args.in_files if _.endswith(".hdf5")] and len(args.in_files) > 1:
-        logging.error("Cannot provide hdf5 with multiple input files")
-        sys.exit(1)
 
-    if len(args.in_files) == 0:
+    # input rules: an hdf5 file stands alone; without inputs --lowmem names the hdf5 to read; an hdf5 input is
+    # streamed (lowmem = 1 marks "in_files[0] is an existing utmos hdf5")
+    n_hdf5 = sum(name.endswith(".hdf5") for name in args.in_files)
+    if n_hdf5 and len(args.in_files) > 1:
+        _fail("Cannot provide hdf5 with multiple input files")
+    if not args.in_files:
         if not args.lowmem:
-            logging.error("No input files provided")
-            sys.exit(1)
-        args.in_files = [args.lowmem]
-        args.lowmem = 1
-
-    if len(args.in_files) == 1 and args.in_files[0].endswith(".hdf5") and not args.lowmem:
+            _fail("No input files provided")
+        args.in_files, args.lowmem = [args.lowmem], 1
+    elif n_hdf5 and not args.lowmem:
         logging.info("Switching on lowmem for hdf5 input")
         args.lowmem = 1
-
     logging.info("Params:\n%s", json.dumps(vars(args), indent=4))
     return args
 
 
+def _torchrun_comm(args):
+    """Under `torchrun -m utmos_b200 select ...`: host collectives of this rank (rows sharded over the ranks, SURVEY.md
+    8e); rank 0 keeps the report, the others write theirs to the null device.  None on a single process."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+    from utmos_b200.distributed import HostCollectives  # pylint: disable=import-outside-toplevel
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")
+    comm = HostCollectives()
+    args.device = int(os.environ.get("LOCAL_RANK", str(comm.rank)))
+    if comm.rank != 0:
+        args.out = os.devnull
+    return comm
+
+
+REPORT_COLUMNS = ("sample", "var_count", "new_count", "tot_captured", "pct_captured")
+
+
 def select_main(cmdargs):
     """
-    Main (utmos/select.py:421-448)
+    `utmos select`: load, check the data against --af, stream the report (utmos/select.py:421-448)
     """
     global MAXMEM  # pylint: disable=global-statement
     args = parse_args(cmdargs)
-
-    # `torchrun --nproc-per-node N -m utmos_b200 select ...`: one process per GPU, the rows of every input are
-    # sharded over the ranks (SURVEY.md 8e); every rank computes the same report, rank 0 writes it
-    comm = None
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        import torch.distributed as dist  # pylint: disable=import-outside-toplevel
-        from utmos_b200.distributed import HostCollectives  # pylint: disable=import-outside-toplevel
-        if not dist.is_initialized():
-            dist.init_process_group("gloo")
-        comm = HostCollectives()
-        args.device = int(os.environ.get("LOCAL_RANK", str(comm.rank)))
-        if comm.rank != 0:
-            args.out = os.devnull
-
+    comm = _torchrun_comm(args)
     data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device, comm=comm)
-    if data["data"].dtype == bool and args.af:
+    stored_af = data["data"].dtype != bool                   # float data = GT * AF, made with --af
+    if args.af and not stored_af:
         logging.critical("HDF5 file doesn't appear to be created with --af weighted scores, remove --af or recreate hdf5")
         sys.exit(1)
-    if data["data"].dtype != bool and not args.af:
+    if stored_af and not args.af:                             # the reference only warns here and carries on (:432-433)
         logging.critical("HDF5 file appears to be created with --af weighted scores, add --af or recreate hdf5")
-
-    args.subset = parse_sample_lists(args.subset)
-    args.exclude = parse_sample_lists(args.exclude)
-    args.weights = parse_weights(args.weights)
-
     MAXMEM = args.maxmem
-    with open(args.out, "w") as fout:
-        fout.write("sample\tvar_count\tnew_count\ttot_captured\tpct_captured\n")
-        m_iter = run_selection(data, args.count, args.subset, args.exclude, args.weights)
-        for result in m_iter:
-            logging.info("Selected %s (%.1f%% of variants)", result[0], result[4] * 100)
-            fout.write("\t".join([str(_) for _ in result]) + "\n")
-            fout.flush()
+    subset, exclude = parse_sample_lists(args.subset), parse_sample_lists(args.exclude)
+    weights = parse_weights(args.weights)
+    with open(args.out, "w") as report:
+        report.write("\t".join(REPORT_COLUMNS) + "\n")
+        for row in run_selection(data, args.count, subset, exclude, weights):
+            logging.info("Selected %s (%.1f%% of variants)", row[0], row[4] * 100)
+            report.write("\t".join(str(value) for value in row) + "\n")
+            report.flush()                                    # one line per pick, visible as soon as it is made
     data.close()
     logging.info("Finished utmos")
