@@ -173,13 +173,13 @@ def test_native_vcf_tokenizer_matches_python_restatement(tmp_path, ending, conta
     """csrc/vcfio.cu against vcf.read_vcf_genotypes_py on genotype forms the fixtures do not contain."""
     import gzip
     sep = "\r\n" if ending == "\r\n" else "\n"
-    text = (VCF_HEAD + sep.join(VCF_LINES) + ending).encode()
+    text = (VCF_HEAD.replace("\n", sep) + sep.join(VCF_LINES) + ending).encode()     # CRLF files: header lines too
     path = tmp_path / ("t.vcf" if container == "plain" else "t.vcf.gz")
     path.write_bytes(text if container == "plain" else gzip.compress(text) if container == "gzip" else _bgzf(text, 97))
     want = list(vcf.read_vcf_genotypes_py(str(path), 3))
     for slab in (1 << 20, 150):                                  # 150-byte slabs: lines straddle slab boundaries
         got = list(vcf.read_vcf_genotypes(str(path), 3, threads=3, slab_bytes=slab))
-        assert list(got[0][0]) == list(want[0][0])
+        assert list(got[0][0]) == list(want[0][0]) == ["A", "B", "C", "D"]       # no '\r' glued to the last name
         a, b = np.concatenate([g for _, g in got]), np.concatenate([g for _, g in want])
         assert a.shape == b.shape == (len(VCF_LINES), 4, 2) and np.array_equal(a, b)
         assert all(g.shape[0] <= 3 for _, g in got)
@@ -386,30 +386,6 @@ def test_vcf_text_is_streamed_from_pipes_and_large_inputs(tmp_path):
     (tmp_path / "cut.bgzf").write_bytes(blobs["bgzf"][:-40])
     with pytest.raises(ValueError):
         list(vcf.read_vcf_genotypes(str(tmp_path / "cut.bgzf")))
-
-
-def test_chained_pick_model_matches_plain_greedy():
-    """The scheme behind select_tail_chain_kernel (tools/simulate_tail.py): exact top-K from per-warp top-K lists, and
-    picks taken down that list while the next candidate's gain has not moved, give the plain greedy order."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("simulate_tail", os.path.join(ROOT, "tools", "simulate_tail.py"))
-    sim = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(sim)
-    rng = np.random.default_rng(2)
-    for n in (1, 5, 33, 1500, 2504):
-        g = rng.integers(0, 7, n)                                   # many ties: first index must win
-        top = sim.two_level_top_k(g, 4)
-        exact = np.lexsort((np.arange(n), -g))[:4]
-        assert [t[1] for t in top if t[0] > 0] == [int(i) for i in exact if g[i] > 0]
-    gt, cols, gains0 = sim.cohort(3000, 517)
-    ref, _, _ = sim.run(gt, cols, gains0, 517, 1)
-    for k in (2, 4):
-        picks, rounds, _ = sim.run(gt, cols, gains0, 517, k)
-        assert picks == ref and len(rounds) < len(ref)
-    # and the model's order is the oracle's order
-    keep, _ = orc.filter_rows_c(gt, 517)
-    o_idx, o_new, _, _ = orc.greedy_c(gt[keep], 517, np.ones(517, np.uint8), None, None, 517, exact=True)
-    assert [p[0] for p in ref] == list(o_idx) and [p[1] for p in ref] == list(o_new)
 
 
 class OracleMatrix:

@@ -946,7 +946,10 @@ int utmos_append_h5_chunks(utmos_ctx *c, const char *path, int64_t n_chunks, con
     if (chunk_bytes > kStageBytes) { set_error("append_h5_chunks: one chunk exceeds the staging buffer"); return UTMOS_E_ARG; }
     const int fd = open(path, O_RDONLY);
     if (fd < 0) { set_error(std::string("append_h5_chunks: cannot open ") + path); return UTMOS_E_ARG; }
-    static const bool gpu_lzf = getenv("UTMOS_B200_H5_GPU_LZF") && atoi(getenv("UTMOS_B200_H5_GPU_LZF")) != 0;
+    // bool chunks are LZF-decoded on the GPU (lzf_unpack_bool_kernel): the host only reads the compressed bytes, so PCIe
+    // carries the file size instead of the dense size (C4 at 50,000 x 200,000: 134 ms against 257 ms with the host codec).
+    // UTMOS_B200_H5_GPU_LZF=0 keeps the host codec for A/B runs.
+    static const bool gpu_lzf = !(getenv("UTMOS_B200_H5_GPU_LZF") && atoi(getenv("UTMOS_B200_H5_GPU_LZF")) == 0);
     if (gpu_lzf && !is_f32 && c->rows_upper == 0 && chunk_bytes / 8 + (8 << 10) + 64 <= (200u << 10)) {
         const int nt = std::max(1, std::min(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), 64));
         const int rc_gpu = append_h5_chunks_gpu_lzf(c, fd, n_chunks, addr, nbytes, fmask, rows_per_chunk, total_rows, lzf, nt);
@@ -1223,8 +1226,9 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         if (!multi && !(c->flags & UTMOS_F_NO_TAIL)) UT_TRY(tail_plan(p, &tail_ok));
         if (multi) tail_ok = c->mg_list_cap > 0;          // same decision on every rank (utmos_mgpu_export)
         // heavy picks in count mode: subtract the newly covered rows (cover_decrement_kernel) instead of recomputing
-        // every gain from the sample-major copy (regain_kernel).  Opt-in until it has been through the full GPU suite.
-        static const bool use_decrement = getenv("UTMOS_B200_DECREMENT") && atoi(getenv("UTMOS_B200_DECREMENT")) != 0;
+        // every gain from the sample-major copy (regain_kernel).  Default since round 2 (full GPU suite green with it,
+        // greedy loop 9.83 -> 9.06 ms on the 1kGP shape); UTMOS_B200_DECREMENT=0 goes back to regain_kernel for A/B runs.
+        static const bool use_decrement = !(getenv("UTMOS_B200_DECREMENT") && atoi(getenv("UTMOS_B200_DECREMENT")) == 0);
         if (use_decrement && !multi && !af && CL > 0 && c->d_cols && !c->d_newmask && !(c->flags & UTMOS_F_STEP_KERNELS))
             UT_TRY(dev_alloc(c, (void **)&c->d_newmask, (size_t)c->colPitchW * 4));
         // Head: greedy steps by the cluster (or grid-wide, or multi-GPU) kernel; a pick that covers very many rows

@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(const unsigned int *
 // in the list of each carrier.  ESTRIDE = 1 (count) or 2 (AF flavours: second uint4 = fixed-point AF limbs).
 // EdgeDst says where the entries go: single GPU = this context's buffers; multi-GPU = the SAME slots of every
 // rank's merged buffers (peer pointers, NVLink stores), so all ranks end up with byte-identical lists.
-// SKIP_SINGLE (opt-in): rows that only one sample carries get no entry.
-template <int ESTRIDE, bool WIDE, bool SKIP_SINGLE = false>
+template <int ESTRIDE, bool WIDE>
 __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d, unsigned int *cursor,
                                                           unsigned int *pool_cursor)
 {
@@ -127,9 +126,6 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
             if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        // opt-in: a row that only one sample carries changes nobody else's gain when it is covered and is already
-        // counted in that sample's own gain (its new_count), so the tail never needs to see it
-        if (SKIP_SINGLE && total == 1) continue;
         uint4 tailq = make_uint4(0u, 0u, 0u, 0u);
         if (ESTRIDE == 2) {
             const unsigned long long ql = p.q_lo[r], qh = p.q_hi[r];
@@ -197,14 +193,13 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
 }
 
 // Re-compaction: one CTA per sample copies the entries whose row is still live (streaming filter).
-template <int ESTRIDE, bool REPORT_LEN = false>
+template <int ESTRIDE>
 __global__ void __launch_bounds__(256) filter_edges_kernel(const uint32_t *__restrict__ live,
                                                            const uint4 *__restrict__ old_lists,
                                                            const unsigned int *__restrict__ old_off,
                                                            const unsigned int *__restrict__ old_len,
                                                            uint4 *__restrict__ new_lists,
-                                                           const unsigned int *__restrict__ new_off,
-                                                           unsigned int *new_len_out)
+                                                           const unsigned int *__restrict__ new_off)
 {
     __shared__ unsigned int s_cursor;
     const int s = blockIdx.x;
@@ -236,17 +231,6 @@ __global__ void __launch_bounds__(256) filter_edges_kernel(const uint32_t *__res
             }
         }
     }
-    if (REPORT_LEN) {                   // lists without single-carrier rows: fewer entries than the gain says
-        __syncthreads();
-        if (threadIdx.x == 0) new_len_out[s] = s_cursor;
-    }
-}
-
-// lists without single-carrier rows: the length of a list is what the build wrote, not the gain
-__global__ void list_len_from_cursor_kernel(const unsigned int *cursor, unsigned int *list_len, int S)
-{
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S) list_len[s] = cursor[s];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -747,273 +731,6 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     if (CL > 1) cg::this_cluster().sync();           // nobody leaves while a peer may still write into its shared memory
 }
 
-// ------------------------------------------------------------------------------------------------
-// Chained picks (opt-in, UTMOS_B200_TAIL_CHAIN=K): count mode without weights, one CTA, 16-bit carriers.
-//
-// Gains only fall.  If the argmax also returns the exact runners-up c1 > c2 > ... (np.argmax order: larger gain, then
-// lower index), then after the walk of the winner the next pick IS c1 whenever c1's own gain did not move: everybody
-// else was behind it and can only have fallen further.  The same holds for c2 after c1's walk, and so on; the first
-// candidate whose gain moved ends the chain and the argmax runs again.  On the 1kGP-shaped cohort the runner-up is
-// untouched in 90 % of the picks of the second half of a selection (1,125 argmax rounds instead of 2,504 with K = 4,
-// simulated on the full cohort), and every candidate's list is prefetched at argmax time.
-// Exact top-K: every warp extracts its own K best with K REDUX rounds (no barrier), one barrier, then every warp
-// merges the 32 sorted lists redundantly (lane l holds warp l's list, K more REDUX rounds).
-// ------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(1024, 1) select_tail_chain_kernel(SelParams p, TailCfg cfg, unsigned long long lists_total)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ uint2 s_topw[32][K];
-    __shared__ unsigned long long s_sum[32];
-    __shared__ unsigned int s_stage_n;
-    constexpr int kPerChunk = 8;
-    constexpr unsigned int kPad = 0xffffu;
-    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(smem);
-    uint8_t *s_mask = smem + cfg.off_mask;
-    unsigned int *s_loff = reinterpret_cast<unsigned int *>(smem + cfg.off_loff);
-    unsigned int *s_llen = reinterpret_cast<unsigned int *>(smem + cfg.off_llen);
-    uint32_t *s_live = reinterpret_cast<uint32_t *>(smem + cfg.off_live);
-    uint4 *s_stage = reinterpret_cast<uint4 *>(smem + cfg.off_stage);
-    const uint4 *pool16 = reinterpret_cast<const uint4 *>(p.pool);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool live_smem = cfg.live_words > 0;
-    const int S = p.S;
-    SelState *st = p.st;
-    for (int i = tid; i < S; i += blockDim.x) {
-        s_cnt[i] = p.gain_cnt[i];
-        s_mask[i] = p.mask[i];
-        s_loff[i] = p.list_off[i];
-        s_llen[i] = p.list_len[i];
-    }
-    for (int i = tid; i < cfg.live_words; i += blockDim.x) s_live[i] = p.live[i];
-    uint32_t *g_live = p.live;
-    long long step = st->step, tot = st->tot;
-    const long long limit = st->limit;
-    int stop = st->stop;
-    int recompact = 0;
-    int since_check = 0;
-    if (tid == 0) s_stage_n = 0;
-    __syncthreads();
-
-    while (stop == 0 && step < limit) {
-        // ---- every 64 picks: how many list entries are still live?  (sum of the gains)
-        if (since_check >= 64) {
-            since_check = 0;
-            unsigned long long acc = 0;
-            for (int i = tid; i < S; i += blockDim.x) acc += s_cnt[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) s_sum[warp] = acc;
-            __syncthreads();
-            unsigned long long live_now = s_sum[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) live_now += __shfl_xor_sync(0xffffffffu, live_now, o);
-            __syncthreads();
-            if (live_now >= cfg.min_recompact && live_now * 2 <= lists_total && limit - step > 128) {
-                recompact = 1;
-                break;
-            }
-        }
-        // ---- exact top-K of the selectable gains, np.argmax order
-        unsigned long long taken = 0ull;                    // this thread's elements already handed out (element e = tid + 1024 e)
-#pragma unroll
-        for (int r = 0; r < K; ++r) {
-            unsigned int bk = 0u, bi = 0x7fffffffu;
-            int be = -1;
-            for (int e = 0, i = tid; i < S; ++e, i += 1024) {
-                if ((taken >> e) & 1ull) continue;
-                const unsigned int k = s_mask[i] == 1 ? s_cnt[i] : 0u;
-                if (be < 0 || k > bk) { bk = k; bi = (unsigned int)i; be = e; }      // ascending index: first kept on ties
-            }
-            const uint2 w = warp_argmax_u32(bk, bi);
-            if (be >= 0 && bi == w.y) taken |= 1ull << be;
-            if (lane == 0) s_topw[warp][r] = w;
-        }
-        __syncthreads();
-        uint2 mine[K], top[K];
-#pragma unroll
-        for (int r = 0; r < K; ++r) mine[r] = s_topw[lane][r];
-        int ptr = 0;
-#pragma unroll
-        for (int r = 0; r < K; ++r) {
-            uint2 c = make_uint2(0u, 0x7fffffffu);
-#pragma unroll
-            for (int q = 0; q < K; ++q)
-                if (q == ptr) c = mine[q];
-            const uint2 g = warp_argmax_u32(c.x, c.y);
-            if (c.y == g.y && g.y != 0x7fffffffu) ptr += 1;
-            top[r] = g;
-        }
-        // warm L2 with the lists of the runners-up
-#pragma unroll
-        for (int r = 1; r < K; ++r) {
-            if (top[r].x == 0u || top[r].y == 0x7fffffffu) continue;
-            const uint4 *l2 = p.lists + (size_t)s_loff[top[r].y];
-            const int lines = ((int)s_llen[top[r].y] + 7) >> 3;          // 128-byte lines
-            for (int i = tid; i < lines; i += blockDim.x) prefetch_l2(l2 + (size_t)i * 8);
-        }
-#pragma unroll 1
-        for (int c = 0; c < K; ++c) {
-            uint2 cand = top[0];
-#pragma unroll
-            for (int q = 1; q < K; ++q)
-                if (q == c) cand = top[q];
-            const unsigned int best_cnt = cand.x;
-            const int best_idx = (int)cand.y;
-            if (c == 0) {
-                if (S == 0 || best_cnt == 0u) {                     // utmos/select.py:51-52
-                    stop = UTMOS_STOP_ZERO;
-                    break;
-                }
-            } else {
-                if (best_cnt == 0u || best_idx == 0x7fffffff || step >= limit) break;
-                // Its gain moved since the argmax -> run the argmax again.  The previous walk ended with a barrier, so the
-                // gain is final when it is read here; the barrier inside the vote keeps every thread's read ahead of the
-                // next walk (which may lower this very gain through a pooled carrier list) and publishes tid 0's resets.
-                if (!__syncthreads_and(s_cnt[best_idx] == best_cnt)) break;
-            }
-            const unsigned int best_off = s_loff[best_idx], best_len = s_llen[best_idx];
-            if (tid == 0) {
-                p.out_idx[step] = best_idx;
-                p.out_new[step] = best_cnt;
-                p.out_score[step] = (double)best_cnt;
-                if (p.dbg_time) p.out_time[step] = global_timer_ns();
-                s_mask[best_idx] = 0;                             // utmos/select.py:100
-            }
-            step += 1;
-            since_check += 1;
-            tot += best_cnt;
-            if (tot >= p.V) {                                     // utmos/select.py:110-112
-                stop = UTMOS_STOP_ALL;
-                break;
-            }
-            // ---- stream the pick's list; a live bit that we clear marks a newly covered row
-            const uint4 *lst = p.lists + (size_t)best_off;
-            const int len = (int)best_len;
-            const int sub = lane & 7, slot = lane >> 3;
-            int staged_any = 0;
-            auto retire_chunk = [&](const uint4 &v) {
-                const unsigned int ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < kPerChunk; ++q) {
-                    const unsigned int cs = (q & 1) ? ww[q >> 1] >> 16 : ww[q >> 1] & 0xffffu;
-                    if (cs != kPad) atomicAdd(s_cnt + cs, 0xffffffffu);
-                }
-            };
-            auto retire_staged = [&]() {
-                const unsigned int staged_n = min(s_stage_n, cfg.stage_cap);
-                for (unsigned int c0 = tid; c0 < staged_n; c0 += blockDim.x) retire_chunk(s_stage[c0]);
-            };
-            const int ept = best_cnt > cfg.stage_cap / 2u ? 1 : 4;
-            const int bstride = ept * (int)blockDim.x;
-            for (int base = 0; base < len; base += bstride) {
-                uint4 e[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = base + u * (int)blockDim.x + tid;
-                    e[u] = (u < ept && i < len) ? __ldg(lst + (size_t)i) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (u >= ept || base + u * (int)blockDim.x + warp * 32 >= len) break;       // warp-uniform
-                    const unsigned int r = e[u].x;
-                    bool fresh = false;
-                    if (r != 0xffffffffu) {
-                        const uint32_t bit = 1u << (r & 31);
-                        uint32_t *lw = (live_smem ? s_live : g_live) + (r >> 5);
-                        fresh = (*reinterpret_cast<volatile uint32_t *>(lw) & bit) != 0;
-                        if (fresh) atomicAnd(lw, ~bit);
-                    }
-                    // entry: {row, n | c0 << 16, c1 | c2 << 16, c3 | c4 << 16}; pooled (n == 0xffff): {row, pooled, first pool element, carriers}
-                    const unsigned int n = e[u].y & 0xffffu;
-                    const bool pooled = n == kPooled;
-                    if (fresh && !pooled) {
-                        const unsigned int cc[kInline] = {e[u].y >> 16, e[u].z & 0xffffu, e[u].z >> 16, e[u].w & 0xffffu, e[u].w >> 16};
-#pragma unroll
-                        for (int j = 0; j < kInline; ++j)
-                            if (j < (int)n) atomicAdd(s_cnt + cc[j], 0xffffffffu);
-                    }
-                    const bool big = fresh && pooled;
-                    unsigned int m = 0;
-                    if (__any_sync(0xffffffffu, big)) {
-                        staged_any = 1;
-                        const unsigned int n8 = big ? (e[u].w + kPerChunk - 1) / kPerChunk : 0u;
-                        const unsigned int my0 = big ? atomicAdd(&s_stage_n, n8) : 0u;
-                        const bool staged = big && my0 + n8 <= cfg.stage_cap;
-                        if (staged) {
-                            const uint4 *src = pool16 + e[u].z / kPerChunk;
-                            for (unsigned int k = 0; k < n8; ++k) {
-                                const unsigned int sa = (unsigned int)__cvta_generic_to_shared(s_stage + my0 + k);
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + k) : "memory");
-                            }
-                        } else if (big) {
-                            for (unsigned int k = my0; k < my0 + n8 && k < cfg.stage_cap; ++k) s_stage[k] = make_uint4(~0u, ~0u, ~0u, ~0u);
-                        }
-                        m = __ballot_sync(0xffffffffu, big && !staged);
-                    }
-                    while (m) {                                   // overflow of the staging area: straight from the pool
-                        int src = -1;
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; ++s4) {
-                            if (m) {
-                                const int bpos = __ffs(m) - 1;
-                                m &= m - 1;
-                                if (slot == s4) src = bpos;
-                            }
-                        }
-                        const int from = src < 0 ? 0 : src;
-                        const unsigned int pbase = __shfl_sync(0xffffffffu, e[u].z, from);
-                        const unsigned int cnt_from = __shfl_sync(0xffffffffu, e[u].w, from);
-                        const unsigned int cnt = src < 0 ? 0u : cnt_from;
-                        const uint4 *pl = pool16 + pbase / kPerChunk;
-                        const unsigned int n8 = (cnt + kPerChunk - 1) / kPerChunk;
-                        for (unsigned int k0 = sub; k0 < n8; k0 += 16) {
-                            const uint4 v0 = __ldg(pl + k0);
-                            const uint4 v1 = k0 + 8 < n8 ? __ldg(pl + k0 + 8) : make_uint4(~0u, ~0u, ~0u, ~0u);
-                            retire_chunk(v0);
-                            retire_chunk(v1);
-                        }
-                    }
-                }
-                if (base + bstride < len) {                       // more batches follow (block-uniform): drain the staging area
-                    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-                    if (__syncthreads_or(staged_any)) {
-                        retire_staged();
-                        __syncthreads();
-                        if (tid == 0) s_stage_n = 0;
-                        __syncthreads();
-                    }
-                    staged_any = 0;
-                }
-            }
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-            if (__syncthreads_or(staged_any)) {
-                retire_staged();
-                __syncthreads();
-            }
-            if (tid == 0) {
-                s_stage_n = 0;                                    // the next walk starts after a barrier (argmax, or the chain's own)
-                s_cnt[best_idx] = 0;                              // keeps sum(gains) == live list entries
-            }
-        }
-    }
-
-    __syncthreads();
-    for (int i = tid; i < S; i += blockDim.x) {
-        p.gain_cnt[i] = s_cnt[i];
-        p.mask[i] = s_mask[i];
-    }
-    for (int i = tid; i < cfg.live_words; i += blockDim.x) p.live[i] = s_live[i];
-    if (tid == 0) {
-        st->step = step;
-        st->tot = tot;
-        st->stop = stop;
-        st->winner = -1;
-        st->regain = 0;
-        st->recompact = recompact;
-    }
-}
-
 // CL: CTAs that share the per-sample state (1 = everything in one CTA)
 int tail_layout(const SelParams &p, int CL, TailCfg *cfg, size_t *smem_bytes)
 {
@@ -1060,13 +777,6 @@ int launch_sum_gains(cudaStream_t stream, const SelParams &p, int *n_launch)
     return UTMOS_OK;
 }
 
-// opt-in (UTMOS_B200_SKIP_SINGLE=1, single GPU): edge lists without the rows that only one sample carries
-static bool skip_single_rows()
-{
-    static const bool on = getenv("UTMOS_B200_SKIP_SINGLE") && atoi(getenv("UTMOS_B200_SKIP_SINGLE")) != 0;
-    return on;
-}
-
 int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, unsigned int *list_off,
                        unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,
                        int *n_launch)
@@ -1079,15 +789,7 @@ int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, un
     d.lists[0] = lists;
     d.pool[0] = pool;
     d.slot_base = list_off;
-    if (!skip_single_rows() || p.S > 65535) return launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch);
-    UT_CUDA(cudaMemsetAsync(pool_cursor, 0, 4, stream));
-    long long blocks = std::max(1ll, std::min((p.V + 7) / 8, 148ll * 16));
-    if (p.af) build_edges_kernel<2, false, true><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
-    else build_edges_kernel<1, false, true><<<(unsigned)blocks, 256, 0, stream>>>(p, d, cursor, pool_cursor);
-    list_len_from_cursor_kernel<<<(p.S + 255) / 256, 256, 0, stream>>>(cursor, list_len, p.S);
-    *n_launch += 2;
-    UT_CUDA(cudaGetLastError());
-    return UTMOS_OK;
+    return launch_build_edges(stream, p, d, cursor, pool_cursor, n_launch);
 }
 
 // cursor[S] must be zero; entries go to d.lists[q][slot_base[s] + k] for every q < d.world
@@ -1113,11 +815,8 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
                         int *n_launch)
 {
     list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.S, new_off, new_len, nullptr);
-    if (skip_single_rows() && p.S <= 65535) {
-        if (p.af) filter_edges_kernel<2, true><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, new_len);
-        else filter_edges_kernel<1, true><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, new_len);
-    } else if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, nullptr);
-    else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off, nullptr);
+    if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off);
+    else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off);
     *n_launch += 2;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
@@ -1215,19 +914,9 @@ int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long list
     } else if (CL == 8) {
         if (p.af) UT_TAIL(2, false, 8, false); else if (p.weights) UT_TAIL(1, false, 8, false); else UT_TAIL(1, true, 8, false);
     } else {
-        static const int chain = getenv("UTMOS_B200_TAIL_CHAIN") ? atoi(getenv("UTMOS_B200_TAIL_CHAIN")) : 1;
         if (p.af) UT_TAIL(2, false, 1, false);
         else if (p.weights) UT_TAIL(1, false, 1, false);
-        else if (chain >= 2 && p.S <= 8192) {
-            // opt-in: chained picks (exact top-K per argmax round); K = 2 or 4
-            if (chain >= 4) {
-                UT_CUDA(cudaFuncSetAttribute(select_tail_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                select_tail_chain_kernel<4><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
-            } else {
-                UT_CUDA(cudaFuncSetAttribute(select_tail_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                select_tail_chain_kernel<2><<<1, 1024, smem, stream>>>(p, cfg, lists_total);
-            }
-        } else UT_TAIL(1, true, 1, false);
+        else UT_TAIL(1, true, 1, false);
     }
 #undef UT_TAIL
     *n_launch += 1;

@@ -149,14 +149,30 @@ def _load_hdf5(path, device, flags, comm=None):
             matrix.append_h5_chunks(path, table[0][c_begin:c_end], table[1][c_begin:c_end], table[2][c_begin:c_end],
                                     dset.chunks[0], rows_here, is_float, dset.has_lzf)
         else:
+            # holes / unordered chunks: a chunk that was never allocated reads as fill-value rows (all zero) in the
+            # reference, and those rows count in num_vars = data.shape[0] (utmos/select.py:153)
             r_begin, r_end = _my_rows(num_rows, comm)
+            next_row = r_begin
+
+            def _zero_rows(upto):
+                nonlocal next_row
+                while next_row < upto:
+                    n = min(upto - next_row, max(1, (64 << 20) // max(1, num_samples * dset.dtype.itemsize)))
+                    matrix.append_dense(np.zeros((n, num_samples), dtype=dset.dtype))
+                    next_row += n
+
             for first, block in dset.iter_chunks():
                 lo, hi = max(first, r_begin), min(first + block.shape[0], r_end)
                 if lo < hi:
+                    _zero_rows(lo)
                     matrix.append_dense(block[lo - first:hi - first])
+                    next_row = hi
+            _zero_rows(r_end)
         samples = h5["samples"].read()
         stored_var_count = h5["var_count"].read() if "var_count" in h5 else None
     var_count = matrix.finalize()
+    if matrix.shape[0] != num_rows:
+        raise h5lite.H5FormatError(f"{path}: ingested {matrix.shape[0]} rows, the dataset has {num_rows}")
     if stored_var_count is not None and not np.array_equal(stored_var_count, var_count):
         logging.warning("var_count stored in %s differs from the data; using the stored values", path)
         var_count = np.asarray(stored_var_count)

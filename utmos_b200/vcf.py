@@ -158,7 +158,7 @@ def read_vcf_genotypes(path, chunk_length=2000, threads=0, slab_bytes=SLAB_BYTES
                     carry = text
                     continue
                 end = len(blob)
-            samples = np.array(blob[pos:end].decode().split("\t")[9:])
+            samples = np.array(blob[pos:end].rstrip(b"\r").decode().split("\t")[9:])     # CRLF files: no '\r' in the last name
             if len(samples) == 0:
                 raise ValueError(f"{path}: no sample columns")
             offset = min(end + 1, len(text))
@@ -188,9 +188,9 @@ def read_vcf_genotypes_py(path, chunk_length=2000):
             if line.startswith("##"):
                 continue
             if line.startswith("#"):
-                samples = np.array(line.rstrip("\n").split("\t")[9:])
+                samples = np.array(line.rstrip("\r\n").split("\t")[9:])
                 continue
-            fields = line.rstrip("\n").split("\t")
+            fields = line.rstrip("\r\n").split("\t")
             fmt = fields[8].split(":")
             try:
                 gi = fmt.index("GT")
