@@ -196,7 +196,9 @@ int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:
- * ms[0]=h2d copies, [1]=ingest kernels, [2]=transpose, [3]=column reduce / gain init, [4]=select loop */
+ * ms[0]=h2d copies, [1]=ingest kernels, [2]=transpose, [3]=column reduce / gain init, [4]=select loop;
+ * parts of the select loop (host clock between stream synchronisations; the list build by its own CUDA events):
+ * [5]=head launches, [6]=hand-over (edge-list build; multi-GPU: merge over NVLink), [7]=list-driven tail */
 int utmos_timings(utmos_ctx *ctx, double *ms, int n, int reset);
 
 /* --lowmem NEW.hdf5 writer (utmos/select.py:198-231): chunk i of the 'data' dataset = rows [i*chunk_rows, +chunk_rows)

@@ -11,6 +11,12 @@ REF_FILES = os.path.join(GOLD, "ref", "test_files")
 REF_KEYS = os.path.join(GOLD, "ref", "answer_key")
 
 
+# Positions (in tests/golden/random_cases.json) of the recorded `--af` cases whose report differs from the unmodified
+# reference's: exactly these 13 of the 72 `--af` cases, each proven a near-tie of the reference's own float64 sums
+# (tests/test_oracle.py).  Pinned as a set: a 14th divergence, or one that disappears, fails the suite.
+NEAR_TIE_CASES = [16, 26, 71, 86, 128, 131, 143, 146, 166, 168, 171, 173, 178]
+
+
 def fixture(name):
     return os.path.join(REF_FILES, name)
 

@@ -308,9 +308,10 @@ class DeviceMatrix:
         return dict(zip(keys, (int(x) for x in arr)))
 
     def timings(self, reset=False):
-        arr = np.zeros(5, dtype=np.float64)
-        check(lib().utmos_timings(self._ctx, _ptr(arr), 5, 1 if reset else 0))
-        return dict(zip(["h2d_ms", "ingest_ms", "transpose_ms", "gain_ms", "select_ms"], (float(x) for x in arr)))
+        arr = np.zeros(8, dtype=np.float64)
+        check(lib().utmos_timings(self._ctx, _ptr(arr), 8, 1 if reset else 0))
+        return dict(zip(["h2d_ms", "ingest_ms", "transpose_ms", "gain_ms", "select_ms", "head_ms", "handover_ms",
+                         "tail_ms"], (float(x) for x in arr)))
 
     def close(self):
         if self._ctx is not None and self._ctx.value:

@@ -60,6 +60,8 @@ constexpr unsigned long long kListBudget = 1ull << 24;       // edge-list entrie
 constexpr unsigned long long kListBudgetWide = 1ull << 28;   // S > 65,535: the rare variants of a 100k-sample cohort alone
                                                              // hold more than 2^24 bits, and the head costs ~20-100 us per step
 enum { T_H2D = 0, T_INGEST = 1, T_TRANSPOSE = 2, T_GAIN = 3, T_SELECT = 4, T_COUNT = 5 };
+// parts of the select loop (host clock between stream synchronisations): head launches, hand-over to the lists, tail
+enum { P_HEAD = 0, P_HANDOVER = 1, P_TAIL = 2, P_COUNT = 3 };
 
 struct Pending {
     int cat;
@@ -161,6 +163,9 @@ struct utmos_ctx {
 
     int n_launch = 0;
     double ms[T_COUNT] = {0, 0, 0, 0, 0};
+    double part_ms[P_COUNT] = {0.0, 0.0, 0.0};
+    cudaEvent_t ev_handover[2] = {nullptr, nullptr};
+    bool handover_unread = false;
     std::vector<Pending> pending;
     size_t dev_bytes = 0;
 };
@@ -775,6 +780,7 @@ int utmos_destroy(utmos_ctx *c)
         big_free(c, c->d_stage[i], kStageBytes);
         if (c->d_af_stage[i]) cudaFreeAsync(c->d_af_stage[i], c->stream);
         if (c->h_af_stage[i]) cudaFreeHost(c->h_af_stage[i]);
+        if (c->ev_handover[i]) cudaEventDestroy(c->ev_handover[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
     }
@@ -1282,6 +1288,12 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             }
         }
         Trace tr("select_steps");
+        auto part_t0 = std::chrono::steady_clock::now();
+        auto part_lap = [&](int which) {
+            const auto now = std::chrono::steady_clock::now();
+            c->part_ms[which] += std::chrono::duration<double, std::milli>(now - part_t0).count();
+            part_t0 = now;
+        };
         while (true) {
             SelParams q = make_params(c, false);
             if (c->lists_valid) {
@@ -1333,6 +1345,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             UT_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
             UT_CUDA(cudaStreamSynchronize(c->stream));
             tr.lap(c->lists_valid ? "tail launch" : "head launches");
+            part_lap(c->lists_valid ? P_TAIL : P_HEAD);
             if (st.stop != 0 || st.step >= limit || st.abort_flag) break;
             if (tail_ok && !c->lists_valid && st.want_tail && st.live_bits <= list_budget) {
                 if (multi) {
@@ -1383,6 +1396,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                     st.mgpu_seq += 2;
                     UT_CUDA(cudaMemcpyAsync(&c->d_state->mgpu_seq, &st.mgpu_seq, sizeof(st.mgpu_seq), cudaMemcpyHostToDevice, c->stream));
                     UT_CUDA(cudaStreamSynchronize(c->stream));
+                    part_lap(P_HANDOVER);
                     SelState chk;
                     UT_CUDA(cudaMemcpy(&chk, c->d_state, sizeof(chk), cudaMemcpyDeviceToHost));
                     if (chk.abort_flag) { st.abort_flag = chk.abort_flag; break; }
@@ -1402,6 +1416,11 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                     continue;
                 }
                 // first compaction: edge lists from the bit matrix
+                if (!c->ev_handover[0]) {
+                    UT_CUDA(cudaEventCreate(&c->ev_handover[0]));
+                    UT_CUDA(cudaEventCreate(&c->ev_handover[1]));
+                }
+                UT_CUDA(cudaEventRecord(c->ev_handover[0], c->stream));
                 UT_TRY(reserve_lists(c->lists_cur, st.live_bits));
                 // pooled carrier lists are padded to 8 entries per row (rows with >= 7 carriers): <= 15/7 per live bit
                 const size_t pool_need = (size_t)mgpu_pool_share(st.live_bits);
@@ -1414,6 +1433,8 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 UT_TRY(launch_build_lists(c->stream, q, c->d_lists[c->lists_cur], c->d_list_off[c->lists_cur],
                                           c->d_list_len[c->lists_cur], c->d_cursor, c->d_pool, c->d_pool_cursor,
                                           &c->n_launch));
+                UT_CUDA(cudaEventRecord(c->ev_handover[1], c->stream));
+                c->handover_unread = true;
                 c->lists_total = st.live_bits;
                 c->lists_valid = true;
                 tr.lap("list allocation + build launch");
@@ -1433,6 +1454,14 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
     }
     t_end(c, c->stream);
     UT_TRY(sync_all(c));
+    if (c->ev_handover[0] && cudaEventQuery(c->ev_handover[1]) == cudaSuccess && c->handover_unread) {
+        float ho = 0.f;
+        if (cudaEventElapsedTime(&ho, c->ev_handover[0], c->ev_handover[1]) == cudaSuccess) {
+            c->part_ms[P_HANDOVER] += ho;          // it was lapped as part of the first tail launch
+            c->part_ms[P_TAIL] -= ho;
+        }
+        c->handover_unread = false;
+    }
     UT_CUDA(cudaMemcpy(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost));
     if (st.abort_flag) {
         set_error("select_steps: device watchdog tripped (grid barrier timeout)");
@@ -1632,9 +1661,12 @@ int utmos_info(utmos_ctx *c, int64_t *info, int n)
 int utmos_timings(utmos_ctx *c, double *ms, int n, int reset)
 {
     if (!c) { set_error("timings: null context"); return UTMOS_E_ARG; }
-    for (int i = 0; i < n && i < T_COUNT; ++i)
-        if (ms) ms[i] = c->ms[i];
-    if (reset) for (int i = 0; i < T_COUNT; ++i) c->ms[i] = 0.0;
+    for (int i = 0; i < n && i < T_COUNT + P_COUNT; ++i)
+        if (ms) ms[i] = i < T_COUNT ? c->ms[i] : c->part_ms[i - T_COUNT];
+    if (reset) {
+        for (int i = 0; i < T_COUNT; ++i) c->ms[i] = 0.0;
+        for (int i = 0; i < P_COUNT; ++i) c->part_ms[i] = 0.0;
+    }
     return UTMOS_OK;
 }
 
