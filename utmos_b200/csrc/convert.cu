@@ -130,6 +130,45 @@ __device__ __forceinline__ uint32_t gt_word(uint32_t v, RowAcc &a, unsigned int 
     return het_b | hom_b;
 }
 
+// 16 genotype bytes = 8 diploid samples -> one MSB-first presence byte (sample j of the piece = bit 7 - j).
+// Fast path: every allele of the piece is 0 or 1 (no missing call, no multi-allelic call) -- then presence = a0 | a1,
+// hom-alt = a0 & a1, and the allele counts follow from the two popcounts (ones = present + hom, called = 16):
+// ~11 integer instructions per 4 genotype bytes instead of ~33 for the byte-compare path (the video SIMD intrinsics
+// are emulated on sm_100a).  `valid` = samples of the piece that exist (8 except at the ragged end of a row).
+__device__ __forceinline__ uint32_t gt_piece(const uint4 &q, int valid, RowAcc &a, unsigned int *hist)
+{
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    if (valid >= 8 && ((q.x | q.y | q.z | q.w) & 0xfefefefeu) == 0u) {
+        uint32_t byte = 0u, homm = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = w[k], sh = v >> 8;
+            const uint32_t t = (v | sh) & 0x00010001u;          // bit 0: sample 2k present, bit 16: sample 2k+1 present
+            byte |= (t << (7 - 2 * k)) | (t >> (10 + 2 * k));
+            homm |= (v & sh & 0x00010001u) << k;
+        }
+        byte &= 0xffu;
+        const unsigned int present = __popc(byte), hom = __popc(homm);
+        a.an += 16u;
+        a.hom += hom;
+        a.het += present - hom;
+        a.one += present + hom;
+        a.zero += 16u - present - hom;
+        return byte;
+    }
+    uint32_t byte = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t v = w[k];
+        if (2 * k >= valid) v = 0xffffffffu;                     // past the row (last group): missing
+        else if (2 * k + 1 >= valid) v |= 0xffff0000u;
+        const uint32_t pr = gt_word(v, a, hist);
+        byte |= ((pr >> 7) & 1u) << (7 - 2 * k);
+        byte |= ((pr >> 23) & 1u) << (6 - 2 * k);
+    }
+    return byte;
+}
+
 // warp-level end of a row: reduce the counters, AF = max alt-allele count / called alleles, singleton flag
 __device__ __forceinline__ void gt_row_finish(RowAcc acc, unsigned int *hist, int lane, long long r, double *af,
                                               uint8_t *singleton, unsigned long long &het_tot, unsigned long long &hom_tot)
@@ -182,19 +221,7 @@ __global__ void __launch_bounds__(256) gt_pack_af_direct_kernel(const int8_t *__
 #pragma unroll 2
         for (int g = lane; g < groups; g += 32) {
             const uint4 q = ld_stream_u128(row + g);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            const int s0 = g * 8;
-            uint32_t byte = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t v = w[k];
-                if (s0 + 2 * k >= S) v = 0xffffffffu;                     // past the row (last group): missing
-                else if (s0 + 2 * k + 1 >= S) v |= 0xffff0000u;
-                const uint32_t pr = gt_word(v, acc, s_hist[warp]);
-                byte |= ((pr >> 7) & 1u) << (7 - 2 * k);
-                byte |= ((pr >> 23) & 1u) << (6 - 2 * k);
-            }
-            out[g] = (uint8_t)byte;
+            out[g] = (uint8_t)gt_piece(q, S - g * 8, acc, s_hist[warp]);
         }
         gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, het_tot, hom_tot);
     }
@@ -267,18 +294,12 @@ __global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const i
             uint8_t *out = packed + r * pitch;
             RowAcc acc = {0u, 0u, 0u, 0u, 0u, false};
             for (int s0 = lane * 8; s0 < S; s0 += 256) {
-                uint32_t byte = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // word k = samples s0+2k (bytes 0,1) and s0+2k+1 (bytes 2,3)
-                    uint32_t v = cvt_le32(s32, o + 2u * s0 + 4u * k);
-                    if (s0 + 2 * k >= S) v = 0xffffffffu;                     // past the row: missing
-                    else if (s0 + 2 * k + 1 >= S) v |= 0xffff0000u;
-                    const uint32_t pr = gt_word(v, acc, s_hist[warp]);
-                    byte |= ((pr >> 7) & 1u) << (7 - 2 * k);
-                    byte |= ((pr >> 23) & 1u) << (6 - 2 * k);
-                }
-                out[s0 >> 3] = (uint8_t)byte;
+                // word k = samples s0+2k (bytes 0,1) and s0+2k+1 (bytes 2,3); five aligned words + funnel shifts
+                const unsigned int ob = o + 2u * s0, wa = ob >> 2, fs = (ob & 3u) * 8u;
+                const uint32_t r0 = s32[wa], r1 = s32[wa + 1], r2 = s32[wa + 2], r3 = s32[wa + 3], r4 = s32[wa + 4];
+                const uint4 q = make_uint4(__funnelshift_r(r0, r1, fs), __funnelshift_r(r1, r2, fs), __funnelshift_r(r2, r3, fs),
+                                           __funnelshift_r(r3, r4, fs));
+                out[s0 >> 3] = (uint8_t)gt_piece(q, S - s0, acc, s_hist[warp]);
             }
             gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, het_tot, hom_tot);
         }

@@ -218,6 +218,43 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
+// ---- TMA (1-D bulk copy) + mbarrier, raw PTX.  One thread arms the barrier with the byte count and issues the copies;
+// everybody waits on the barrier's phase.  The staged tile is ONE contiguous byte run of the input whatever the row pitch.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count)
+{
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned int bytes, unsigned long long *bar)
+{
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    const unsigned int b = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+    const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(a), "r"(parity) : "memory");
+}
+
 // little-endian 4 bytes at byte offset o of the staged tile (any alignment)
 __device__ __forceinline__ uint32_t smem_le32(const uint32_t *s32, unsigned int o)
 {
@@ -242,6 +279,9 @@ __device__ __forceinline__ uint32_t smem_bytes_any(const uint32_t *s32, unsigned
 // pieces are nonzero in a bitmap, one thread per row then tests the bitmap bits of the pieces that lie wholly
 // inside its row and the few bytes it shares with its neighbours; the store loop splits its unit index without
 // an integer division; the look-back can read kLook tiles per lane and round trip (window = 32 * kLook tiles).
+// FLAVOUR 3: the tile is staged by the TMA (cp.async.bulk, one elected thread, mbarrier complete_tx) instead of
+// LDG + STS in every thread, the nonzero-piece bitmap is then read back from shared memory, and the look-back reads
+// 256 tile states per round trip (every warp of the CTA takes a window of 32) instead of 32.
 template <int FLAVOUR>
 __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *__restrict__ raw, long long n_rows,
                                                                  long long pitch_in, const double *__restrict__ af_in,
@@ -256,7 +296,11 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
     __shared__ unsigned short s_src[kFastMaxRows];
     __shared__ uint8_t s_flag[kFastMaxRows];
     __shared__ uint32_t s_nz[(kFastSmemRaw + 64) / 16 / 32 + 10];      // FLAVOUR 1: bit i = staged piece i is nonzero
+    __shared__ __align__(8) unsigned long long s_mbar;                 // FLAVOUR 3
+    __shared__ unsigned long long s_lb_sum[kThreads / 32];
+    __shared__ unsigned int s_lb_has[kThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (FLAVOUR == 3 && tid == 0) mbar_init(&s_mbar, 1u);
     if (tid == 0) s_tile = (unsigned int)atomicAdd(state, 1ull);
     __syncthreads();
     const long long tile = s_tile;
@@ -303,7 +347,39 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
         const uint4 *g16 = reinterpret_cast<const uint4 *>(raw + a0);
         const int n_in = (int)min((long long)n16, (total_bytes - a0) >> 4);     // pieces that lie wholly inside the input
         const int n_iter = (n16 + 2 + kThreads - 1) / kThreads * kThreads;      // whole warps: the ballot needs every lane
-        if (FLAVOUR == 2) {
+        if (FLAVOUR == 3) {
+            // n_in whole pieces come from the TMA; the ragged last piece of the input (and the two zero pieces behind the
+            // tile) are written by ordinary stores to OTHER addresses
+            if (tid == 0 && n_in > 0) {
+                mbar_expect_tx(&s_mbar, (unsigned int)n_in * 16u);
+                for (int c0 = 0; c0 < n_in; c0 += 1024) {                       // copies of at most 16 KB
+                    const int n = min(1024, n_in - c0);
+                    bulk_load(s16 + c0, g16 + c0, (unsigned int)n * 16u, &s_mbar);
+                }
+            }
+            for (int i = n_in + tid; i < n16 + 2; i += kThreads) {
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (i < n16) {
+                    const long long off = a0 + 16ll * i;
+                    unsigned long long lo = 0ull, hi = 0ull;
+                    for (int b = 0; b < 16 && off + b < total_bytes; ++b) {
+                        const unsigned long long y = __ldg(raw + off + b);
+                        if (b < 8) lo |= y << (8 * b);
+                        else hi |= y << (8 * (b - 8));
+                    }
+                    x = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+                }
+                s16[i] = x;
+            }
+            __syncthreads();                                                    // ragged pieces visible, barrier initialised
+            if (n_in > 0) mbar_wait(&s_mbar, 0u);
+            for (int i = tid; i < n_iter; i += kThreads) {
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (i < n16 + 2) x = s16[i];
+                const uint32_t nz = __ballot_sync(0xffffffffu, (x.x | x.y | x.z | x.w) != 0u);
+                if (lane == 0 && i < n16 + 2) s_nz[i >> 5] = nz;
+            }
+        } else if (FLAVOUR == 2) {
             // opt-in: kLoadBatch loads of a thread are issued before the first of them is used.  In FLAVOUR 1 the vote
             // on the loaded piece sits in the load loop, so every trip waits for its own load (SASS: one LDG.128 and
             // one VOTE per trip) -- seven dependent DRAM round trips per tile.

@@ -401,6 +401,59 @@ __global__ void __launch_bounds__(256) cover_decrement_kernel(SelParams p, const
     }
 }
 
+// K3, AF limbs (sample-major source): gain_lo/hi[s] = sum of q_lo/hi[r] over the live rows r that carry s
+// (the step-0 scores of utmos/select.py:37-40 with data = GT * AF, :317-320, as exact fixed-point integers).
+// CTA = (tile of kAfRows rows) x (group of kAfSamples samples).  The limbs of the tile's rows are staged in shared
+// memory ONCE (16 bytes per row) instead of being gathered from L2 once per set bit; a thread then takes whole
+// samples: it reads the sample's 256 contiguous bytes of the tile with 128-bit loads and adds the staged limbs of its
+// set bits into registers.  One pair of 64-bit atomics per (sample, tile).  Algorithmic bytes: V'*pitch + 16*V'.
+constexpr int kAfRows = 2048;
+constexpr int kAfWords = kAfRows / 32;
+constexpr int kAfSamples = 512;
+
+__global__ void __launch_bounds__(256) col_af_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ live,
+                                                     const unsigned long long *__restrict__ q_lo,
+                                                     const unsigned long long *__restrict__ q_hi, long long colPitchW,
+                                                     long long V, int S, unsigned long long *gain_lo,
+                                                     unsigned long long *gain_hi)
+{
+    __shared__ ulonglong2 s_q[kAfRows];
+    __shared__ uint32_t s_live[kAfWords];
+    const long long w0 = (long long)blockIdx.x * kAfWords;
+    const long long r0 = w0 * 32;
+    for (int i = threadIdx.x; i < kAfRows; i += blockDim.x) {
+        const long long r = r0 + i;
+        s_q[i] = r < V ? make_ulonglong2(__ldg(q_lo + r), __ldg(q_hi + r)) : make_ulonglong2(0ull, 0ull);
+    }
+    if (threadIdx.x < kAfWords) s_live[threadIdx.x] = w0 + threadIdx.x < colPitchW ? __ldg(live + w0 + threadIdx.x) : 0u;
+    __syncthreads();
+    const int s_end = min(S, (int)(blockIdx.y + 1) * kAfSamples);
+    for (int s = (int)blockIdx.y * kAfSamples + threadIdx.x; s < s_end; s += blockDim.x) {
+        const uint4 *col = reinterpret_cast<const uint4 *>(cols + (long long)s * colPitchW + w0);
+        unsigned long long lo = 0ull, hi = 0ull;
+#pragma unroll 4
+        for (int j = 0; j < kAfWords / 4; ++j) {
+            if (w0 + 4 * j >= colPitchW) break;                 // colPitchW is a multiple of 8 words
+            const uint4 c = ld_stream_u128(col + j);
+            const uint32_t w[4] = {c.x & s_live[4 * j], c.y & s_live[4 * j + 1], c.z & s_live[4 * j + 2], c.w & s_live[4 * j + 3]};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t x = w[k];
+                while (x) {
+                    const ulonglong2 q = s_q[(4 * j + k) * 32 + (__ffs(x) - 1)];
+                    x &= x - 1;
+                    lo += q.x;
+                    hi += q.y;
+                }
+            }
+        }
+        if (lo | hi) {
+            atomicAdd(gain_lo + s, lo);
+            atomicAdd(gain_hi + s, hi);
+        }
+    }
+}
+
 // K3 (variant-major source): one warp per row, one reduction per set bit.
 //   WHAT bit 0: var_count over all rows, bit 1: gain_cnt over live rows, bit 2: AF limbs over live rows
 __global__ void __launch_bounds__(256) row_gain_kernel(SelParams p, unsigned int *var_count, int what)
@@ -1363,7 +1416,13 @@ int launch_gain_init(cudaStream_t stream, const SelParams &p, unsigned int *var_
     } else {
         what |= 1 | 2;
     }
-    if (p.af) what |= 4;
+    if (p.af && p.cols) {
+        const dim3 grid((unsigned)((p.colPitchW + kAfWords - 1) / kAfWords), (unsigned)((p.S + kAfSamples - 1) / kAfSamples));
+        col_af_kernel<<<grid, 256, 0, stream>>>(p.cols, p.live, p.q_lo, p.q_hi, p.colPitchW, p.V, p.S, p.gain_lo, p.gain_hi);
+        *n_launch += 1;
+    } else if (p.af) {
+        what |= 4;
+    }
     if (what) {
         const long long warps_needed = p.V;
         long long blocks = (warps_needed + 7) / 8;
