@@ -405,8 +405,7 @@ def main():
     achieved = sel_bytes / 1e9 / (phases["select_ms"] / 1e3) if phases["select_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": ["argmax_step_kernel+cover_step_kernel", "select_persistent_kernel", "select_cluster_kernel",
                            "select_tail_kernel (head: select_cluster_kernel + cover_decrement_kernel)", "select_mgpu_kernel",
-                           "select_tail_kernel replicated on every rank (head: select_mgpu_kernel, hand-over: build_edges_kernel over NVLink)",
-                           "select_lazy_kernel (lazy greedy over per-sample row lists; lists: build_rowlists_kernel)"][info["flavour"]],
+                           "select_tail_kernel replicated on every rank (head: select_mgpu_kernel, hand-over: build_edges_kernel over NVLink)"][info["flavour"]],
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_from_ncu() if world == 1 and n_vars == N_VARS and not with_af else None, "algorithmic_bytes": sel_bytes, "kernel_ms": phases["select_ms"],
                 "note": "latency-bound: %d dependent greedy steps, %.2f us per step; achieved = algorithmic bytes of the whole greedy loop "

@@ -52,7 +52,6 @@ typedef struct utmos_ctx utmos_ctx;
 #define UTMOS_F_FORCE_TRANSPOSE 4u   /* fail instead of falling back when the sample-major copy does not fit */
 #define UTMOS_F_NO_CLUSTER 8u        /* grid-wide persistent kernel instead of the one-cluster DSMEM kernel */
 #define UTMOS_F_NO_TAIL 16u          /* never switch to the single-CTA list-driven tail kernel */
-#define UTMOS_F_NO_LAZY 64u          /* never use the lazy-greedy kernel (lazy.cu): keep the list-driven tail of tail.cu */
 #define UTMOS_F_DSMEM_GAINS 32u      /* cluster kernel keeps the gains in distributed shared memory (default: L2 atomics) */
 
 /* stop reasons reported by utmos_select_steps (utmos/select.py:91, :51-52/:93-96, :110-112) */
@@ -140,6 +139,15 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
                      uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
                      uint8_t *singleton_out);
 
+/* The same with flags.  UTMOS_CVT_DROP_SINGLETONS (`utmos convert --no-singleton`, utmos/convert.py:58-62): rows with
+ * singleton_out[v] == 1 are left out of num_het / num_hom, as the reference drops them before it computes presence and
+ * stats; their packed row and AF are still written (the caller compacts the rows by the flags).  One kernel launch per
+ * block either way. */
+#define UTMOS_CVT_DROP_SINGLETONS 1
+int utmos_convert_gt_ex(int device, const int8_t *gt, int64_t n_vars, int64_t n_samples, int64_t ploidy,
+                        uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
+                        uint8_t *singleton_out, int flags);
+
 /* CUDA-event milliseconds the K1 kernel launches of the last utmos_convert_gt call took (copies excluded). */
 int utmos_convert_kernel_ms(double *ms_out);
 
@@ -185,10 +193,6 @@ int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
 #define UTMOS_OPT_GLOBAL_ROWS 4       /* multi-GPU: informative rows summed over all ranks; set before utmos_finalize */
 #define UTMOS_OPT_STEP_TIMES 2        /* 1: record %globaltimer per pick for utmos_debug_step_times (adds latency) */
 #define UTMOS_OPT_TAIL_ROWS 3         /* hand over to the list-driven tail kernel once a pick covers fewer rows (default 2048) */
-#define UTMOS_OPT_LAZY_ROWS 6         /* hand over to the lazy-greedy kernel once a pick covers fewer rows (default -1: from the first pick) */
-#define UTMOS_OPT_LAZY_G1 7           /* lazy kernel: longest row list one warp evaluates alone (default 1024) */
-#define UTMOS_OPT_LAZY_G4 8           /* ... a group of four warps evaluates (default 16384); longer lists take the whole CTA */
-#define UTMOS_OPT_LAZY_SLACK 9        /* ... candidates within (best bound >> value) of the best bound share a round (default 5) */
 #define UTMOS_OPT_TAIL_SINGLE_ROWS 5  /* tail kernel: 8-CTA owner-computes cluster until a pick covers fewer rows
                                          (default 0 = single CTA only) */
 int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
@@ -197,7 +201,7 @@ int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
  * [4]=fixed-point scale (AF flavours), [5]=AF values not exactly representable (count), [6]=kernels launched,
  * [7]=selection kernel flavour used: 0 step kernels, 1 grid-wide persistent, 2 one-cluster DSMEM,
  *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2), 4 multi-GPU kernel (per-step exchange),
- *   5 multi-GPU head followed by the replicated tail, 6 lazy-greedy kernel (lazy.cu) */
+ *   5 multi-GPU head followed by the replicated tail */
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:

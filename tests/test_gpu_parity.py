@@ -17,8 +17,7 @@ from utmos_b200 import convert as ucvt
 pytestmark = pytest.mark.gpu
 
 MODES = {
-    "lazy": 0,
-    "tail": _native.F_NO_LAZY,
+    "tail": 0,
     "tail_persistent_head": _native.F_NO_CLUSTER,
     "cluster": _native.F_NO_TAIL,
     "cluster_dsmem": _native.F_NO_TAIL | _native.F_DSMEM_GAINS,
@@ -369,7 +368,7 @@ def test_tail_flavours_vs_c_oracle(use_af, weighted, single_rows, tail_rows):
     wts = synth.synthetic_weights(n_samples) if weighted else None
     mask = np.ones(n_samples, np.uint8)
     mask[5::89] = 2
-    dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE, flags=_native.F_NO_LAZY)
+    dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE)
     dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
     dm.finalize()
     dm.set_option(3, tail_rows)
@@ -382,84 +381,6 @@ def test_tail_flavours_vs_c_oracle(use_af, weighted, single_rows, tail_rows):
     o_idx, o_new, o_score = _tail_case_oracle(use_af, weighted)
     assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
     dm.close()
-    coh.close()
-
-
-@pytest.mark.parametrize("use_af", [False, True], ids=["count", "af"])
-@pytest.mark.parametrize("weighted", [False, True], ids=["plain", "weights"])
-@pytest.mark.parametrize("lazy_rows,g1,g4,slack", [(-1, 1024, 16384, 5), (-1, 32, 16384, 5), (-1, 32, 32, 5), (-1, 64, 256, 0),
-                                                   (-1, 1024, 16384, 31), (512, 1024, 16384, 5), (64, 32, 128, 3)],
-                         ids=["from_step0", "four_warp_groups", "whole_cta_groups", "mixed_groups_wide_rounds",
-                              "one_candidate_rounds", "head_then_lazy", "late_hand_over_small_groups"])
-def test_lazy_kernel_vs_c_oracle(use_af, weighted, lazy_rows, g1, g4, slack):
-    """select_lazy_kernel (lazy.cu): every evaluation flavour (one warp / four warps / the whole CTA per candidate), wide and
-    narrow rounds, hand-over from the head kernels at different points, two batches of steps (resume with stale bounds),
-    count / --weights / --af / both, exclusions -- against the exact oracle, scores included."""
-    n_vars, n_samples = 30000, 1777
-    coh = synth.DeviceCohort(3, n_vars, n_samples)
-    wts = synth.synthetic_weights(n_samples) if weighted else None
-    mask = np.ones(n_samples, np.uint8)
-    mask[5::89] = 2
-    dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE)
-    dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
-    dm.finalize()
-    dm.set_option(6, lazy_rows)
-    dm.set_option(7, g1)
-    dm.set_option(8, g4)
-    dm.set_option(9, slack)
-    dm.begin(mask, wts)
-    i1, n1, s1, _ = dm.steps(150)
-    i2, n2, s2, _ = dm.steps(n_samples)
-    idx, new, score = np.concatenate([i1, i2]), np.concatenate([n1, n2]), np.concatenate([s1, s2])
-    assert dm.info()["flavour"] == 6
-    o_idx, o_new, o_score = _tail_case_oracle(use_af, weighted)
-    assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)
-    dm.close()
-    coh.close()
-
-
-def test_lazy_kernel_zero_weights_and_negative_weight_fallback():
-    """Zero weights are fine for the lazy kernel (upper bounds of the gain stay upper bounds of the score); one negative
-    weight sends the selection to the list-driven tail instead.  Both against the oracle (utmos/select.py:43-52)."""
-    n_vars, n_samples = 20000, 777
-    coh = synth.DeviceCohort(9, n_vars, n_samples)
-    gt, _af = coh.to_host()
-    mask = np.ones(n_samples, np.uint8)
-    for negative in (False, True):
-        wts = np.ones(n_samples)
-        wts[::3] = 0.0
-        wts[1::7] = 2.5
-        if negative:
-            wts[4] = -1.0
-        dm = _native.DeviceMatrix(n_samples, _native.AF_NONE)
-        dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, 0)
-        dm.finalize()
-        dm.begin(mask, wts)
-        idx, new, score, stop = dm.steps(n_samples)
-        assert dm.info()["flavour"] == (3 if negative else 6)
-        dm.close()
-        o_idx, o_new, o_score, o_stop = orc.greedy_c(gt, n_samples, mask, wts, None, n_samples, exact=True)
-        assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score) and stop == o_stop
-    coh.close()
-
-
-def test_lazy_kernel_live_mask_in_global_memory():
-    """More rows than the shared-memory live mask holds (> ~1.7 M): the kernel works on the global copy in place."""
-    n_vars, n_samples = 2_000_000, 64
-    coh = synth.DeviceCohort(21, n_vars, n_samples)
-    gt, af = coh.to_host()
-    mask = np.ones(n_samples, np.uint8)
-    mask[3] = 2
-    for use_af in (False, True):
-        dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE, rows_hint=n_vars)
-        dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
-        dm.finalize()
-        dm.begin(mask)
-        idx, new, score, stop = dm.steps(n_samples)
-        assert dm.info()["flavour"] == 6
-        dm.close()
-        o_idx, o_new, o_score, o_stop = orc.greedy_c(gt, n_samples, mask, None, af if use_af else None, n_samples, exact=True)
-        assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score) and stop == o_stop
     coh.close()
 
 
@@ -513,7 +434,7 @@ def test_hand_over_without_gain_recompute_on_a_large_input():
     n_vars, n_samples = 250_000, 2504
     coh = synth.DeviceCohort(2, n_vars, n_samples)
     results = []
-    for regain, flags in ((-1, _native.F_NO_LAZY), (0, _native.F_NO_LAZY), (0, _native.F_NO_TRANSPOSE)):
+    for regain, flags in ((-1, 0), (0, 0), (0, _native.F_NO_TRANSPOSE)):
         dm = _native.DeviceMatrix(n_samples, _native.AF_NONE, rows_hint=n_vars, flags=flags)
         dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, 0)
         vc = dm.finalize()
@@ -620,6 +541,23 @@ def test_read_vcf_reproduces_fixture_jl(name):
     assert data["stats"] == gold["stats"]
     assert list(data["samples"]) == list(np.asarray(gold["samples"]).astype(str))
     assert data["AF"].shape == (1000, 1)
+
+
+@pytest.mark.parametrize("no_singleton", [False, True], ids=["all_rows", "no_singleton"])
+def test_read_vcf_hand_built_rows(tmp_path, no_singleton):
+    """K1 on missing / half-missing / haploid / AN = 0 / multi-allelic rows against answers worked out from scikit-allel's
+    definitions (tests/helpers.py HAND_VCF_ROWS; utmos/convert.py:57-77), with and without --no-singleton (:58-62)."""
+    path = tmp_path / "hand.vcf"
+    path.write_text(H.HAND_VCF_HEAD + "\n".join(r[0] for r in H.HAND_VCF_ROWS) + "\n")
+    data = ucvt.read_vcf(str(path), False, 3, no_singleton=no_singleton)       # blocks of 3 rows
+    rows = [r for r in H.HAND_VCF_ROWS if not (no_singleton and r[5])]
+    assert list(data["samples"]) == ["A", "B", "C", "D"]
+    assert data["GT"].shape == (len(rows), 1) and data["AF"].shape == (len(rows), 1)
+    bits = np.unpackbits(data["GT"], axis=1, count=4)
+    for i, (_line, presence, af, _het, _hom, _single) in enumerate(rows):
+        assert list(bits[i]) == presence, i
+        assert (np.isnan(data["AF"][i, 0]) and np.isnan(af)) or data["AF"][i, 0] == af, i
+    assert data["stats"] == {"num_het": sum(r[3] for r in rows), "num_hom": sum(r[4] for r in rows)}
 
 
 def test_read_vcf_no_singleton_matches_oracle():

@@ -222,6 +222,24 @@ def test_convert_oracle_edge_genotypes():
     assert np.isnan(empty["AF"][0, 0])
 
 
+def test_convert_oracle_and_vcf_parser_on_hand_built_rows(tmp_path):
+    """Missing, half-missing, haploid, AN = 0 and multi-allelic rows (none of them in the reference's fixtures): the host VCF
+    parsers and the convert oracle against answers worked out from scikit-allel's definitions (tests/helpers.py)."""
+    path = tmp_path / "hand.vcf"
+    path.write_text(H.HAND_VCF_HEAD + "\n".join(r[0] for r in H.HAND_VCF_ROWS) + "\n")
+    for reader in (vcf.read_vcf_genotypes_py, vcf.read_vcf_genotypes):
+        blocks = list(reader(str(path), 100))
+        assert list(blocks[0][0]) == ["A", "B", "C", "D"]
+        gts = np.concatenate([b[1] for b in blocks])
+        out = orc.convert_gt_c(gts)
+        bits = np.unpackbits(out["GT"], axis=1, count=4)
+        for i, (_line, presence, af, _het, _hom, single) in enumerate(H.HAND_VCF_ROWS):
+            assert list(bits[i]) == presence, i
+            assert (np.isnan(out["AF"][i, 0]) and np.isnan(af)) or out["AF"][i, 0] == af, i
+            assert bool(out["singleton"][i]) == single, i
+        assert out["stats"] == {"num_het": sum(r[3] for r in H.HAND_VCF_ROWS), "num_hom": sum(r[4] for r in H.HAND_VCF_ROWS)}
+
+
 def test_count_resolution_and_sample_lists(tmp_path):
     assert usel.resolve_select_count(-1, 2504) == 2504
     assert usel.resolve_select_count(0.02, 2504) == 50
@@ -294,6 +312,57 @@ def test_h5writer_roundtrip_bool_float_and_multilevel_btree(tmp_path):
         assert h5["data"].chunks == (4, n_samples) and h5["data"].shape == full.shape
         assert len(h5["data"]._chunk_index()) == (full.shape[0] + 3) // 4 > 64
         assert np.array_equal(h5["data"].read(), full)
+
+
+@pytest.mark.parametrize("name", ["tiny.hdf5", "tiny.af.hdf5"])
+@pytest.mark.parametrize("path_kind", ["dense", "packed"])
+def test_h5writer_structure_equals_h5py_fixture(tmp_path, name, path_kind):
+    """utmos/select.py:198-238 / utmos_ssshtests.sh:197-235: a file written by H5Writer for the content of the reference's
+    h5py-written fixture has the same structure message by message -- superblock fields, group entries, and for every
+    dataset the object-header messages in order with their flags, dataspace (dims, max dims), datatype (class, bit
+    fields, size, properties), fill value, filter pipeline (LZF id, name, flags, client values), layout (chunk dims) and
+    the chunk offsets / filter masks -- and every B-tree / heap / header invariant of the format holds (tests/h5struct.py,
+    an independent strict reader).  Only addresses and compressed chunk sizes may differ.  h5py itself is not
+    installed here; this is the closest statement available that stock h5py / the reference can re-read the file."""
+    from tests import h5struct
+    ref = h5struct.File(H.fixture(name))
+    with h5lite.H5File(H.fixture(name)) as h5:
+        data, samples, vc = h5["data"].read(), h5["samples"].read(), h5["var_count"].read()
+    out = str(tmp_path / "w.hdf5")
+    is_float = data.dtype != bool
+    w = h5lite.H5Writer(out, samples, float_data=is_float)
+    if path_kind == "dense":
+        w.append_dense(data[:100])
+        w.append_dense(data[100:])
+    else:                                                  # from packed .jl rows + AF, the way load_files feeds it
+        af = data.max(axis=1).astype(np.float64) if is_float else None
+        packed = np.packbits(data != 0, axis=1)
+        w.append_packed(packed[:150], None if af is None else af[:150])
+        w.append_packed(packed[150:], None if af is None else af[150:])
+    w.close(vc)
+    ours = h5struct.File(out)
+    assert h5struct.comparable(ours) == h5struct.comparable(ref)
+    with h5lite.H5File(out) as h5:                          # and the content reads back bit for bit
+        assert np.array_equal(h5["data"].read(), data) and h5["data"].dtype == data.dtype
+        assert np.array_equal(h5["samples"].read(), samples) and np.array_equal(h5["var_count"].read(), vc)
+
+
+def test_h5struct_rejects_broken_files(tmp_path):
+    """The strict reader really checks: a wrong end-of-file address, a broken sibling pointer and an unsorted key fail."""
+    from tests import h5struct
+    blob = bytearray(open(H.fixture("tiny.hdf5"), "rb").read())
+    bad = bytearray(blob)
+    bad[40:48] = (len(blob) + 8).to_bytes(8, "little")             # end-of-file address
+    (tmp_path / "a.hdf5").write_bytes(bad)
+    with pytest.raises(h5struct.Bad):
+        h5struct.File(str(tmp_path / "a.hdf5"))
+    ref = h5struct.File(H.fixture("tiny.hdf5"))
+    root = ref.datasets["data"]["layout"]["btree"]
+    bad = bytearray(blob)
+    bad[root + 8:root + 16] = (1234).to_bytes(8, "little")         # left sibling of the root must be undefined
+    (tmp_path / "b.hdf5").write_bytes(bad)
+    with pytest.raises(h5struct.Bad):
+        h5struct.File(str(tmp_path / "b.hdf5"))
 
 
 def test_h5writer_native_chunk_encoder_matches_numpy_path(tmp_path):

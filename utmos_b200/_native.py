@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libutmos_b200.so")
 
 AF_NONE, AF_F64, AF_F32 = 0, 1, 2
-F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL, F_DSMEM_GAINS, F_NO_LAZY = 1, 2, 4, 8, 16, 32, 64
+F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL, F_DSMEM_GAINS = 1, 2, 4, 8, 16, 32
 STOP_NONE, STOP_ZERO, STOP_ALL = 0, 1, 2
 E_NOGPU = -3
 
@@ -20,7 +20,7 @@ E_NOGPU = -3
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_append_h5_chunks", "utmos_finalize", "utmos_select_begin",
-           "utmos_select_steps", "utmos_convert_gt", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
+           "utmos_select_steps", "utmos_convert_gt", "utmos_convert_gt_ex", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
            "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_h5_encode_chunks", "utmos_gz_size", "utmos_gz_inflate", "utmos_vcf_parse_gt", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
@@ -65,6 +65,7 @@ def lib():
         "utmos_select_begin": (i32, [p, p, p]),
         "utmos_select_steps": (i32, [p, i64, p, p, p, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
         "utmos_convert_gt": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p]),
+        "utmos_convert_gt_ex": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p, i32]),
         "utmos_convert_kernel_ms": (i32, [ctypes.POINTER(ctypes.c_double)]),
         "utmos_debug_gains": (i32, [p, p, p]),
         "utmos_info": (i32, [p, p, i32]),
@@ -325,9 +326,13 @@ class DeviceMatrix:
             pass
 
 
-def convert_gt(gt, device=0):
+CVT_DROP_SINGLETONS = 1
+
+
+def convert_gt(gt, device=0, drop_singletons=False):
     """utmos/convert.py:57-87 on the GPU.  gt: int8 [V, S, ploidy].  Returns (packed, af(V,1), num_het, num_hom,
-    singleton flags)."""
+    singleton flags).  ``drop_singletons`` (--no-singleton, convert.py:58-62): the het / hom totals leave the flagged
+    rows out; the caller drops their packed rows and AF (one kernel launch instead of two)."""
     gt = np.ascontiguousarray(gt, dtype=np.int8)
     if gt.ndim != 3:
         raise ValueError("GT tensor must be [variants, samples, ploidy]")
@@ -337,8 +342,9 @@ def convert_gt(gt, device=0):
     single = np.zeros(n_vars, dtype=np.uint8)
     het = ctypes.c_int64(0)
     hom = ctypes.c_int64(0)
-    check(lib().utmos_convert_gt(device, _ptr(gt), n_vars, n_samples, ploidy, _ptr(packed), _ptr(af),
-                                 ctypes.byref(het), ctypes.byref(hom), _ptr(single)))
+    check(lib().utmos_convert_gt_ex(device, _ptr(gt), n_vars, n_samples, ploidy, _ptr(packed), _ptr(af),
+                                    ctypes.byref(het), ctypes.byref(hom), _ptr(single),
+                                    CVT_DROP_SINGLETONS if drop_singletons else 0))
     return packed, af.reshape(-1, 1), het.value, hom.value, single.astype(bool)
 
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libutmos_b200.so")
-SOURCES = ["api.cu", "ingest.cu", "select.cu", "tail.cu", "lazy.cu", "mgpu.cu", "convert.cu", "hostio.cu", "vcfio.cu", "synth.cu"]
+SOURCES = ["api.cu", "ingest.cu", "select.cu", "tail.cu", "mgpu.cu", "convert.cu", "hostio.cu", "vcfio.cu", "synth.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "utmos_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

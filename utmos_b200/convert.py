@@ -56,16 +56,12 @@ def read_vcf(in_file, lowmem=False, chunk_length=2000, no_singleton=False, devic
     for samples, gts in read_vcf_genotypes(in_file, chunk_length):
         if gts.shape[0] == 0:
             continue
-        packed, af, het, hom, single = _native.convert_gt(gts, device)
-        if no_singleton:
-            # utmos/convert.py:58-62 drops singleton rows BEFORE presence / stats / AF are computed
+        # utmos/convert.py:58-62 drops singleton rows BEFORE presence / stats / AF are computed: presence and AF are per row,
+        # so the kernel only has to leave those rows out of the het / hom totals; their rows are compacted away here
+        packed, af, het, hom, single = _native.convert_gt(gts, device, drop_singletons=no_singleton)
+        if no_singleton and single.any():
             removed += int(single.sum())
-            keep = ~single
-            if not keep.all():
-                if keep.any():
-                    packed, af, het, hom, _ = _native.convert_gt(gts[keep], device)
-                else:
-                    packed, af, het, hom = packed[:0], af[:0], 0, 0
+            packed, af = packed[~single], af[~single]
         num_hets += het
         num_homs += hom
         packed_parts.append(packed)

@@ -108,6 +108,7 @@ struct utmos_ctx {
     unsigned long long *d_gain_lo = nullptr, *d_gain_hi = nullptr, *d_gain0_lo = nullptr, *d_gain0_hi = nullptr;
     unsigned long long *d_q_lo = nullptr, *d_q_hi = nullptr;
     uint8_t *d_mask = nullptr;
+    uint32_t *d_selw = nullptr;        // bitmask of the samples that were selectable at select_begin
     double *d_weights = nullptr;
     bool has_weights = false;
     long long *d_out_idx = nullptr, *d_out_new = nullptr;
@@ -122,13 +123,6 @@ struct utmos_ctx {
     int lists_cur = 0;
     unsigned long long lists_total = 0;   // entries in the current lists (live bits when they were built)
     bool lists_valid = false;
-    // lazy-greedy tail (lazy.cu): per-sample row lists live in d_lists[0] (as uint32), offsets / lengths in d_list_off[0] / d_list_len[0]
-    bool lazy_valid = false;           // the row lists are built: select_lazy_kernel runs every remaining step
-    bool lazy_fresh = false;           // ... and nothing was picked since (every bound is exact)
-    bool lazy_allowed = false;         // decided per selection (single GPU, sample-major copy, weights >= 0, state fits one SM)
-    bool weights_nonneg = true;
-    unsigned int lazy_rows = 0xffffffffu;   // hand over to the lazy kernel once a pick covers fewer rows (default: from step 0)
-    int lazy_tune[3] = {1024, 16384, 5};    // UTMOS_OPT_LAZY_G1 / _G4 / _SLACK (see launch_lazy)
     int dbg_time = 0;
     // multi-GPU (rows sharded over ranks)
     int mg_rank = 0, mg_world = 1;
@@ -474,6 +468,7 @@ void free_select_state(utmos_ctx *c)
     dev_free(c, c->d_q_lo, (size_t)c->V * 8);
     dev_free(c, c->d_q_hi, (size_t)c->V * 8);
     dev_free(c, c->d_mask, S);
+    dev_free(c, c->d_selw, (size_t)c->nW * 4);
     dev_free(c, c->d_weights, S * 8);
     dev_free(c, c->d_out_idx, S * 8);
     dev_free(c, c->d_out_new, S * 8);
@@ -617,6 +612,7 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.q_lo = c->d_q_lo;
     p.q_hi = c->d_q_hi;
     p.mask = c->d_mask;
+    p.selw = c->d_selw;
     p.weights = c->has_weights ? c->d_weights : nullptr;
     p.out_idx = c->d_out_idx;
     p.out_new = c->d_out_new;
@@ -638,7 +634,6 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.tail_budget = c->tail_budget;
     // N ranks: N times the rows per pick at the same sparsity (measured on 4 x B200: 1536 per rank beats 2048)
     p.tail_rows = c->mg_world > 1 ? std::min(c->tail_rows, 1536u) * (unsigned int)c->mg_world : c->tail_rows;
-    if (c->lazy_allowed) p.tail_rows = c->lazy_rows;        // the lazy kernel takes over much earlier (lazy.cu)
     p.dbg_time = c->dbg_time;
     p.dsmem_gains = (c->flags & UTMOS_F_DSMEM_GAINS) ? 1 : 0;
     p.st = c->d_state;
@@ -747,11 +742,6 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
     c->pitchW = (c->nW + 3) / 4 * 4;
     c->af_mode = af_mode;
     c->flags = flags;
-    {
-        const char *names[3] = {"UTMOS_B200_LAZY_G1", "UTMOS_B200_LAZY_G4", "UTMOS_B200_LAZY_SLACK"};     // A/B runs
-        for (int i = 0; i < 3; ++i)
-            if (getenv(names[i])) c->lazy_tune[i] = std::max(0, atoi(getenv(names[i])));
-    }
     int rc = UTMOS_OK;
     do {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1162,15 +1152,16 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
     const size_t S = (size_t)c->S;
     for (size_t i = 0; i < S; ++i)
         if (mask[i] > 2) { set_error("select_begin: mask values must be 0, 1 or 2"); return UTMOS_E_ARG; }
-    bool nonneg = true;
     if (weights)
-        for (size_t i = 0; i < S; ++i) {
+        for (size_t i = 0; i < S; ++i)
             if (!isfinite(weights[i])) { set_error("select_begin: weights must be finite"); return UTMOS_E_ARG; }
-            if (weights[i] < 0.0) nonneg = false;
-        }
-    c->weights_nonneg = nonneg;
     UT_CUDA(cudaSetDevice(c->device));
     UT_CUDA(cudaMemcpyAsync(c->d_mask, mask, S, cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint32_t> selw((size_t)c->nW, 0u);
+    for (size_t i = 0; i < S; ++i)
+        if (mask[i] == 1) selw[i >> 5] |= 1u << (i & 31);
+    if (!c->d_selw) UT_TRY(dev_alloc(c, (void **)&c->d_selw, (size_t)c->nW * 4));
+    UT_CUDA(cudaMemcpyAsync(c->d_selw, selw.data(), (size_t)c->nW * 4, cudaMemcpyHostToDevice, c->stream));
     const bool had_weights = c->has_weights;
     c->has_weights = weights != nullptr;
     if (weights) UT_CUDA(cudaMemcpyAsync(c->d_weights, weights, S * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1201,9 +1192,6 @@ int utmos_select_begin(utmos_ctx *c, const uint8_t *mask, const double *weights)
     UT_CUDA(cudaStreamSynchronize(c->stream));      // host buffers (mask, weights, st) may go away
     if ((c->flags & UTMOS_F_STEP_KERNELS) && (!c->graph_exec || had_weights != c->has_weights)) UT_TRY(build_graph(c));
     c->lists_valid = false;
-    c->lazy_valid = false;
-    c->lazy_fresh = false;
-    c->lazy_allowed = false;
     c->lists_cur = 0;                  // the first compaction of a selection goes to the buffer sized for it (no re-allocation)
     c->mg_tail = false;
     c->selecting = true;
@@ -1267,40 +1255,6 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         const unsigned long long list_budget = multi ? c->mg_list_cap - 64 : (wide ? kListBudgetWide : kListBudget);
         const size_t estride = af ? 2 : 1;
         c->tail_budget = tail_ok ? list_budget : 0;
-        // Lazy-greedy tail (lazy.cu): row lists of 4 bytes per live bit, no per-carrier decrements.  Single GPU, sample-major
-        // copy present, no negative weight, per-sample state fits one SM.  UTMOS_B200_LAZY=0 / UTMOS_F_NO_LAZY keep the
-        // list-driven tail of tail.cu (A/B runs, and the flavour under test for cohorts the lazy kernel does not take).
-        static const bool lazy_env = !(getenv("UTMOS_B200_LAZY") && atoi(getenv("UTMOS_B200_LAZY")) == 0);
-        static const long long lazy_rows_env = getenv("UTMOS_B200_LAZY_ROWS") ? atoll(getenv("UTMOS_B200_LAZY_ROWS")) : -1;
-        constexpr unsigned long long kLazyBudget = 1ull << 29;       // row-list entries (2 GB)
-        c->lazy_allowed = lazy_env && !multi && tail_ok && !(c->flags & UTMOS_F_NO_LAZY) && c->d_cols && c->weights_nonneg &&
-                          c->V < 0xfffffff0ll && lazy_possible(p, c->has_weights);
-        if (c->lazy_allowed) {
-            if (lazy_rows_env >= 0) c->lazy_rows = (unsigned int)std::min<long long>(lazy_rows_env, 0xffffffffll);
-            c->tail_budget = kLazyBudget;
-        }
-        auto build_lazy = [&](unsigned long long live_bits) -> int {
-            if (!c->ev_handover[0]) {
-                UT_CUDA(cudaEventCreate(&c->ev_handover[0]));
-                UT_CUDA(cudaEventCreate(&c->ev_handover[1]));
-            }
-            UT_CUDA(cudaEventRecord(c->ev_handover[0], c->stream));
-            const size_t need = (size_t)(live_bits + 3) / 4 + 1;                    // uint4 units: four row ids each
-            if (need > c->lists_cap[0]) {
-                big_free(c, c->d_lists[0], c->lists_cap[0] * 16);
-                UT_TRY(big_alloc(c, (void **)&c->d_lists[0], need * 16));
-                c->lists_cap[0] = need;
-            }
-            const SelParams q = make_params(c, false);
-            UT_TRY(launch_rowlist_offsets(c->stream, q, c->d_list_off[0], c->d_list_len[0], nullptr, &c->n_launch));
-            UT_TRY(launch_build_rowlists(c->stream, q, c->d_list_off[0], (unsigned int *)c->d_lists[0], &c->n_launch));
-            UT_CUDA(cudaEventRecord(c->ev_handover[1], c->stream));
-            c->handover_unread = true;
-            c->lazy_valid = true;
-            c->lazy_fresh = true;
-            c->lists_cur = 0;
-            return UTMOS_OK;
-        };
         auto reserve_lists = [&](int which, unsigned long long entries) -> int {
             const size_t need = (size_t)std::max<unsigned long long>(entries, 1) * estride;
             if (need > c->lists_cap[which]) {
@@ -1348,16 +1302,9 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             c->part_ms[which] += std::chrono::duration<double, std::milli>(now - part_t0).count();
             part_t0 = now;
         };
-        if (c->lazy_allowed && !c->lazy_valid && !c->lists_valid && c->lazy_rows == 0xffffffffu && st.live_bits <= kLazyBudget)
-            UT_TRY(build_lazy(st.live_bits));                  // lazy from the first pick on: no head kernels at all
         while (true) {
             SelParams q = make_params(c, false);
-            if (c->lazy_valid) {
-                UT_TRY(launch_lazy(c->stream, q, (unsigned int *)c->d_lists[0], c->d_list_off[0], c->d_list_len[0], c->lazy_fresh,
-                                   c->lazy_tune, &c->n_launch));
-                c->lazy_fresh = false;
-                c->flavour_used = 6;
-            } else if (c->lists_valid) {
+            if (c->lists_valid) {
                 // heavy picks: cluster of 8 CTAs, each applying the decrements of the samples it owns; light picks: one CTA
                 const unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
                 const bool cluster = single_rows > 0 || tail_cluster_size(q, false) != 1;     // wide / mid-size cohorts: sliced state
@@ -1406,13 +1353,8 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             UT_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
             UT_CUDA(cudaStreamSynchronize(c->stream));
             tr.lap(c->lists_valid ? "tail launch" : "head launches");
-            part_lap((c->lists_valid || c->lazy_valid) ? P_TAIL : P_HEAD);
+            part_lap(c->lists_valid ? P_TAIL : P_HEAD);
             if (st.stop != 0 || st.step >= limit || st.abort_flag) break;
-            if (c->lazy_valid) continue;
-            if (c->lazy_allowed && !c->lists_valid && st.want_tail && st.live_bits <= kLazyBudget) {
-                UT_TRY(build_lazy(st.live_bits));
-                continue;
-            }
             if (tail_ok && !c->lists_valid && st.want_tail && st.live_bits <= list_budget) {
                 if (multi) {
                     // replicated tail: every rank writes its live rows into the merged lists of all ranks (mgpu.cu)
@@ -1550,14 +1492,6 @@ int utmos_debug_gains(utmos_ctx *c, int64_t *count_out, double *score_out)
     UT_CUDA(cudaSetDevice(c->device));
     const size_t S = (size_t)c->S;
     const SelParams p = make_params(c, false);
-    if (c->lazy_valid) {
-        // the lazy kernel keeps upper bounds, not gains: recompute them from the sample-major copy and the live mask
-        const unsigned int one = 1u, zero = 0u;
-        UT_CUDA(cudaMemcpyAsync(&c->d_state->regain, &one, 4, cudaMemcpyHostToDevice, c->stream));
-        UT_TRY(launch_regain(c->stream, p, &c->n_launch));
-        UT_CUDA(cudaMemcpyAsync(&c->d_state->regain, &zero, 4, cudaMemcpyHostToDevice, c->stream));
-        UT_CUDA(cudaStreamSynchronize(c->stream));
-    }
     if (count_out) {
         std::vector<unsigned int> tmp(S);
         UT_CUDA(cudaMemcpy(tmp.data(), c->d_gain_cnt, S * 4, cudaMemcpyDeviceToHost));
@@ -1718,11 +1652,6 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
     if (option == UTMOS_OPT_GLOBAL_ROWS) { c->global_rows = value; return UTMOS_OK; }
     if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
-    if (option >= UTMOS_OPT_LAZY_G1 && option <= UTMOS_OPT_LAZY_SLACK) {
-        c->lazy_tune[option - UTMOS_OPT_LAZY_G1] = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
-        return UTMOS_OK;
-    }
-    if (option == UTMOS_OPT_LAZY_ROWS) { c->lazy_rows = value < 0 ? 0xffffffffu : (unsigned int)std::min<int64_t>(value, 0xffffffffll); return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_SINGLE_ROWS) { c->tail_single_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");
     return UTMOS_E_ARG;
@@ -1790,6 +1719,14 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
                      uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
                      uint8_t *singleton_out)
 {
+    return utmos_convert_gt_ex(device, gt, n_vars, n_samples, ploidy, packed_out, af_out, num_het_out, num_hom_out,
+                               singleton_out, 0);
+}
+
+int utmos_convert_gt_ex(int device, const int8_t *gt, int64_t n_vars, int64_t n_samples, int64_t ploidy,
+                        uint8_t *packed_out, double *af_out, int64_t *num_het_out, int64_t *num_hom_out,
+                        uint8_t *singleton_out, int flags)
+{
     if (n_vars < 0 || n_samples <= 0 || ploidy <= 0 || ploidy > 8) { set_error("convert_gt: bad shape"); return UTMOS_E_ARG; }
     if (n_vars > 0 && (!gt || !packed_out || !af_out)) { set_error("convert_gt: null buffer"); return UTMOS_E_ARG; }
     int n = 0;
@@ -1826,7 +1763,7 @@ int utmos_convert_gt(int device, const int8_t *gt, int64_t n_vars, int64_t n_sam
             CV(cudaMemcpyAsync(d_gt, gt + (size_t)r0 * row_in, (size_t)m * row_in, cudaMemcpyHostToDevice, stream));
             CV(cudaEventRecord(ev0, stream));
             rc = launch_convert_gt(stream, d_gt, m, (int)n_samples, (int)ploidy, d_packed, pitch, d_af, d_hh, d_single,
-                                   &launches);
+                                   (flags & UTMOS_CVT_DROP_SINGLETONS) ? 1 : 0, &launches);
             if (rc != UTMOS_OK) break;
             CV(cudaEventRecord(ev1, stream));
             CV(cudaMemcpyAsync(packed_out + (size_t)r0 * (size_t)pitch, d_packed, (size_t)m * (size_t)pitch,

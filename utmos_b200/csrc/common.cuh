@@ -65,6 +65,7 @@ struct SelParams {
     const unsigned long long *q_lo;    // [V] per-row fixed-point AF, low limb (L bits)
     const unsigned long long *q_hi;    // [V] high limb
     uint8_t *mask;                     // [S] working copy of sample_mask
+    const uint32_t *selw;              // [nW] bit s set = sample s was selectable (mask == 1) at select_begin
     const double *weights;             // [S] or null
     long long *out_idx;                // [S] report rows
     long long *out_new;
@@ -287,18 +288,9 @@ int mgpu_grid(int device, int *grid_out, int *block_out);
 int cluster_plan(const SelParams &p, int *cluster_out);
 int launch_cluster(cudaStream_t stream, const SelParams &p, int CL, int *n_launch, uint32_t *newmask = nullptr);
 
-// lazy.cu
-int lazy_possible(const SelParams &p, bool weights);
-int launch_rowlist_offsets(cudaStream_t stream, const SelParams &p, unsigned int *rl_off, unsigned int *rl_len,
-                           unsigned long long *d_total, int *n_launch);
-int launch_build_rowlists(cudaStream_t stream, const SelParams &p, const unsigned int *rl_off, unsigned int *rl,
-                          int *n_launch);
-int launch_lazy(cudaStream_t stream, const SelParams &p, unsigned int *rl, const unsigned int *rl_off,
-                unsigned int *rl_len, bool fresh, const int *tune, int *n_launch);
-
 // convert.cu
 int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S, int ploidy, uint8_t *packed,
                       long long pitch_out, double *af, unsigned long long *het_hom, uint8_t *singleton,
-                      int *n_launch);
+                      int drop_single, int *n_launch);
 
 }  // namespace utmos

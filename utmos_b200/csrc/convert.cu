@@ -26,7 +26,7 @@ template <int PLOIDY>
 __global__ void __launch_bounds__(256) gt_pack_af_kernel(const int8_t *__restrict__ gt, long long V, int S, int ploidy_rt,
                                                          uint8_t *__restrict__ packed, long long pitch,
                                                          double *__restrict__ af, unsigned long long *het_hom,
-                                                         uint8_t *__restrict__ singleton)
+                                                         uint8_t *__restrict__ singleton, int drop_single)
 {
     __shared__ unsigned int s_hist[128];       // counts of alleles 1..127 (allele 0 is counted in registers)
     __shared__ unsigned int s_an, s_zero, s_het, s_hom;
@@ -90,9 +90,12 @@ __global__ void __launch_bounds__(256) gt_pack_af_kernel(const int8_t *__restric
                 const unsigned int n = s_an;
                 // max over alleles of count/an == (max count)/an: the divide is monotone in the numerator
                 af[r] = n ? (double)m / (double)n : CUDART_NAN;
-                if (singleton) singleton[r] = (s_hist[1] == 1u || s_zero == 1u) ? 1 : 0;
-                if (s_het) atomicAdd(het_hom + 0, (unsigned long long)s_het);
-                if (s_hom) atomicAdd(het_hom + 1, (unsigned long long)s_hom);
+                const bool single = s_hist[1] == 1u || s_zero == 1u;
+                if (singleton) singleton[r] = single ? 1 : 0;
+                if (!(drop_single && single)) {            // --no-singleton: the row is dropped before the stats (convert.py:58-69)
+                    if (s_het) atomicAdd(het_hom + 0, (unsigned long long)s_het);
+                    if (s_hom) atomicAdd(het_hom + 1, (unsigned long long)s_hom);
+                }
             }
         }
         __syncthreads();
@@ -171,7 +174,8 @@ __device__ __forceinline__ uint32_t gt_piece(const uint4 &q, int valid, RowAcc &
 
 // warp-level end of a row: reduce the counters, AF = max alt-allele count / called alleles, singleton flag
 __device__ __forceinline__ void gt_row_finish(RowAcc acc, unsigned int *hist, int lane, long long r, double *af,
-                                              uint8_t *singleton, unsigned long long &het_tot, unsigned long long &hom_tot)
+                                              uint8_t *singleton, int drop_single, unsigned long long &het_tot,
+                                              unsigned long long &hom_tot)
 {
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) {
@@ -192,9 +196,12 @@ __device__ __forceinline__ void gt_row_finish(RowAcc acc, unsigned int *hist, in
     if (lane == 0) {
         // max over alleles of count/an == (max count)/an: the divide is monotone in the numerator
         af[r] = acc.an ? (double)m / (double)acc.an : CUDART_NAN;
-        if (singleton) singleton[r] = (acc.one == 1u || acc.zero == 1u) ? 1 : 0;
-        het_tot += acc.het;
-        hom_tot += acc.hom;
+        const bool single = acc.one == 1u || acc.zero == 1u;
+        if (singleton) singleton[r] = single ? 1 : 0;
+        if (!(drop_single && single)) {                // --no-singleton: the row is dropped before the stats (convert.py:58-69)
+            het_tot += acc.het;
+            hom_tot += acc.hom;
+        }
     }
 }
 
@@ -204,7 +211,7 @@ __device__ __forceinline__ void gt_row_finish(RowAcc acc, unsigned int *hist, in
 __global__ void __launch_bounds__(256) gt_pack_af_direct_kernel(const int8_t *__restrict__ gt, long long V, int S,
                                                                 uint8_t *__restrict__ packed, long long pitch,
                                                                 double *__restrict__ af, unsigned long long *het_hom,
-                                                                uint8_t *__restrict__ singleton)
+                                                                uint8_t *__restrict__ singleton, int drop_single)
 {
     __shared__ unsigned int s_hist[8][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(256) gt_pack_af_direct_kernel(const int8_t *__
             const uint4 q = ld_stream_u128(row + g);
             out[g] = (uint8_t)gt_piece(q, S - g * 8, acc, s_hist[warp]);
         }
-        gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, het_tot, hom_tot);
+        gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, drop_single, het_tot, hom_tot);
     }
     if (lane == 0) {
         if (het_tot) atomicAdd(het_hom + 0, het_tot);
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const i
                                                                          int rows_per_tile, uint8_t *__restrict__ packed,
                                                                          long long pitch, double *__restrict__ af,
                                                                          unsigned long long *het_hom,
-                                                                         uint8_t *__restrict__ singleton)
+                                                                         uint8_t *__restrict__ singleton, int drop_single)
 {
     extern __shared__ __align__(16) uint8_t c_smem[];
     __shared__ unsigned int s_hist[kCvtWarps][128];
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const i
                                            __funnelshift_r(r3, r4, fs));
                 out[s0 >> 3] = (uint8_t)gt_piece(q, S - s0, acc, s_hist[warp]);
             }
-            gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, het_tot, hom_tot);
+            gt_row_finish(acc, s_hist[warp], lane, r, af, singleton, drop_single, het_tot, hom_tot);
         }
     }
     if (lane == 0) {
@@ -313,13 +320,14 @@ __global__ void __launch_bounds__(kCvtWarps * 32) gt_pack_af_tile_kernel(const i
 }  // namespace
 
 int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S, int ploidy, uint8_t *packed,
-                      long long pitch_out, double *af, unsigned long long *het_hom, uint8_t *singleton, int *n_launch)
+                      long long pitch_out, double *af, unsigned long long *het_hom, uint8_t *singleton, int drop_single,
+                      int *n_launch)
 {
     if (V <= 0) return UTMOS_OK;
     if (ploidy == 2 && ((uintptr_t)gt & 15u) == 0 && (2ll * S) % 16 == 0 && pitch_out == (S + 7) / 8) {
         const long long warps = V;
         const unsigned grid = (unsigned)std::min<long long>((warps + 7) / 8, 148ll * 16);
-        gt_pack_af_direct_kernel<<<grid, 256, 0, stream>>>(gt, V, S, packed, pitch_out, af, het_hom, singleton);
+        gt_pack_af_direct_kernel<<<grid, 256, 0, stream>>>(gt, V, S, packed, pitch_out, af, het_hom, singleton, drop_single);
         *n_launch += 1;
         UT_CUDA(cudaGetLastError());
         return UTMOS_OK;
@@ -337,16 +345,16 @@ int launch_convert_gt(cudaStream_t stream, const int8_t *gt, long long V, int S,
         }
         const long long tiles = (V + R - 1) / R;
         const unsigned grid = (unsigned)std::min<long long>(tiles, 148ll * 8);
-        gt_pack_af_tile_kernel<<<grid, kCvtWarps * 32, smem, stream>>>(gt, V, S, R, packed, pitch_out, af, het_hom, singleton);
+        gt_pack_af_tile_kernel<<<grid, kCvtWarps * 32, smem, stream>>>(gt, V, S, R, packed, pitch_out, af, het_hom, singleton, drop_single);
         *n_launch += 1;
         UT_CUDA(cudaGetLastError());
         return UTMOS_OK;
     }
     const unsigned grid = (unsigned)(V < 148ll * 16 ? V : 148ll * 16);
     if (ploidy == 2)
-        gt_pack_af_kernel<2><<<grid, 256, 0, stream>>>(gt, V, S, ploidy, packed, pitch_out, af, het_hom, singleton);
+        gt_pack_af_kernel<2><<<grid, 256, 0, stream>>>(gt, V, S, ploidy, packed, pitch_out, af, het_hom, singleton, drop_single);
     else
-        gt_pack_af_kernel<0><<<grid, 256, 0, stream>>>(gt, V, S, ploidy, packed, pitch_out, af, het_hom, singleton);
+        gt_pack_af_kernel<0><<<grid, 256, 0, stream>>>(gt, V, S, ploidy, packed, pitch_out, af, het_hom, singleton, drop_single);
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;

@@ -464,7 +464,46 @@ __global__ void __launch_bounds__(kThreads) ingest_packed_kernel(const uint8_t *
     unsigned int total;
     const unsigned int ex = block_exclusive_scan(keep, &total);
     if (keep) s_src[ex] = (unsigned short)tid;
-    if (warp == 0) {
+    if (FLAVOUR == 3) {
+        // decoupled look-back by the whole CTA: warp w reads the 32 tile states at distance 32w .. 32w+31, so one round
+        // trip covers 256 tiles (kThreads / 32 windows).  A window's result = the values from the nearest tile down to its
+        // first inclusive prefix (if it holds one); the windows are then combined nearest first.
+        if (tid == 0) st_relaxed_u64(state + 1 + tile, (tile == 0 ? kTilePrefix : kTileAgg) | total);
+        unsigned long long excl = 0;
+        long long j = tile - 1;
+        bool done = tile == 0;
+        while (!done) {
+            const long long idx = j - 32ll * warp - lane;
+            unsigned long long v;
+            unsigned int pm, zm, need;
+            int first_p;
+            do {
+                v = idx >= 0 ? ld_relaxed_u64(state + 1 + idx) : kTilePrefix;
+                pm = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                zm = __ballot_sync(0xffffffffu, (v >> 62) == 0ull);
+                first_p = pm ? __ffs(pm) - 1 : 32;
+                need = first_p >= 31 ? 0xffffffffu : ((2u << first_p) - 1u);
+            } while (zm & need);
+            unsigned long long c = lane <= first_p ? (v & kTileValue) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) { s_lb_sum[warp] = c; s_lb_has[warp] = first_p < 32 ? 1u : 0u; }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) {
+                if (done) break;
+                excl += s_lb_sum[w];
+                done = s_lb_has[w] != 0u;
+            }
+            __syncthreads();                                      // s_lb_* are rewritten by the next round
+            j -= kThreads;
+        }
+        if (tid == 0) {
+            if (tile != 0) st_relaxed_u64(state + 1 + tile, kTilePrefix | (excl + total));
+            s_excl = excl;
+            if (tile == n_tiles - 1) *d_chunk_total = (long long)(excl + total);
+        }
+    } else if (warp == 0) {
         // decoupled look-back: publish this tile's count, then sum the tiles before it.  The status word carries its
         // own payload (no other memory is handed over through it), so relaxed accesses are enough.
         unsigned long long excl = 0;
@@ -860,12 +899,14 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
             UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+            UT_CUDA(cudaFuncSetAttribute(ingest_packed_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
             const char *env = getenv("UTMOS_B200_INGEST");       // A/B runs: 0 = first version, 2 = batched loads (opt-in)
-            if (env) flavour = atoi(env) == 0 ? 0 : atoi(env) == 2 ? 2 : 1;
+            if (env) flavour = atoi(env) == 0 ? 0 : atoi(env) == 2 ? 2 : atoi(env) == 3 ? 3 : 1;
             configured = true;
         }
         UT_CUDA(cudaMemsetAsync(sc.tile_state, 0, sizeof(unsigned long long) * (size_t)(n_tiles + 1), stream));
-        auto kernel = flavour == 0 ? ingest_packed_kernel<0> : flavour == 2 ? ingest_packed_kernel<2> : ingest_packed_kernel<1>;
+        auto kernel = flavour == 0 ? ingest_packed_kernel<0> : flavour == 2 ? ingest_packed_kernel<2>
+                      : flavour == 3 ? ingest_packed_kernel<3> : ingest_packed_kernel<1>;
         kernel<<<(unsigned)n_tiles, kThreads, smem, stream>>>((const uint8_t *)raw, n_rows, pitch_in, af_in, S, pitchW, R, n_tiles,
                                                               sc.tile_state, d_nrows, d_total, rows_out, af_out);
         bump_rows_kernel<<<1, 1, 0, stream>>>(d_nrows, d_total);

@@ -37,10 +37,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 __global__ void __launch_bounds__(256) live_colpop_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ live,
-                                                          long long colPitchW, int S, unsigned int *out)
+                                                          const uint8_t *__restrict__ mask, long long colPitchW, int S,
+                                                          unsigned int *out)
 {
     const int s = blockIdx.x;
     if (s >= S) return;
+    if (mask[s] != 1) {                        // no list for a sample that can never be picked (tail.cu: build_edges_kernel)
+        if (threadIdx.x == 0) out[s] = 0u;
+        return;
+    }
     const uint4 *col = reinterpret_cast<const uint4 *>(cols + (long long)s * colPitchW);
     const uint4 *lv = reinterpret_cast<const uint4 *>(live);
     const long long n4 = colPitchW / 4;
@@ -228,7 +233,7 @@ int launch_live_counts(cudaStream_t stream, const SelParams &p, unsigned int *lc
         UT_CUDA(cudaMemsetAsync(lcnt, 0, (size_t)p.S * 4, stream));
         return UTMOS_OK;
     }
-    live_colpop_kernel<<<p.S, 256, 0, stream>>>(p.cols, p.live, p.colPitchW, p.S, lcnt);
+    live_colpop_kernel<<<p.S, 256, 0, stream>>>(p.cols, p.live, p.mask, p.colPitchW, p.S, lcnt);
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;

@@ -43,7 +43,9 @@ __global__ void __launch_bounds__(1024) sum_gains_kernel(SelParams p)
 {
     __shared__ unsigned long long s_part[32];
     unsigned long long acc = 0;
-    for (int s = threadIdx.x; s < p.S; s += blockDim.x) acc += p.gain_cnt[s];
+    // the gains of the SELECTABLE samples: they are what the edge lists hold (carriers that can never be picked get no
+    // entries and, once the lists exist, no decrements either -- their gains go stale, nobody reads them)
+    for (int s = threadIdx.x; s < p.S; s += blockDim.x) acc += p.mask[s] == 1 ? p.gain_cnt[s] : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -55,9 +57,10 @@ __global__ void __launch_bounds__(1024) sum_gains_kernel(SelParams p)
     }
 }
 
-// list_len[s] = gain_cnt[s]; list_off = exclusive scan (single CTA, running carry); cursor[s] = 0
-__global__ void __launch_bounds__(1024) list_offsets_kernel(const unsigned int *gain_cnt, int S, unsigned int *list_off,
-                                                            unsigned int *list_len, unsigned int *cursor)
+// list_len[s] = gain_cnt[s] for selectable samples (0 for the others: they are never walked); list_off = exclusive
+// scan (single CTA, running carry); cursor[s] = 0
+__global__ void __launch_bounds__(1024) list_offsets_kernel(const unsigned int *gain_cnt, const uint8_t *mask, int S,
+                                                            unsigned int *list_off, unsigned int *list_len, unsigned int *cursor)
 {
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned int s_carry;
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(const unsigned int *
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < S; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        const unsigned int v = i < S ? gain_cnt[i] : 0u;
+        const unsigned int v = (i < S && mask[i] == 1) ? gain_cnt[i] : 0u;
         unsigned int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -117,8 +120,11 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
         if (!((p.live[r >> 5] >> (r & 31)) & 1u)) continue;
         const uint32_t *row = p.rows + r * p.pitchW;
         const unsigned int rg = (unsigned int)(r + d.row_base);          // row id in the (merged) live mask
+        // only carriers that can still be picked get entries (and are listed as other carriers): p.selw = bitmask of the
+        // samples with mask == 1 at select_begin.  Excluded samples (utmos/select.py:168-175) never score, so nobody needs
+        // their gains; on a run with --subset this halves the lists and the decrements of the tail.
         int mine = 0;
-        for (int k = lane; k < p.nW; k += 32) mine += __popc(__ldg(row + k));
+        for (int k = lane; k < p.nW; k += 32) mine += __popc(__ldg(row + k) & p.selw[k]);
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
             if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;                                        // carried by excluded samples only
         uint4 tailq = make_uint4(0u, 0u, 0u, 0u);
         if (ESTRIDE == 2) {
             const unsigned long long ql = p.q_lo[r], qh = p.q_hi[r];
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
         if (total - 1 <= kInl) {
             int pos = incl - mine;
             for (int k = lane; k < p.nW; k += 32) {
-                uint32_t x = __ldg(row + k);
+                uint32_t x = __ldg(row + k) & p.selw[k];
                 while (x) {
                     s_car[wib][pos++] = (unsigned int)((k << 5) + (__ffs(x) - 1));
                     x &= x - 1;
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(256) build_edges_kernel(SelParams p, EdgeDst d
             }
             int pos = incl - mine;
             for (int k = lane; k < p.nW; k += 32) {
-                uint32_t x = __ldg(row + k);
+                uint32_t x = __ldg(row + k) & p.selw[k];
                 while (x) {
                     const unsigned int s = (unsigned int)((k << 5) + (__ffs(x) - 1));
                     x &= x - 1;
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
         if (++since_check >= 64) {
             since_check = 0;
             unsigned long long acc = 0;
-            for (int li = tid; li < n_own; li += blockDim.x) acc += s_cnt[li];
+            for (int li = tid; li < n_own; li += blockDim.x) acc += s_mask[li] == 1 ? s_cnt[li] : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) s_sum[warp] = acc;
@@ -781,7 +788,7 @@ int launch_build_lists(cudaStream_t stream, const SelParams &p, uint4 *lists, un
                        unsigned int *list_len, unsigned int *cursor, unsigned short *pool, unsigned int *pool_cursor,
                        int *n_launch)
 {
-    list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.S, list_off, list_len, cursor);
+    list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.mask, p.S, list_off, list_len, cursor);
     *n_launch += 1;
     EdgeDst d;
     memset(&d, 0, sizeof(d));
@@ -814,7 +821,7 @@ int launch_filter_lists(cudaStream_t stream, const SelParams &p, const uint4 *ol
                         const unsigned int *old_len, uint4 *new_lists, unsigned int *new_off, unsigned int *new_len,
                         int *n_launch)
 {
-    list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.S, new_off, new_len, nullptr);
+    list_offsets_kernel<<<1, 1024, 0, stream>>>(p.gain_cnt, p.mask, p.S, new_off, new_len, nullptr);
     if (p.af) filter_edges_kernel<2><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off);
     else filter_edges_kernel<1><<<p.S, 256, 0, stream>>>(p.live, old_lists, old_off, old_len, new_lists, new_off);
     *n_launch += 2;

@@ -345,6 +345,25 @@ def _message(mtype, payload, flags=0):
     return struct.pack("<HHB3x", mtype, len(payload), flags) + payload
 
 
+def _auto_chunk_rows(n, typesize):
+    """Chunk length h5py picks for a 1-D dataset created with ``chunks=True`` / a compression filter and no explicit
+    chunk shape (its published ``guess_chunk`` heuristic: aim at 16 KB * 2^log10(bytes / 1 MB), clamped to 8 KB .. 1 MB,
+    halving the length until the chunk is within 50 % of that) -- so `samples` and `var_count` get the chunk shape the
+    reference's files have (utmos/select.py:209, :238; 2,504 samples -> chunks of 1,252)."""
+    base, lo, hi = 16 * 1024, 8 * 1024, 1024 * 1024
+    c = float(max(1, n))
+    target = base * (2 ** np.log10(c * typesize / (1024.0 * 1024.0)))
+    target = min(max(target, lo), hi)
+    while True:
+        nbytes = c * typesize
+        if (nbytes < target or abs(nbytes - target) / target < 0.5) and nbytes < hi:
+            break
+        if c == 1:
+            break
+        c = np.ceil(c / 2.0)
+    return int(c)
+
+
 class _ChunkedDataset:
     """Bookkeeping of one chunked dataset while the file is being written."""
 
@@ -565,10 +584,10 @@ class H5Writer:
         self.data.finish()
         width = max(1, self.samples.dtype.itemsize)
         str_type = struct.pack("<BBBBI", 0x13, 0x01, 0, 0, width)
-        ds_samples = _ChunkedDataset(self, str_type, width, (), max(1, self.n_samples), True)
+        ds_samples = _ChunkedDataset(self, str_type, width, (), _auto_chunk_rows(self.n_samples, width), True)
         ds_samples.append(self.samples.astype(f"S{width}"))
         ds_samples.finish()
-        ds_vc = _ChunkedDataset(self, _I64_TYPE, 8, (), max(1, self.n_samples), False)
+        ds_vc = _ChunkedDataset(self, _I64_TYPE, 8, (), _auto_chunk_rows(self.n_samples, 8), False)
         ds_vc.append(np.asarray(var_count, dtype="<i8"))
         ds_vc.finish()
         self._pos = (self._pos + 7) // 8 * 8
