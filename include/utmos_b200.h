@@ -131,6 +131,21 @@ int utmos_select_steps(utmos_ctx *ctx, int64_t max_steps, int64_t *idx_out, int6
                        double *score_out, int64_t *n_out, int *stop_out);
 
 /*
+ * Resume (no counterpart in the reference, which cannot resume a selection: SURVEY.md section 8, "next" item 4).
+ * utmos_select_export copies out the state of the selection in progress: the working sample mask (picked samples are
+ * 0), the live-row mask (utmos_info()[8] words; bit r = row r is not covered yet) and the report rows so far.
+ * utmos_select_import starts a selection from such a state on a context that holds the same matrix: it recomputes
+ * every gain from the matrix and the live mask, so utmos_select_steps continues with exactly the rows an uninterrupted
+ * run would have produced.  Single-GPU contexts only.
+ */
+int utmos_select_export(utmos_ctx *ctx, uint8_t *mask_out, uint32_t *live_out, int64_t live_words, int64_t *idx_out,
+                        int64_t *new_out, double *score_out, int64_t rows_cap, int64_t *n_rows_out, int64_t *tot_out,
+                        int *stop_out);
+int utmos_select_import(utmos_ctx *ctx, const uint8_t *mask, const double *weights, const uint32_t *live,
+                        int64_t live_words, const int64_t *idx, const int64_t *new_count, const double *score,
+                        int64_t n_rows, int64_t tot, int stop);
+
+/*
  * utmos/convert.py:57-87 on a host int8 tensor gt[V][S][ploidy] (missing allele = -1).
  * packed_out: V x ceil(S/8) bytes, MSB-first (np.packbits); af_out[V] (NaN when no allele is called);
  * singleton_out[V] (may be NULL) = count(allele 1)==1 || count(allele 0)==1 (convert.py:58-60).
@@ -201,7 +216,8 @@ int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
  * [4]=fixed-point scale (AF flavours), [5]=AF values not exactly representable (count), [6]=kernels launched,
  * [7]=selection kernel flavour used: 0 step kernels, 1 grid-wide persistent, 2 one-cluster DSMEM,
  *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2), 4 multi-GPU kernel (per-step exchange),
- *   5 multi-GPU head followed by the replicated tail */
+ *   5 multi-GPU head followed by the replicated tail;
+ * [8]=32-bit words of the live-row mask (utmos_select_export / _import) */
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:

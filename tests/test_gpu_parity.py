@@ -194,6 +194,68 @@ def test_step_batches_equal_one_shot():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("use_af", [False, True], ids=["count", "af"])
+def test_export_import_state_resumes_bit_for_bit(use_af, flags):
+    """a selection exported after k picks and imported into a FRESH context over the same matrix continues
+    with exactly the rows of an uninterrupted run (utmos/select.py:91-112), in every kernel flavour, with weights and
+    exclusions; the gains of the restored state equal the oracle's score vector."""
+    parts = H.load_jl_parts(["chunk0.jl", "chunk1.jl"])
+    n = 2504
+    rng = np.random.default_rng(4)
+    mask = np.ones(n, np.uint8)
+    mask[rng.random(n) < 0.1] = 2
+    wts = np.ones(n)
+    wts[rng.random(n) < 0.05] = 3.0
+    af_mode = _native.AF_F64 if use_af else _native.AF_NONE
+
+    def fresh():
+        dm = _native.DeviceMatrix(n, af_mode, flags=flags)
+        for part in parts:
+            dm.append_packed(part["GT"], part["AF"])
+        dm.finalize()
+        return dm
+
+    dm = fresh()
+    dm.begin(mask, wts)
+    full = dm.steps(n)
+    dm.close()
+    for k in (0, 1, 37, 300):
+        a = fresh()
+        a.begin(mask, wts)
+        first = a.steps(k) if k else (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0), 0)
+        state = a.export_state()
+        a.close()
+        assert len(state["idx"]) == k and np.array_equal(state["idx"], full[0][:k])
+        b = fresh()
+        b.import_state(state, wts)
+        rest = b.steps(n)
+        b.close()
+        idx = np.concatenate([first[0], rest[0]])
+        new = np.concatenate([first[1], rest[1]])
+        score = np.concatenate([first[2], rest[2]])
+        assert np.array_equal(idx, full[0]) and np.array_equal(new, full[1]) and np.array_equal(score, full[2]), k
+        assert rest[3] == full[3]
+
+
+def test_cli_resume_continues_the_report(tmp_path, monkeypatch):
+    """`utmos select --resume FILE`: a run cut short after its first batch, run again, writes the report of one run."""
+    monkeypatch.setattr(usel, "STEP_BATCH", 7)
+    out_a, out_b, ck = tmp_path / "a.txt", tmp_path / "b.txt", str(tmp_path / "ck.npz")
+    files = [H.fixture("chunk0.jl"), H.fixture("chunk1.jl")]
+    usel.select_main(["-c", "40", "-o", str(out_a)] + files)
+    gen_data = usel.load_files(files)
+    rows = usel.run_selection(gen_data, 40, None, None, None, resume=ck)
+    got = [next(rows) for _ in range(10)]                        # 10 rows consumed: two batches of 7 were computed and saved
+    del rows
+    gen_data.close()
+    assert len(got) == 10 and os.path.exists(ck)
+    usel.select_main(["-c", "40", "-o", str(out_b), "--resume", ck] + files)
+    assert out_b.read_text() == out_a.read_text()
+    # a checkpoint of other options is ignored, not misused
+    usel.select_main(["-c", "20", "-o", str(out_b), "--resume", ck, "--exclude", "NA21117"] + files)
+    assert out_b.read_text() == H.answer_key("select_exclude.txt")
+
+
 def test_gains_after_k_steps_match_oracle_score_vector(flags):
     parts = H.load_jl_parts(["chunk0.jl"])
     n = 2504

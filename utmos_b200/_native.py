@@ -20,7 +20,7 @@ E_NOGPU = -3
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_append_h5_chunks", "utmos_finalize", "utmos_select_begin",
-           "utmos_select_steps", "utmos_convert_gt", "utmos_convert_gt_ex", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
+           "utmos_select_steps", "utmos_select_export", "utmos_select_import", "utmos_convert_gt", "utmos_convert_gt_ex", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
            "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_h5_encode_chunks", "utmos_gz_size", "utmos_gz_inflate", "utmos_vcf_parse_gt", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
@@ -64,6 +64,9 @@ def lib():
         "utmos_finalize": (i32, [p, ctypes.POINTER(i64), p]),
         "utmos_select_begin": (i32, [p, p, p]),
         "utmos_select_steps": (i32, [p, i64, p, p, p, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
+        "utmos_select_export": (i32, [p, p, p, i64, p, p, p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64),
+                                      ctypes.POINTER(ctypes.c_int)]),
+        "utmos_select_import": (i32, [p, p, p, p, i64, p, p, p, i64, i64, ctypes.c_int]),
         "utmos_convert_gt": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p]),
         "utmos_convert_gt_ex": (i32, [i32, p, i64, i64, i64, p, p, ctypes.POINTER(i64), ctypes.POINTER(i64), p, i32]),
         "utmos_convert_kernel_ms": (i32, [ctypes.POINTER(ctypes.c_double)]),
@@ -275,6 +278,33 @@ class DeviceMatrix:
                                        ctypes.byref(n), ctypes.byref(stop)))
         return idx[:n.value], new[:n.value], score[:n.value], stop.value
 
+    # -- resume --------------------------------------------------------------------------------------
+    def export_state(self):
+        """State of the selection in progress (utmos_select_export): dict of mask, live, idx, new, score, tot, stop."""
+        words = self.info()["live_words"]
+        mask = np.zeros(self.n_samples, dtype=np.uint8)
+        live = np.zeros(words, dtype=np.uint32)
+        idx = np.zeros(self.n_samples, dtype=np.int64)
+        new = np.zeros(self.n_samples, dtype=np.int64)
+        score = np.zeros(self.n_samples, dtype=np.float64)
+        n, tot, stop = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+        check(lib().utmos_select_export(self._ctx, _ptr(mask), _ptr(live), words, _ptr(idx), _ptr(new), _ptr(score),
+                                        self.n_samples, ctypes.byref(n), ctypes.byref(tot), ctypes.byref(stop)))
+        return {"mask": mask, "live": live, "idx": idx[:n.value].copy(), "new": new[:n.value].copy(),
+                "score": score[:n.value].copy(), "tot": int(tot.value), "stop": int(stop.value)}
+
+    def import_state(self, state, weights=None):
+        """Continue a selection from ``export_state()`` output on a context holding the same matrix."""
+        mask = np.ascontiguousarray(state["mask"], dtype=np.uint8)
+        live = np.ascontiguousarray(state["live"], dtype=np.uint32)
+        idx = np.ascontiguousarray(state["idx"], dtype=np.int64)
+        new = np.ascontiguousarray(state["new"], dtype=np.int64)
+        score = np.ascontiguousarray(state["score"], dtype=np.float64)
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.float64)
+        check(lib().utmos_select_import(self._ctx, _ptr(mask), _ptr(weights), _ptr(live), len(live), _ptr(idx), _ptr(new),
+                                        _ptr(score), len(idx), int(state["tot"]), int(state["stop"])))
+
     # -- introspection -----------------------------------------------------------------------------
     def gains(self):
         cnt = np.zeros(self.n_samples, dtype=np.int64)
@@ -302,10 +332,10 @@ class DeviceMatrix:
         check(lib().utmos_set_option(self._ctx, 1, int(rows)))
 
     def info(self):
-        arr = np.zeros(8, dtype=np.int64)
-        check(lib().utmos_info(self._ctx, _ptr(arr), 8))
+        arr = np.zeros(9, dtype=np.int64)
+        check(lib().utmos_info(self._ctx, _ptr(arr), 9))
         keys = ["num_vars", "row_pitch_bytes", "has_sample_major", "device_bytes", "fixed_scale", "af_inexact",
-                "kernel_launches", "flavour"]
+                "kernel_launches", "flavour", "live_words"]
         return dict(zip(keys, (int(x) for x in arr)))
 
     def timings(self, reset=False):

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) colpop_kernel(const uint32_t *__restrict_
     if (threadIdx.x == 0) {
         unsigned int a = 0, b = 0;
         for (int i = 0; i < 8; ++i) { a += s_all[i]; b += s_alive[i]; }
-        var_count[s] = a;
+        if (var_count) var_count[s] = a;
         gain_cnt[s] = b;
     }
 }
@@ -1423,6 +1423,7 @@ int launch_gain_init(cudaStream_t stream, const SelParams &p, unsigned int *var_
     } else if (p.af) {
         what |= 4;
     }
+    if (!var_count) what &= ~1;                 // gains of a restored live mask only (utmos_select_import)
     if (what) {
         const long long warps_needed = p.V;
         long long blocks = (warps_needed + 7) / 8;

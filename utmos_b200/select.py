@@ -35,13 +35,17 @@ def resolve_select_count(select_count, num_samples):
     return max(1, int(num_samples * select_count) if select_count < 1 else int(select_count))
 
 
-def run_selection(data, select_count=0.02, subset=None, exclude=None, weights=None):
+def run_selection(data, select_count=0.02, subset=None, exclude=None, weights=None, resume=None):
     """
     Setup the selection calculation and iterate it (utmos/select.py:147-195 + :69-112)
     if select_count [0,1], select that percent of samples
     if select_count >= 1, select that number of samples
 
     Generator of [sample, var_count, new_count, tot_captured, pct_captured].
+
+    ``resume`` (not in the reference): path of a checkpoint file.  When it exists and belongs to this matrix and these
+    options, the rows it holds are yielded again and the selection continues after them; the file is rewritten after
+    every batch of picks, so a killed `--count -1` run over a large cohort loses at most one batch.
     """
     matrix = data["data"]
     num_vars, num_samples = matrix.shape
@@ -75,16 +79,67 @@ def run_selection(data, select_count=0.02, subset=None, exclude=None, weights=No
                 sample_weights[pos] = column.loc[i]
 
     total_variant_count = np.asarray(data["var_count"][:])
-    matrix.begin(sample_mask.astype(np.uint8), sample_weights)
+    sample_mask = sample_mask.astype(np.uint8)
+    done = None
+    if resume:
+        if not hasattr(matrix, "export_state"):
+            logging.error("--resume is not available for a matrix sharded over several GPUs")
+            sys.exit(1)
+        tag = _checkpoint_tag(sample_mask, sample_weights, total_variant_count, num_vars)
+        state = _load_checkpoint(resume, tag)
+        if state is not None:
+            logging.info("Resuming after %d picks from %s", len(state["idx"]), resume)
+            matrix.import_state(state, sample_weights)
+            done = (state["idx"], state["new"], state["stop"])
+        else:
+            matrix.begin(sample_mask, sample_weights)
+        return _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_vars, done, (resume, tag))
+    matrix.begin(sample_mask, sample_weights)
     return _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_vars)
 
 
-def _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_vars):
-    """Report rows of utmos/select.py:91-112, fed by batches of GPU steps."""
+def _checkpoint_tag(sample_mask, sample_weights, var_count, num_vars):
+    """Fingerprint of what a checkpoint belongs to: the matrix (shape, var_count) and the scoring options."""
+    import hashlib  # pylint: disable=import-outside-toplevel
+    h = hashlib.sha256()
+    h.update(np.int64(num_vars).tobytes())
+    h.update(np.ascontiguousarray(var_count, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(sample_mask, dtype=np.uint8).tobytes())
+    h.update(b"w" + (np.ascontiguousarray(sample_weights, dtype=np.float64).tobytes() if sample_weights is not None else b""))
+    return h.hexdigest()
+
+
+def _load_checkpoint(path, tag):
+    if not os.path.exists(path):
+        return None
+    with np.load(path, allow_pickle=False) as z:
+        if str(z["tag"]) != tag:
+            logging.warning("%s belongs to another matrix or other options: starting over", path)
+            return None
+        return {k: z[k] for k in ("mask", "live", "idx", "new", "score")} | {"tot": int(z["tot"]), "stop": int(z["stop"])}
+
+
+def _save_checkpoint(path, tag, state):
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, tag=np.array(tag), **state)
+    os.replace(tmp, path)                                    # the old checkpoint stays valid until the new one is complete
+
+
+def _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_vars, done=None, checkpoint=None):
+    """Report rows of utmos/select.py:91-112, fed by batches of GPU steps.  ``done`` = (idx, new, stop) of the rows a
+    checkpoint already holds: they are yielded first, from the same expressions."""
     tot_captured = 0
     emitted = 0
+    first = True
     while emitted < select_count:
-        idx, new, _score, stop = matrix.steps(min(STEP_BATCH, select_count - emitted))
+        resumed_batch = first and done is not None
+        if resumed_batch:
+            idx, new, stop = done[0][:select_count], done[1][:select_count], done[2]
+        else:
+            idx, new, _score, stop = matrix.steps(min(STEP_BATCH, select_count - emitted))
+            if checkpoint is not None and len(idx):
+                _save_checkpoint(checkpoint[0], checkpoint[1], matrix.export_state())
+        first = False
         for use_sample, new_variant_count in zip(idx, new):
             tot_captured += new_variant_count               # np.int64, like counts[use_sample]
             emitted += 1
@@ -102,7 +157,7 @@ def _greedy_rows(matrix, total_variant_count, select_count, vcf_samples, num_var
         if stop == _native.STOP_ALL:
             logging.warning("Ran out of new variants")
             return
-        if len(idx) == 0:
+        if len(idx) == 0 and not resumed_batch:
             return
 
 
@@ -276,6 +331,8 @@ _SELECT_OPTIONS = (
                                  help="how many samples: a fraction of the cohort below 1, a number from 1 up, -1 for all (%(default)s)")),
         (("-o", "--out"), dict(type=str, default="/dev/stdout", help="report file (%(default)s)")),
         (("--debug",), dict(action="store_true", help="log at debug level")),
+        (("--resume",), dict(type=str, default=None,
+                             help="checkpoint file (not in the reference): continue from it if it exists, rewrite it after every batch of picks")),
     )),
     ("Scoring", (
         (("--af",), dict(action="store_true", help="score a variant by its allele frequency instead of 1")),
@@ -368,7 +425,7 @@ def select_main(cmdargs):
     weights = parse_weights(args.weights)
     with open(args.out, "w") as report:
         report.write("\t".join(REPORT_COLUMNS) + "\n")
-        for row in run_selection(data, args.count, subset, exclude, weights):
+        for row in run_selection(data, args.count, subset, exclude, weights, resume=args.resume):
             logging.info("Selected %s (%.1f%% of variants)", row[0], row[4] * 100)
             report.write("\t".join(str(value) for value in row) + "\n")
             report.flush()                                    # one line per pick, visible as soon as it is made
