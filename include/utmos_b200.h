@@ -76,6 +76,15 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
 int utmos_destroy(utmos_ctx *ctx);
 
 /*
+ * ".jl v2" rows (the "both axis pack" of the reference's README.md:59-63, which the reference never implemented;
+ * SURVEY.md section 8 "next" item 3).  Row v occupies payload[offsets[v] .. offsets[v+1]): either its ceil(S/8)
+ * np.packbits bytes, or -- when shorter -- the little-endian uint16 (idx_bytes 2) / uint32 (idx_bytes 4) sample indices of
+ * its carriers.  Decoded on the GPU, then filtered and stored exactly like utmos_append_packed rows.
+ */
+int utmos_append_packed2(utmos_ctx *ctx, const uint8_t *payload, const uint64_t *offsets, int64_t n_rows, int idx_bytes,
+                         const double *af);
+
+/*
  * Append one .jl part: `n_rows` rows of `pitch_bytes` (>= ceil(S/8)) bytes, MSB-first bit packed
  * (np.packbits, utmos/convert.py:85), with one float64 AF per row (may be NULL when af_mode == NONE).
  * Rows without any of the first S bits set are dropped together with their AF (utmos/select.py:276-280).

@@ -605,6 +605,58 @@ def test_read_vcf_reproduces_fixture_jl(name):
     assert data["AF"].shape == (1000, 1)
 
 
+@pytest.mark.parametrize("n_samples,n_vars", [(2504, 3000), (37, 500), (70001, 600)], ids=["1kgp_pitch", "ragged", "wide_u32"])
+def test_jl2_rows_decoded_on_the_gpu_equal_packed_rows(n_samples, n_vars):
+    """`.jl` v2: rows stored as carrier lists / np.packbits bytes, rebuilt by unpack_rows2_kernel, give the same
+    matrix (kept rows, var_count) and the same selection as the v1 rows -- incl. uninformative (zero-length) rows, --af."""
+    from utmos_b200 import jl2
+    gt, af = synth.mirror_rows(8, 0, n_vars, n_samples)
+    gt[::17] = 0                                                             # uninformative rows: dropped at load
+    g2 = jl2.encode(gt, n_samples)
+    mask = np.ones(n_samples, np.uint8)
+    mask[::11] = 2
+    out = []
+    for kind in ("v1", "v2"):
+        dm = _native.DeviceMatrix(n_samples, _native.AF_F64)
+        if kind == "v1":
+            dm.append_packed(gt[:1000], af[:1000])
+            dm.append_packed(gt[1000:], af[1000:])
+        else:
+            dm.append_packed2(jl2.slice_rows(g2, 0, 1000), af[:1000])
+            dm.append_packed2(jl2.slice_rows(g2, 1000, n_vars), af[1000:])
+        vc = dm.finalize()
+        dm.begin(mask)
+        idx, new, score, stop = dm.steps(60)
+        out.append((dm.num_vars, vc, idx, new, score, stop))
+        dm.close()
+    a, b = out
+    assert a[0] == b[0] == int((gt != 0).any(axis=1).sum())
+    for x, y in zip(a[1:], b[1:]):
+        assert np.array_equal(x, y)
+    bad = jl2.encode(gt[:10], n_samples)
+    bad["payload"] = bad["payload"].copy()
+    first_sparse = int(np.nonzero((bad["lengths"] > 0) & (bad["lengths"] < gt.shape[1]))[0][0])
+    o = int(bad["offsets"][first_sparse])
+    bad["payload"][o:o + 2] = 0xff                                            # sample index 65535 (or more): out of range
+    if n_samples <= 65535:
+        dm = _native.DeviceMatrix(n_samples, _native.AF_NONE)
+        with pytest.raises(_native.NativeError):
+            dm.append_packed2(bad)
+        dm.close()
+
+
+def test_convert_pack2_and_select_reproduce_answer_key(tmp_path):
+    """`utmos convert --pack2` + `utmos select` on the v2 file = the reference's answer key for the v1 path."""
+    import joblib
+    out = tmp_path / "c1.jl"
+    ucvt.cvt_main([H.fixture("chunk1.vcf.gz"), str(out), "--pack2"])
+    dat = joblib.load(out)
+    assert "GT" not in dat and set(dat["GT2"]) == {"payload", "lengths", "idx_bytes", "n_samples"}
+    rep = tmp_path / "r.txt"
+    usel.select_main(["-o", str(rep), str(out)])
+    assert rep.read_text() == H.answer_key("select_fileout.txt")
+
+
 @pytest.mark.parametrize("no_singleton", [False, True], ids=["all_rows", "no_singleton"])
 def test_read_vcf_hand_built_rows(tmp_path, no_singleton):
     """K1 on missing / half-missing / haploid / AN = 0 / multi-allelic rows against answers worked out from scikit-allel's

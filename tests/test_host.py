@@ -240,6 +240,28 @@ def test_convert_oracle_and_vcf_parser_on_hand_built_rows(tmp_path):
         assert out["stats"] == {"num_het": sum(r[3] for r in H.HAND_VCF_ROWS), "num_hom": sum(r[4] for r in H.HAND_VCF_ROWS)}
 
 
+def test_jl2_row_compression_roundtrip():
+    """`.jl` v2 (utmos_b200/jl2.py): encode / decode / slice are lossless on the reference's fixtures and on
+    ragged sample counts, rare rows become carrier lists and the payload is several times smaller than np.packbits rows."""
+    from utmos_b200 import jl2
+    part = H.load_jl_parts(["chunk1.jl"])[0]
+    g2 = jl2.encode(part["GT"], 2504)
+    assert np.array_equal(jl2.decode(jl2.for_file(g2)), part["GT"])
+    assert g2["payload"].nbytes * 4 < part["GT"].nbytes and g2["idx_bytes"] == 2
+    assert int(g2["lengths"].max()) == 313                                   # common variants stay np.packbits rows
+    sl = jl2.slice_rows(g2, 17, 400)
+    assert jl2.n_rows(sl) == 383 and int(sl["offsets"][0]) == int(g2["offsets"][17])
+    for n_samples in (1, 7, 8, 9, 70001):
+        rng = np.random.default_rng(n_samples)
+        dense = rng.random((40, n_samples)) < 0.02
+        dense[5] = True                                                       # a full row
+        dense[6] = False                                                      # an empty row: zero-length entry
+        gt = np.packbits(dense, axis=1)
+        g = jl2.encode(gt, n_samples)
+        assert g["idx_bytes"] == (4 if n_samples > 65536 else 2)
+        assert np.array_equal(jl2.decode(g), gt) and int(g["lengths"][6]) == 0
+
+
 def test_count_resolution_and_sample_lists(tmp_path):
     assert usel.resolve_select_count(-1, 2504) == 2504
     assert usel.resolve_select_count(0.02, 2504) == 50

@@ -20,7 +20,7 @@ E_NOGPU = -3
 SYMBOLS = ["utmos_last_error", "utmos_version", "utmos_device_count", "utmos_host_alloc", "utmos_host_free",
            "utmos_create", "utmos_destroy", "utmos_append_packed", "utmos_append_packed_device",
            "utmos_append_dense_u8", "utmos_append_dense_f32", "utmos_append_h5_chunks", "utmos_finalize", "utmos_select_begin",
-           "utmos_select_steps", "utmos_select_export", "utmos_select_import", "utmos_convert_gt", "utmos_convert_gt_ex", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
+           "utmos_append_packed2", "utmos_select_steps", "utmos_select_export", "utmos_select_import", "utmos_convert_gt", "utmos_convert_gt_ex", "utmos_convert_kernel_ms", "utmos_rows", "utmos_mgpu_layout", "utmos_mgpu_export", "utmos_mgpu_connect", "utmos_get_gains0", "utmos_set_gains0",
            "utmos_debug_gains", "utmos_debug_step_times", "utmos_debug_counters", "utmos_set_option", "utmos_info", "utmos_timings", "utmos_timer_start", "utmos_timer_stop",
            "utmos_lzf_decompress", "utmos_lzf_compress", "utmos_h5_encode_chunks", "utmos_gz_size", "utmos_gz_inflate", "utmos_vcf_parse_gt", "utmos_device_alloc", "utmos_device_free",
            "utmos_device_to_host", "utmos_synth_packed_device"]
@@ -64,6 +64,7 @@ def lib():
         "utmos_finalize": (i32, [p, ctypes.POINTER(i64), p]),
         "utmos_select_begin": (i32, [p, p, p]),
         "utmos_select_steps": (i32, [p, i64, p, p, p, ctypes.POINTER(i64), ctypes.POINTER(i32)]),
+        "utmos_append_packed2": (i32, [p, p, p, i64, i32, p]),
         "utmos_select_export": (i32, [p, p, p, i64, p, p, p, i64, ctypes.POINTER(i64), ctypes.POINTER(i64),
                                       ctypes.POINTER(ctypes.c_int)]),
         "utmos_select_import": (i32, [p, p, p, p, i64, p, p, p, i64, i64, ctypes.c_int]),
@@ -190,6 +191,24 @@ class DeviceMatrix:
         """Rows already resident in HBM (raw device pointers as ints)."""
         check(lib().utmos_append_packed_device(self._ctx, ctypes.c_void_p(d_rows), n_rows, pitch,
                                                ctypes.c_void_p(d_af) if d_af else None))
+
+    def append_packed2(self, gt2, af=None):
+        """One `.jl` v2 part (utmos_b200/jl2.py): row-compressed rows, decoded on the GPU (utmos_append_packed2)."""
+        if "offsets" not in gt2:
+            from utmos_b200 import jl2  # pylint: disable=import-outside-toplevel
+            gt2 = jl2.with_offsets(gt2)
+        payload = np.ascontiguousarray(gt2["payload"], dtype=np.uint8)
+        offsets = np.ascontiguousarray(gt2["offsets"], dtype=np.uint64)
+        if int(gt2["n_samples"]) != self.n_samples:
+            raise ValueError("GT2 part has another sample count")
+        n = len(offsets) - 1
+        if af is not None:
+            af = np.ascontiguousarray(np.asarray(af, dtype=np.float64).reshape(-1))
+            if len(af) != n:
+                raise ValueError("AF length does not match the rows")
+        if len(payload) == 0:
+            payload = np.zeros(1, dtype=np.uint8)
+        check(lib().utmos_append_packed2(self._ctx, _ptr(payload), _ptr(offsets), n, int(gt2["idx_bytes"]), _ptr(af)))
 
     def append_dense(self, chunk):
         """One hdf5 chunk: bool/uint8 [n, S] or float32 [n, S] (GT*AF)."""

@@ -11,7 +11,7 @@ import logging
 import joblib
 import numpy as np
 
-from utmos_b200 import _native
+from utmos_b200 import _native, jl2
 from utmos_b200.logutil import setup_logging
 from utmos_b200.vcf import read_vcf_genotypes
 
@@ -24,6 +24,9 @@ _CONVERT_OPTIONS = (
     (("--lowmem",), dict(action="store_true", help="accepted for compatibility: the VCF is streamed block by block anyway")),
     (("-B", "--buffer"), dict(type=int, default=50000, help="variants per block (%(default)s)")),
     (("-c", "--compress"), dict(type=int, default=5, help="joblib compression level of the .jl file (%(default)s)")),
+    (("--pack2",), dict(action="store_true",
+                        help="write the row-compressed .jl v2 (the README's \"both axis pack\": rare variants as carrier lists; "
+                             "read by this `utmos select`, not by the reference)")),
 )
 
 
@@ -89,5 +92,8 @@ def cvt_main(cmdargs):
     rows, n_samples = data["GT"].shape[0], len(data["samples"])
     logging.info("Saving %d variants x %d samples (%d het, %d hom-alt calls)", rows, n_samples,
                  int(data["stats"]["num_het"]), int(data["stats"]["num_hom"]))
+    if args.pack2:
+        data["GT2"] = jl2.for_file(jl2.encode(data.pop("GT"), n_samples))
+        logging.info("Row-compressed rows: %d bytes for %d packed", len(data["GT2"]["payload"]), rows * ((n_samples + 7) // 8))
     joblib.dump(data, args.out_file, compress=args.compress)
     logging.info("Finished conversion")

@@ -392,6 +392,24 @@ bool is_pinned(const void *p)
     return attr.type == cudaMemoryTypeHost;
 }
 
+// pageable -> pinned staging with several host threads: one core copies at 10-14 GB/s, which is a quarter of what the
+// PCIe link takes (joblib.load hands the CLI pageable memory, so this is the path `utmos select a.jl` really uses)
+void staged_memcpy(void *dst, const void *src, size_t bytes)
+{
+    static const int n_threads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+    if (bytes < (8u << 20) || n_threads == 1) { memcpy(dst, src, bytes); return; }
+    const size_t piece = (bytes / (size_t)n_threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) {
+        const size_t off = piece * (size_t)t;
+        if (off >= bytes) break;
+        const size_t n = std::min(piece, bytes - off);
+        pool.emplace_back([=]() { memcpy((char *)dst + off, (const char *)src + off, n); });
+    }
+    memcpy(dst, src, std::min(piece, bytes));
+    for (auto &th : pool) th.join();
+}
+
 // host chunk pipeline: (pageable -> pinned staging ->) cudaMemcpyAsync on the copy stream -> ingest kernels
 int append_host(utmos_ctx *c, int kind, const void *src, long long n_rows, long long pitch_in, const double *af)
 {
@@ -421,7 +439,7 @@ int append_host(utmos_ctx *c, int kind, const void *src, long long n_rows, long 
         if (src_pinned) {
             UT_CUDA(cudaMemcpyAsync(c->d_stage[b], chunk, bytes, cudaMemcpyHostToDevice, c->copy_stream));
         } else {
-            memcpy(c->h_stage[b], chunk, bytes);
+            staged_memcpy(c->h_stage[b], chunk, bytes);
             UT_CUDA(cudaMemcpyAsync(c->d_stage[b], c->h_stage[b], bytes, cudaMemcpyHostToDevice, c->copy_stream));
         }
         const double *d_af_chunk = nullptr;
@@ -808,6 +826,75 @@ int utmos_append_packed(utmos_ctx *c, const uint8_t *rows, int64_t n_rows, int64
     if (pitch_bytes < (c->S + 7) / 8) { set_error("append_packed: pitch smaller than ceil(S/8)"); return UTMOS_E_ARG; }
     UT_CUDA(cudaSetDevice(c->device));
     return append_host(c, RAW_PACKED_MSB, rows, n_rows, pitch_bytes, af);
+}
+
+// .jl v2 rows: payload + offsets on the host; decoded on the GPU into the raw staging buffer, then
+// ingested exactly like utmos_append_packed rows (same filter, same order).
+int utmos_append_packed2(utmos_ctx *c, const uint8_t *payload, const uint64_t *offsets, int64_t n_rows, int idx_bytes,
+                         const double *af)
+{
+    if (!c) { set_error("null context"); return UTMOS_E_ARG; }
+    if (n_rows < 0 || (n_rows > 0 && (!payload || !offsets))) { set_error("append_packed2: bad arguments"); return UTMOS_E_ARG; }
+    if (idx_bytes != 2 && idx_bytes != 4) { set_error("append_packed2: idx_bytes must be 2 or 4"); return UTMOS_E_ARG; }
+    if (idx_bytes == 2 && c->S > 65536) { set_error("append_packed2: 16-bit indices need S <= 65536"); return UTMOS_E_ARG; }
+    if (c->finalized) { set_error("append after finalize"); return UTMOS_E_ARG; }
+    if (n_rows == 0) return UTMOS_OK;
+    const bool want_af = c->af_mode != UTMOS_AF_NONE;
+    if (want_af && !af) { set_error("append_packed2: AF required for an AF context"); return UTMOS_E_ARG; }
+    UT_CUDA(cudaSetDevice(c->device));
+    const long long pitch = (c->S + 7) / 8;
+    for (int64_t r = 0; r < n_rows; ++r)
+        if (offsets[r + 1] < offsets[r] || offsets[r + 1] - offsets[r] > (uint64_t)pitch) {
+            set_error("append_packed2: row offsets must ascend by at most ceil(S/8) bytes");
+            return UTMOS_E_ARG;
+        }
+    UT_TRY(grow_rows(c, c->rows_upper + n_rows));
+    const long long chunk_rows = std::max(1ll, (long long)(kStageBytes / (size_t)pitch));
+    UT_TRY(ensure_stage(c, want_af ? std::min<long long>(chunk_rows, n_rows) : 0, false));
+    uint8_t *d_payload = nullptr;
+    unsigned long long *d_off = nullptr;
+    int *d_bad = nullptr;
+    const size_t pay_cap = (size_t)std::min<long long>(chunk_rows, n_rows) * (size_t)pitch;
+    UT_TRY(dev_alloc(c, (void **)&d_payload, pay_cap));
+    UT_TRY(dev_alloc(c, (void **)&d_off, ((size_t)std::min<long long>(chunk_rows, n_rows) + 1) * 8));
+    UT_TRY(dev_alloc(c, (void **)&d_bad, 4));
+    UT_CUDA(cudaMemsetAsync(d_bad, 0, 4, c->stream));
+    int rc = UTMOS_OK;
+    for (long long r0 = 0; r0 < n_rows && rc == UTMOS_OK; r0 += chunk_rows) {
+        const long long n = std::min<long long>(chunk_rows, n_rows - r0);
+        const int b = c->stage_next;
+        c->stage_next ^= 1;
+        if (c->stage_used[b]) UT_CUDA(cudaEventSynchronize(c->ev_consumed[b]));
+        const size_t bytes = (size_t)(offsets[r0 + n] - offsets[r0]);
+        t_begin(c, T_H2D, c->stream);
+        if (bytes) UT_CUDA(cudaMemcpyAsync(d_payload, payload + offsets[r0], bytes, cudaMemcpyHostToDevice, c->stream));
+        UT_CUDA(cudaMemcpyAsync(d_off, offsets + r0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        const double *d_af_chunk = nullptr;
+        if (want_af) {
+            UT_CUDA(cudaMemcpyAsync(c->d_af_stage[b], af + r0, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+            d_af_chunk = c->d_af_stage[b];
+        }
+        t_end(c, c->stream);
+        t_begin(c, T_INGEST, c->stream);
+        rc = launch_unpack_rows2(c->stream, d_payload, d_off, n, (int)c->S, pitch, idx_bytes, (uint8_t *)c->d_stage[b], d_bad,
+                                 &c->n_launch);
+        if (rc == UTMOS_OK)
+            rc = launch_ingest(c->stream, c->scratch, RAW_PACKED_MSB, c->d_stage[b], n, pitch, d_af_chunk, (int)c->S, c->pitchW,
+                               c->d_rows, want_af ? c->d_af : nullptr, c->d_nrows, &c->n_launch);
+        t_end(c, c->stream);
+        UT_CUDA(cudaEventRecord(c->ev_consumed[b], c->stream));
+        c->stage_used[b] = true;
+        UT_CUDA(cudaStreamSynchronize(c->stream));            // d_payload / d_off are reused by the next chunk
+    }
+    int bad = 0;
+    if (rc == UTMOS_OK) UT_CUDA(cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost));
+    dev_free(c, d_payload, pay_cap);
+    dev_free(c, d_off, ((size_t)std::min<long long>(chunk_rows, n_rows) + 1) * 8);
+    dev_free(c, d_bad, 4);
+    if (rc != UTMOS_OK) return rc;
+    c->rows_upper += n_rows;
+    if (bad) { set_error("append_packed2: " + std::to_string(bad) + " rows are malformed (index >= S or ragged length)"); return UTMOS_E_DATA; }
+    return UTMOS_OK;
 }
 
 int utmos_append_packed_device(utmos_ctx *c, const uint8_t *d_rows, int64_t n_rows, int64_t pitch_bytes,

@@ -238,6 +238,9 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
                   long long pitch_in, const double *af_in, int S, int pitchW, uint32_t *rows_out, double *af_out,
                   long long *d_nrows, int *n_launch);
 
+int launch_unpack_rows2(cudaStream_t stream, const uint8_t *payload, const unsigned long long *off, long long n_rows, int S,
+                        long long pitch, int idx_bytes, uint8_t *raw_out, int *bad, int *n_launch);
+
 int launch_lzf_unpack_bool(cudaStream_t stream, const uint8_t *blob, const long long *off, const int *len,
                            const uint8_t *stored_raw, long long n_chunks, int rows_per_chunk, long long rows_in_batch,
                            int S, int pitchW, long long row0, uint32_t *rows_out, long long *d_nrows, int *bad,

@@ -949,6 +949,72 @@ int launch_ingest(cudaStream_t stream, IngestScratch &sc, int kind, const void *
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ".jl v2" rows (the "both axis pack" the reference's README floats, README.md:59-63): a row is stored
+// either as its np.packbits bytes (length == pitch) or, when that is shorter, as the list of its carriers' sample
+// indices (little-endian uint16 / uint32).  One warp per row rebuilds the MSB-first packed bytes in shared memory and
+// writes them to the raw staging buffer the ingest kernel reads, so PCIe carries ~10x fewer bytes for a sparse cohort.
+// bad[0] counts rows whose encoding is malformed (length not a whole number of indices, index >= S).
+// ------------------------------------------------------------------------------------------------
+template <int IDX_BYTES>
+__global__ void __launch_bounds__(256) unpack_rows2_kernel(const uint8_t *__restrict__ payload,
+                                                           const unsigned long long *__restrict__ off, long long n_rows,
+                                                           int S, long long pitch, uint8_t *__restrict__ raw_out, int *bad)
+{
+    extern __shared__ __align__(16) uint32_t u_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int row_words = (int)((pitch + 3) >> 2);
+    uint32_t *s_row = u_smem + (size_t)wib * row_words;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned long long off0 = off[0];
+    for (long long r = warp0; r < n_rows; r += nwarps) {
+        const unsigned long long b = off[r] - off0, e = off[r + 1] - off0;
+        const long long len = (long long)(e - b);
+        const uint8_t *src = payload + b;
+        uint8_t *out = raw_out + r * pitch;
+        if (len == pitch) {
+            for (long long k = lane; k < pitch; k += 32) out[k] = src[k];
+            continue;
+        }
+        for (int k = lane; k < row_words; k += 32) s_row[k] = 0u;
+        __syncwarp();
+        bool ok = len >= 0 && len % IDX_BYTES == 0 && len < pitch;
+        const long long n = ok ? len / IDX_BYTES : 0;
+        for (long long i = lane; i < n; i += 32) {
+            unsigned int idx = (unsigned int)src[i * IDX_BYTES] | ((unsigned int)src[i * IDX_BYTES + 1] << 8);
+            if (IDX_BYTES == 4) idx |= ((unsigned int)src[i * 4 + 2] << 16) | ((unsigned int)src[i * 4 + 3] << 24);
+            if (idx >= (unsigned int)S) { ok = false; continue; }
+            atomicOr(s_row + (idx >> 5), 1u << (8u * ((idx >> 3) & 3u) + 7u - (idx & 7u)));       // MSB-first within the byte
+        }
+        __syncwarp();
+        for (long long k = lane; k < pitch; k += 32) out[k] = (uint8_t)(s_row[k >> 2] >> (8 * (k & 3)));
+        if (__any_sync(0xffffffffu, !ok) && lane == 0) atomicAdd(bad, 1);
+        __syncwarp();
+    }
+}
+
+int launch_unpack_rows2(cudaStream_t stream, const uint8_t *payload, const unsigned long long *off, long long n_rows, int S,
+                        long long pitch, int idx_bytes, uint8_t *raw_out, int *bad, int *n_launch)
+{
+    if (n_rows <= 0) return UTMOS_OK;
+    const size_t smem = (size_t)8 * (size_t)((pitch + 3) / 4) * 4;
+    if (smem > 200 * 1024) { set_error("unpack_rows2: row too wide for the on-chip row buffer"); return UTMOS_E_ARG; }
+    static size_t configured[2] = {0, 0};
+    const int which = idx_bytes == 4 ? 1 : 0;
+    if (smem > configured[which]) {
+        if (which) UT_CUDA(cudaFuncSetAttribute(unpack_rows2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else UT_CUDA(cudaFuncSetAttribute(unpack_rows2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[which] = smem;
+    }
+    const unsigned grid = (unsigned)std::min<long long>((n_rows + 7) / 8, 148ll * 8);
+    if (which) unpack_rows2_kernel<4><<<grid, 256, smem, stream>>>(payload, off, n_rows, S, pitch, raw_out, bad);
+    else unpack_rows2_kernel<2><<<grid, 256, smem, stream>>>(payload, off, n_rows, S, pitch, raw_out, bad);
+    *n_launch += 1;
+    UT_CUDA(cudaGetLastError());
+    return UTMOS_OK;
+}
+
 // hdf5 bool chunks decoded on the GPU.  blob/off/len/stored_raw: device copies of the compressed chunks of one batch;
 // the rows go to rows_out[(row0 + chunk * rows_per_chunk + r) * pitchW] and *d_nrows grows by rows_in_batch.
 // Returns UTMOS_E_ARG when a chunk does not fit the kernel's shared-memory bit buffer (caller falls back).

@@ -76,6 +76,9 @@ class ShardedMatrix:
     def append_packed(self, gt, af=None):
         self.local.append_packed(gt, af)
 
+    def append_packed2(self, gt2, af=None):
+        self.local.append_packed2(gt2, af)
+
     def append_packed_device(self, d_rows, n_rows, pitch, d_af=None):
         self.local.append_packed_device(d_rows, n_rows, pitch, d_af)
 

@@ -17,7 +17,7 @@ import joblib
 import numpy as np
 import pandas as pd
 
-from utmos_b200 import _native, h5lite
+from utmos_b200 import _native, h5lite, jl2
 from utmos_b200.convert import read_vcf
 from utmos_b200.logutil import setup_logging
 
@@ -262,16 +262,22 @@ def load_files(in_files, lowmem=None, buffer=32768, calc_af=False, device=0, fla
             logging.error("Unknown filetype %s. Expected `.vcf[.gz]`, `.jl`", i)
             sys.exit(1)
 
+        packed2 = jl2.with_offsets(dat["GT2"]) if "GT" not in dat and "GT2" in dat else None     # `.jl` v2 (jl2.py)
+        part_rows = jl2.n_rows(packed2) if packed2 is not None else dat["GT"].shape[0]
         if samples is None:
             samples = np.asarray(dat["samples"]).astype("S")
-            matrix = _new_matrix(len(samples), af_mode, dat["GT"].shape[0] * len(in_files), device, flags, comm)
+            matrix = _new_matrix(len(samples), af_mode, part_rows * len(in_files), device, flags, comm)
             if lowmem is not None and (comm is None or comm.rank == 0):
                 writer = h5lite.H5Writer(lowmem, samples, float_data=calc_af)     # rank 0 writes the whole file
-        r_begin, r_end = _my_rows(dat["GT"].shape[0], comm)                       # under torchrun: this rank's rows
-        matrix.append_packed(dat["GT"][r_begin:r_end], np.asarray(dat["AF"])[r_begin:r_end] if calc_af else None)
+        r_begin, r_end = _my_rows(part_rows, comm)                                # under torchrun: this rank's rows
+        part_af = np.asarray(dat["AF"])[r_begin:r_end] if calc_af else None
+        if packed2 is not None:
+            matrix.append_packed2(jl2.slice_rows(packed2, r_begin, r_end), part_af)   # decoded on the GPU
+        else:
+            matrix.append_packed(dat["GT"][r_begin:r_end], part_af)
         if writer is not None:
-            writer.append_packed(dat["GT"], dat["AF"])
-        load_row_count += dat["GT"].shape[0]
+            writer.append_packed(jl2.decode(packed2) if packed2 is not None else dat["GT"], dat["AF"])
+        load_row_count += part_rows
         logging.debug("Loaded %d of %d (%.2f%%) with %d vars", load_count + 1, len(in_files),
                       (load_count + 1) / len(in_files) * 100, load_row_count)
 
