@@ -618,12 +618,13 @@ def test_jl2_rows_decoded_on_the_gpu_equal_packed_rows(n_samples, n_vars):
     out = []
     for kind in ("v1", "v2"):
         dm = _native.DeviceMatrix(n_samples, _native.AF_F64)
+        cut = n_vars // 3
         if kind == "v1":
-            dm.append_packed(gt[:1000], af[:1000])
-            dm.append_packed(gt[1000:], af[1000:])
+            dm.append_packed(gt[:cut], af[:cut])
+            dm.append_packed(gt[cut:], af[cut:])
         else:
-            dm.append_packed2(jl2.slice_rows(g2, 0, 1000), af[:1000])
-            dm.append_packed2(jl2.slice_rows(g2, 1000, n_vars), af[1000:])
+            dm.append_packed2(jl2.slice_rows(g2, 0, cut), af[:cut])
+            dm.append_packed2(jl2.slice_rows(g2, cut, n_vars), af[cut:])
         vc = dm.finalize()
         dm.begin(mask)
         idx, new, score, stop = dm.steps(60)

@@ -59,7 +59,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except OSError:
         pass
-    print(json.dumps({"kernel": "gt_pack_af_direct_kernel" if (2 * s) % 16 == 0 else "gt_pack_af_tile_kernel", "variants": v, "samples": s, "exceptions": "scattered" if args.scatter else "row-clustered", "kernel_ms": best,
+    print(json.dumps({"kernel": "gt_pack_af_direct_kernel" if (2 * s) % 16 == 0 else "gt_pack_af_unaligned_kernel", "variants": v, "samples": s, "exceptions": "scattered" if args.scatter else "row-clustered", "kernel_ms": best,
                       "algorithmic_bytes": alg, "GBps": alg / 1e9 / (best / 1e3), "frac_of_measured_peak": alg / 1e9 / (best / 1e3) / peak,
                       "host_call_wall_ms_incl_pcie": wall * 1e3, "num_het": int(het), "num_hom": int(hom)}))
 

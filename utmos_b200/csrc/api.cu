@@ -652,6 +652,10 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.tail_budget = c->tail_budget;
     // N ranks: N times the rows per pick at the same sparsity (measured on 4 x B200: 1536 per rank beats 2048)
     p.tail_rows = c->mg_world > 1 ? std::min(c->tail_rows, 1536u) * (unsigned int)c->mg_world : c->tail_rows;
+    // one GPU, many rows: a pick covers rows in proportion to V, so the hand-over point moves with it (8 x 1,103,547 rows
+    // x 2,504 samples: 46.5 ms with 16,384 against 73.1 ms with 2,048; the 1kGP shape keeps 2,048)
+    if (c->mg_world == 1 && c->tail_rows == 2048u && c->S <= 65535)
+        p.tail_rows = (unsigned int)std::min<long long>(std::max<long long>(2048, c->V / 540), 1 << 20);
     p.dbg_time = c->dbg_time;
     p.dsmem_gains = (c->flags & UTMOS_F_DSMEM_GAINS) ? 1 : 0;
     p.st = c->d_state;
@@ -1333,6 +1337,8 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         // every gain from the sample-major copy (regain_kernel).  Default since round 2 (full GPU suite green with it,
         // greedy loop 9.83 -> 9.06 ms on the 1kGP shape); UTMOS_B200_DECREMENT=0 goes back to regain_kernel for A/B runs.
         static const bool use_decrement = !(getenv("UTMOS_B200_DECREMENT") && atoi(getenv("UTMOS_B200_DECREMENT")) == 0);
+        // (AF flavours keep regain_kernel: a tiled AF decrement over the newly covered rows was measured on config C3 and
+        // bought nothing -- head 4.96 ms against 4.76 ms -- because that head is bound by the cluster kernel's own steps)
         if (use_decrement && !multi && !af && CL > 0 && c->d_cols && !c->d_newmask && !(c->flags & UTMOS_F_STEP_KERNELS))
             UT_TRY(dev_alloc(c, (void **)&c->d_newmask, (size_t)c->colPitchW * 4));
         // Head: greedy steps by the cluster (or grid-wide, or multi-GPU) kernel; a pick that covers very many rows

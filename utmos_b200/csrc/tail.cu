@@ -284,6 +284,20 @@ __device__ __forceinline__ Cand warp_argmax(Cand c)
     return out;
 }
 
+// 64-bit add on shared memory from two native 32-bit atomics.  atomicAdd(unsigned long long *) on shared memory is a
+// compare-and-swap loop on sm_100a (SASS: ATOMS.CAST.SPIN.64); the AF flavours retire two 64-bit limbs per decrement,
+// so that loop bounded their tail.  The low word's atomic returns the old value, which tells exactly whether THIS add
+// wrapped; the wrap is folded into the high word's add.  Sums are exact modulo 2^64 whatever the interleaving; readers
+// only look after a barrier.
+__device__ __forceinline__ void smem_add64(unsigned long long *p, unsigned long long v)
+{
+    unsigned int *w = reinterpret_cast<unsigned int *>(p);
+    const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+    const unsigned int old = atomicAdd(w, lo);
+    const unsigned int carry = (old + lo) < old ? 1u : 0u;
+    if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+
 struct TailCfg {
     int off_lo, off_hi, off_w, off_mask, off_loff, off_llen, off_live;   // byte offsets, counts at 0
     int live_words;      // > 0: live mask held in shared memory
@@ -544,7 +558,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                 if (cs != kPad && UT_OWNED(cs)) {
                     n_pool += 1;
                     atomicAdd(s_cnt + UT_LI(cs), 0xffffffffu);
-                    if (AF) { atomicAdd(s_lo + UT_LI(cs), gl); atomicAdd(s_hi + UT_LI(cs), gh); }
+                    if (AF) { smem_add64(s_lo + UT_LI(cs), gl); smem_add64(s_hi + UT_LI(cs), gh); }
                 }
             }
         };
@@ -583,9 +597,20 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     // a row appears once in a list, so nobody else clears this bit during the walk: test with a plain
                     // load (shared-memory atomics cost ~2 cycles per lane) and clear only the bits that are set
                     const uint32_t bit = 1u << (r & 31);
-                    uint32_t *lw = (live_smem ? s_live : g_live) + (r >> 5);
-                    fresh = (*reinterpret_cast<volatile uint32_t *>(lw) & bit) != 0;
-                    if (fresh) atomicAnd(lw, ~bit);
+                    if (live_smem) {
+                        uint32_t *lw = s_live + (r >> 5);
+                        fresh = (*reinterpret_cast<volatile uint32_t *>(lw) & bit) != 0;
+                        if (fresh) atomicAnd(lw, ~bit);
+                    } else {
+                        // live mask in global memory (more rows than one SM holds, e.g. the merged rows of several GPUs):
+                        // the old value is not needed, so clear the bit with a fire-and-forget RED instead of an atomic
+                        // that waits for its answer (ncu r2: 22 % of the stall samples of this kernel sat on that wait)
+                        uint32_t *lw = g_live + (r >> 5);
+                        uint32_t cur;
+                        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(cur) : "l"(lw) : "memory");
+                        fresh = (cur & bit) != 0;
+                        if (fresh) asm volatile("red.global.and.b32 [%0], %1;" ::"l"(lw), "r"(~bit) : "memory");
+                    }
                 }
                 // narrow entry: {row, n | c0 << 16, c1 | c2 << 16, c3 | c4 << 16}; wide entry: {row, n, c0, c1};
                 // pooled (n == all ones): {row, pooled, first pool element, carriers}
@@ -608,7 +633,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
                     for (int j = 0; j < kInl; ++j) {
                         if (j < (int)n && UT_OWNED(c[j])) {
                             atomicAdd(s_cnt + UT_LI(c[j]), 0xffffffffu);
-                            if (AF) { atomicAdd(s_lo + UT_LI(c[j]), nl); atomicAdd(s_hi + UT_LI(c[j]), nh); }
+                            if (AF) { smem_add64(s_lo + UT_LI(c[j]), nl); smem_add64(s_hi + UT_LI(c[j]), nh); }
                         }
                     }
                 }
