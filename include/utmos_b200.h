@@ -52,6 +52,8 @@ typedef struct utmos_ctx utmos_ctx;
 #define UTMOS_F_FORCE_TRANSPOSE 4u   /* fail instead of falling back when the sample-major copy does not fit */
 #define UTMOS_F_NO_CLUSTER 8u        /* grid-wide persistent kernel instead of the one-cluster DSMEM kernel */
 #define UTMOS_F_NO_TAIL 16u          /* never switch to the single-CTA list-driven tail kernel */
+#define UTMOS_F_REF_TIES 64u         /* --af: order exact-arithmetic (near-)ties by replaying the reference's sequential float64 sums
+                                      * (utmos/select.py:37-48); implies UTMOS_F_STEP_KERNELS and needs the sample-major copy */
 #define UTMOS_F_DSMEM_GAINS 32u      /* cluster kernel keeps the gains in distributed shared memory (default: L2 atomics) */
 
 /* stop reasons reported by utmos_select_steps (utmos/select.py:91, :51-52/:93-96, :110-112) */

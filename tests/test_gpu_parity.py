@@ -184,6 +184,53 @@ def test_random_cases_match_reference_and_exact_oracle(flags):
     assert near_ties == H.NEAR_TIE_CASES
 
 
+def test_ref_ties_reproduces_the_reference_order_on_every_recorded_af_case():
+    """UTMOS_F_REF_TIES: candidates whose exact scores (nearly) tie are ordered by replaying the reference's sequential
+    float64 sums (utmos/select.py:37-48).  All 72 recorded `--af` cases -- including the 13 pinned near-tie cases that the
+    exact-arithmetic order gets differently -- must give the unmodified reference's report, and scores within 1e-9."""
+    cases, arrays = H.random_cases()
+    checked = 0
+    for pos, case in enumerate(cases):
+        opt = case["options"]
+        if not opt["af"]:
+            continue
+        packed, af, names = H.case_inputs(case, arrays)
+        n = case["n_samples"]
+        cuts = arrays[f"cuts_{case['case']}"]
+        mask = orc.build_mask(names, opt["subset"], opt["exclude"])
+        wts = orc.build_weights(names, opt["weights"]) if opt["weights"] is not None else None
+        steps = orc.resolve_count(opt["count"], n)
+        parts = [packed[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+        afs = [af[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+        idx, new, score, _stop, var_count, num_vars, _ = run_gpu(parts, afs, n, mask, wts, steps, _native.AF_F64, _native.F_REF_TIES)
+        rows = orc.report_rows(names, var_count, idx, new, num_vars)
+        got = [[r[0], r[1], r[2], r[3], str(r[4])] for r in rows]
+        gold = [[g[0], g[1], g[2], g[3], g[5]] for g in case["rows"]]
+        assert got == gold, (pos, case["case"], opt)
+        np.testing.assert_allclose(score, case["argmax_scores"][:len(score)], rtol=1e-9)
+        checked += 1
+    assert checked == 72
+
+
+def test_ref_ties_full_af_ordering_and_cli(tmp_path):
+    """The 855-row `--af` ordering of the fixtures and the `--af` answer keys with --ref-ties (same reports as without:
+    the fixtures have no near-tie that the exact order resolves differently)."""
+    gold = H.golden_json("full_order_af.json")
+    parts = H.load_jl_parts(gold["files"])
+    names = np.asarray(parts[0]["samples"]).astype(str)
+    n = len(names)
+    idx, new, score, _stop, var_count, num_vars, _ = run_gpu([p["GT"] for p in parts], [p["AF"] for p in parts], n,
+                                                             np.ones(n, np.uint8), None, n, _native.AF_F64, _native.F_REF_TIES)
+    assert [names[i] for i in idx] == [g[0] for g in gold["rows"]]
+    assert [int(x) for x in new] == [g[2] for g in gold["rows"]]
+    np.testing.assert_allclose(score, gold["argmax_scores"][:len(score)], rtol=1e-12)
+    out = tmp_path / "r.txt"
+    usel.select_main(["-c", "20", "--af", "--ref-ties", "-o", str(out), H.fixture("chunk0.jl"), H.fixture("chunk1.jl")])
+    assert out.read_text() == H.answer_key("select_af.txt")
+    usel.select_main(["--af", "--ref-ties", "--maxmem", "1", "-c", "20", "-o", str(out), H.fixture("tiny.af.hdf5")])
+    assert out.read_text() == H.answer_key("select_af_h5.txt")
+
+
 def test_step_batches_equal_one_shot():
     """utmos_select_steps is resumable: 7-step batches give the same rows as one call."""
     gold = H.golden_json("full_order_count.json")

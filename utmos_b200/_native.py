@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libutmos_b200.so")
 
 AF_NONE, AF_F64, AF_F32 = 0, 1, 2
-F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL, F_DSMEM_GAINS = 1, 2, 4, 8, 16, 32
+F_NO_TRANSPOSE, F_STEP_KERNELS, F_FORCE_TRANSPOSE, F_NO_CLUSTER, F_NO_TAIL, F_DSMEM_GAINS, F_REF_TIES = 1, 2, 4, 8, 16, 32, 64
 STOP_NONE, STOP_ZERO, STOP_ALL = 0, 1, 2
 E_NOGPU = -3
 

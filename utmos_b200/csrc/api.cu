@@ -632,6 +632,9 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.mask = c->d_mask;
     p.selw = c->d_selw;
     p.weights = c->has_weights ? c->d_weights : nullptr;
+    p.af_vals = c->d_af;
+    p.ref_ties = (c->flags & UTMOS_F_REF_TIES) ? 1 : 0;
+    p.af_f32 = c->af_mode == UTMOS_AF_F32 ? 1 : 0;
     p.out_idx = c->d_out_idx;
     p.out_new = c->d_out_new;
     p.out_score = c->d_out_score;
@@ -764,6 +767,7 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
     c->pitchW = (c->nW + 3) / 4 * 4;
     c->af_mode = af_mode;
     c->flags = flags;
+    if (flags & UTMOS_F_REF_TIES) c->flags |= UTMOS_F_STEP_KERNELS;        // the replay lives in argmax_step_kernel
     // --af: the 8-CTA owner-computes flavour of the tail until a pick covers fewer than 64 rows (three shared-memory
     // atomics per decrement, two of them 64-bit: measured 10.0 ms against 11.9 ms for the tail of config C3)
     if (af_mode != UTMOS_AF_NONE) c->tail_single_rows = 64;

@@ -67,6 +67,9 @@ struct SelParams {
     uint8_t *mask;                     // [S] working copy of sample_mask
     const uint32_t *selw;              // [nW] bit s set = sample s was selectable (mask == 1) at select_begin
     const double *weights;             // [S] or null
+    const double *af_vals;             // [V] per-row AF as given (UTMOS_F_REF_TIES replays the reference's float64 sums from it)
+    int ref_ties;                      // 1: order exact-arithmetic near-ties like the reference does (step-kernel flavour)
+    int af_f32;                        // 1: the rows are float32 GT*AF (hdf5 flavour): AF rounds through float first
     long long *out_idx;                // [S] report rows
     long long *out_new;
     double *out_score;

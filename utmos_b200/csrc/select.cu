@@ -604,17 +604,94 @@ __device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long
 // ------------------------------------------------------------------------------------------------
 // step-kernel flavour (UTMOS_F_STEP_KERNELS): two launches per step, replayed from a CUDA graph
 // ------------------------------------------------------------------------------------------------
+// UTMOS_F_REF_TIES (--af only): the reference adds the float64 AF of the uncovered rows that carry a sample one after the
+// other in row order (utmos/select.py:37-40), so two samples whose exact sums tie -- or nearly tie -- are ordered by the
+// rounding noise of those sequential sums.  The exact fixed-point scores decide everything else; for the candidates within
+// 2^-30 relative of the best exact score (the reference's accumulated error is below V * 2^-53 <= 2^-32) one warp per
+// candidate replays the reference's sum: the live rows of its sample-major row in ascending order, one float64 add each
+// (the lanes locate the set bits, the adds stay strictly sequential), times the weight (:47); the first maximum wins (:48).
+__device__ __forceinline__ double replay_reference_sum(const SelParams &p, int t, int lane)
+{
+    const uint32_t *col = p.cols + (long long)t * p.colPitchW;
+    const long long words = (p.V + 31) >> 5;
+    double acc = 0.0;
+    for (long long w0 = 0; w0 < words; w0 += 32) {
+        const long long w = w0 + lane;
+        uint32_t x = w < words ? (__ldg(col + w) & __ldcg(p.live + w)) : 0u;
+        unsigned int m = __ballot_sync(0xffffffffu, x != 0u);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            if (lane == l) {
+                double a = acc;
+                while (x) {
+                    const long long r = (w << 5) + (__ffs(x) - 1);
+                    x &= x - 1;
+                    double v = __ldg(p.af_vals + r);
+                    if (p.af_f32) v = (double)(float)v;          // hdf5 flavour: float32 GT*AF rows (utmos/select.py:218-223)
+                    a += v;
+                }
+                acc = a;
+            }
+            acc = __shfl_sync(0xffffffffu, acc, l);
+        }
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(1024) argmax_step_kernel(SelParams p)
 {
     __shared__ Best s_red[32];
+    __shared__ int s_cand[1024];
+    __shared__ int s_ncand;
     SelState *st = p.st;
     const bool idle = st->stop != 0 || st->step >= st->limit;
+    if (threadIdx.x == 0) s_ncand = 0;
     __syncthreads();
     if (idle) {
         if (threadIdx.x == 0) st->winner = -1;
         return;
     }
     Best b = block_best(scan_best(p, 0, p.S), s_red);
+    if (p.ref_ties && p.af && p.cols && p.af_vals && b.score > 0.0) {
+        const double thr = b.score * (1.0 - 9.313225746154785e-10);        // 2^-30
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        // how many candidates are there at all?  (one: the exact winner stands)
+        int mine = 0;
+        for (int s = (int)threadIdx.x; s < p.S; s += 1024) {
+            double sc;
+            unsigned int c;
+            sample_score(p, s, &sc, &c);
+            mine += sc >= thr ? 1 : 0;
+        }
+        const int holders = __syncthreads_count(mine > 0);                  // threads that hold a candidate
+        const bool several = __syncthreads_or(mine > 1) || holders > 1;
+        if (several) {
+            Best rb{-1.0e308, 0x7fffffff, 0u};
+            for (int base = 0; base < p.S; base += 1024) {                 // at most 1,024 candidates per round
+                const int s = base + (int)threadIdx.x;
+                if (s < p.S) {
+                    double sc;
+                    unsigned int c;
+                    sample_score(p, s, &sc, &c);
+                    if (sc >= thr) s_cand[atomicAdd(&s_ncand, 1)] = s;
+                }
+                __syncthreads();
+                const int n = s_ncand;
+                for (int i = warp; i < n; i += 32) {
+                    const int t = s_cand[i];
+                    double f = replay_reference_sum(p, t, lane);
+                    if (p.weights) f *= __ldg(p.weights + t);
+                    if (lane == 0 && arg_better(f, t, rb.score, rb.idx)) { rb.score = f; rb.idx = t; rb.cnt = __ldcg(p.gain_cnt + t); }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) s_ncand = 0;
+                __syncthreads();
+            }
+            if (lane != 0) rb = Best{-1.0e308, 0x7fffffff, 0u};
+            b = block_best(rb, s_red);
+        }
+    }
     if (threadIdx.x == 0) {
         if (p.S == 0 || b.score == 0.0) {                 // utmos/select.py:51-52
             st->stop = UTMOS_STOP_ZERO;

@@ -342,6 +342,9 @@ _SELECT_OPTIONS = (
     )),
     ("Scoring", (
         (("--af",), dict(action="store_true", help="score a variant by its allele frequency instead of 1")),
+        (("--ref-ties",), dict(action="store_true",
+                               help="with --af: order samples whose exact scores tie (or nearly tie) the way the reference's "
+                                    "sequential float64 sums do; slower per-step kernels (not in the reference: it IS the reference's order)")),
         (("--weights",), dict(type=str, default=None, help="TSV of sample<TAB>weight; scores are multiplied by it")),
         (("--subset",), dict(type=str, default=None, action="append",
                              help="only these samples can be picked: a file of names or a comma separated list (repeatable)")),
@@ -419,7 +422,10 @@ def select_main(cmdargs):
     global MAXMEM  # pylint: disable=global-statement
     args = parse_args(cmdargs)
     comm = _torchrun_comm(args)
-    data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device, comm=comm)
+    flags = _native.F_REF_TIES if (args.ref_ties and args.af) else 0
+    if flags and comm is not None:
+        _fail("--ref-ties is not available on several GPUs")
+    data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device, flags=flags, comm=comm)
     stored_af = data["data"].dtype != bool                   # float data = GT * AF, made with --af
     if args.af and not stored_af:
         logging.critical("HDF5 file doesn't appear to be created with --af weighted scores, remove --af or recreate hdf5")
