@@ -4,11 +4,14 @@
     python oracle/make_golden_full.py cohort      # seed-0 synthetic cohort 2,504 x 1,103,547 -> /tmp cache (NumPy mirror)
     python oracle/make_golden_full.py c2          # count mode, --count -1                -> tests/golden/c2_full_order.npz
     python oracle/make_golden_full.py c3          # --af --weights --subset --exclude -1  -> tests/golden/c3_full_order.npz
+    python oracle/make_golden_full.py c3ref       # the same in the REFERENCE's float64 order -> tests/golden/c3ref_full_order.npz
 
 The cohort is the NumPy mirror (utmos_b200/synth.py:mirror_rows) of the device generator, i.e. the rows bench.py and
 tools/run_configs.py select from.  The orderings come from oracle/greedy_oracle.c (utmos/select.py:24-53, :69-112 restated
 on packed bits; pinned to the unmodified reference by tests/test_oracle.py), one thread, minutes per config in the
-build container.  C3 uses the exact (fixed-point) score mode, the arithmetic the CUDA --af path is bit-equal to.
+build container.  C3 uses the exact (fixed-point) score mode, the arithmetic the CUDA --af path is bit-equal to; c3ref uses
+mode 0 -- sequential float64 sums in row order, utmos/select.py:37-41, bit-identical to the reference's doubles -- which is
+what `--ref-ties` (UTMOS_F_REF_TIES) reproduces: at this shape the two orders part at pick 225 of 1,239.
 """
 import hashlib
 import os
@@ -78,7 +81,7 @@ def run(config):
         mask, weights, afs, exact = np.ones(N_SAMPLES, np.uint8), None, None, False
     else:
         mask, weights = c3_setup()
-        afs, exact = af, True
+        afs, exact = af, config == "c3"
     idx, new, score, stop = orc.greedy_c(rows, N_SAMPLES, mask, weights, afs, N_SAMPLES, exact=exact)
     sec = time.perf_counter() - t0
     out = os.path.join(GOLD, f"{config}_full_order.npz")

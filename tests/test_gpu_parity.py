@@ -595,6 +595,30 @@ def test_full_shape_properties_and_mode_agreement():
     assert np.array_equal(vc, gold["var_count"])
 
 
+def test_full_shape_c3_ref_ties_matches_reference_order_oracle():
+    """Config C3 at its named shape with UTMOS_F_REF_TIES: every pick and new_count equals the plain-C oracle's run in the
+    REFERENCE's arithmetic (mode 0: sequential float64 sums in row order, utmos/select.py:37-41; 150 s on one CPU core),
+    which parts from the exact-arithmetic order at pick 225 of 1,239; winning scores within 1e-12."""
+    n_vars, n_samples = 1_103_547, 2504
+    gold = np.load(os.path.join(H.GOLD, "c3ref_full_order.npz"))
+    exact = np.load(os.path.join(H.GOLD, "c3_full_order.npz"))
+    assert not np.array_equal(gold["idx"], exact["idx"])           # the two orders really differ at this shape
+    names = synth.sample_names(n_samples)
+    weights = synth.synthetic_weights(n_samples)
+    mask = np.where(np.isin(names, names[: n_samples // 2]), 1, 2).astype(np.uint8)
+    mask = np.where(np.isin(names, names[::97]), 2, mask).astype(np.uint8)
+    coh = synth.DeviceCohort(0, n_vars, n_samples)
+    dm = _native.DeviceMatrix(n_samples, _native.AF_F64, rows_hint=n_vars, flags=_native.F_REF_TIES)
+    dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
+    dm.finalize()
+    dm.begin(mask, weights)
+    idx, new, score, stop = dm.steps(n_samples)
+    dm.close()
+    coh.close()
+    assert np.array_equal(idx, gold["idx"]) and np.array_equal(new, gold["new"]) and stop == int(gold["stop"])
+    np.testing.assert_allclose(score, gold["score"], rtol=1e-12)
+
+
 def test_full_shape_c3_matches_oracle_golden():
     """Config C3 at its named shape (2,504 x 1,103,547, --af --weights --subset --exclude, --count -1): every pick,
     new_count and winning float64 score equals the plain-C oracle's exact-arithmetic run (155 s on one CPU core)."""
