@@ -278,18 +278,19 @@ def main():
         comm = HostCollectives()
 
     def one_selection(resident, rows_dev=None, rows_host=None, rows_n=None, af_dev=None, single=False, af_mode_=None,
-                      mask_=None, weights_=None):
+                      mask_=None, weights_=None, flags_=None):
         """One complete selection.  Default inputs: this rank's cohort; `single` forces the one-GPU code path."""
         rows_n = n_vars if rows_n is None else rows_n
         mode = af_mode if af_mode_ is None else af_mode_
         msk = mask if mask_ is None else mask_
         wts = weights if weights_ is None and mask_ is None else weights_
         t = [time.perf_counter()]
+        fl = args.flags if flags_ is None else flags_
         if world > 1 and not single:
-            sm = ShardedMatrix(n_samples, mode, rows_hint=rows_n, device=device, flags=args.flags, comm=comm)
+            sm = ShardedMatrix(n_samples, mode, rows_hint=rows_n, device=device, flags=fl, comm=comm)
             dm = sm.local
         else:
-            sm = dm = _native.DeviceMatrix(n_samples, mode, rows_hint=rows_n, device=device, flags=args.flags)
+            sm = dm = _native.DeviceMatrix(n_samples, mode, rows_hint=rows_n, device=device, flags=fl)
         t.append(time.perf_counter())
         if resident:
             parts = rows_dev if rows_dev is not None else [(cohort.rows.ptr, n_vars, cohort.af.ptr)]
@@ -457,6 +458,22 @@ def main():
                          "step0_gains": {"bytes": gain_bytes, "ms": c3_ph["gain_ms"],
                                          "frac": gain_bytes / 1e9 / (c3_ph["gain_ms"] / 1e3) / peak if c3_ph["gain_ms"] > 0 else None},
                          "dtype": "u64 fixed-point limbs -> f64 (one rounding per comparison)"}
+        # the same selection in the REFERENCE's tie order (UTMOS_F_REF_TIES, what `utmos select --af` runs on one GPU):
+        # checked against the plain-C oracle's mode-0 run (sequential float64 sums, utmos/select.py:37-41)
+        gold3r = golden("c3ref", args.seed, n_vars, n_samples)
+        if gold3r is not None:
+            one_selection(True, af_mode_=_native.AF_F64, mask_=c3_mask, weights_=c3_w, flags_=_native.F_REF_TIES)
+            _native.timer_start(device)
+            r_idx, r_new, r_score, r_stop, _vc, _info, r_tim = one_selection(True, af_mode_=_native.AF_F64, mask_=c3_mask,
+                                                                            weights_=c3_w, flags_=_native.F_REF_TIES)
+            r_ms = _native.timer_stop(device)
+            r_ok = bool(np.array_equal(r_idx, gold3r["idx"]) and np.array_equal(r_new, gold3r["new"]) and
+                        r_stop == int(gold3r["stop"]) and np.allclose(r_score, gold3r["score"], rtol=1e-12, atol=0))
+            assert r_ok, "config C3 with UTMOS_F_REF_TIES differs from the reference-order oracle (tests/golden/c3ref_full_order.npz)"
+            configs["c3"]["reference_tie_order"] = {
+                "ms_per_selection": r_ms, "select_ms": r_tim["select_ms"], "verified_vs_reference_order_golden": r_ok,
+                "picks_in_the_same_position_as_the_exact_order": int(np.sum(r_idx == c_idx)) if len(r_idx) == len(c_idx) else None,
+                "note": "per-step kernels + one warp per tied candidate replaying the reference's sequential float64 sum"}
 
     # ---- CPU baseline: the unmodified reference, complete run on a reduced row count, and this repo on the same rows
     cpu_baseline = None

@@ -767,7 +767,10 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
     c->pitchW = (c->nW + 3) / 4 * 4;
     c->af_mode = af_mode;
     c->flags = flags;
-    if (flags & UTMOS_F_REF_TIES) c->flags |= UTMOS_F_STEP_KERNELS;        // the replay lives in argmax_step_kernel
+    if (flags & UTMOS_F_REF_TIES) {
+        if (af_mode != UTMOS_AF_NONE) c->flags |= UTMOS_F_STEP_KERNELS;    // the replay lives in argmax_step_kernel
+        else c->flags &= ~UTMOS_F_REF_TIES;                                 // count mode has no float sums to replay
+    }
     // --af: the 8-CTA owner-computes flavour of the tail until a pick covers fewer than 64 rows (three shared-memory
     // atomics per decrement, two of them 64-bit: measured 10.0 ms against 11.9 ms for the tail of config C3)
     if (af_mode != UTMOS_AF_NONE) c->tail_single_rows = 64;
@@ -1204,6 +1207,10 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
                 return UTMOS_E_NOMEM;
             }
         }
+    }
+    if ((c->flags & UTMOS_F_REF_TIES) && v > 0 && !c->d_cols) {
+        set_error("finalize: UTMOS_F_REF_TIES needs the sample-major copy (it does not fit, or UTMOS_F_NO_TRANSPOSE is set)");
+        return UTMOS_E_NOMEM;
     }
     tr.lap("sample-major allocation");
     if (c->d_cols) {

@@ -171,6 +171,8 @@ class LoadedData(dict):
 
 def _new_matrix(num_samples, af_mode, rows_hint, device, flags, comm):
     """One GPU: DeviceMatrix.  Under torchrun (comm given): this rank's shard of the rows (distributed.ShardedMatrix)."""
+    if af_mode == _native.AF_NONE:
+        flags &= ~_native.F_REF_TIES                          # count mode has no float sums to replay
     if comm is None:
         return _native.DeviceMatrix(num_samples, af_mode, rows_hint=rows_hint, device=device, flags=flags)
     from utmos_b200.distributed import ShardedMatrix  # pylint: disable=import-outside-toplevel
@@ -342,9 +344,11 @@ _SELECT_OPTIONS = (
     )),
     ("Scoring", (
         (("--af",), dict(action="store_true", help="score a variant by its allele frequency instead of 1")),
-        (("--ref-ties",), dict(action="store_true",
-                               help="with --af: order samples whose exact scores tie (or nearly tie) the way the reference's "
-                                    "sequential float64 sums do; slower per-step kernels (not in the reference: it IS the reference's order)")),
+        (("--exact-ties",), dict(action="store_true",
+                                 help="with --af: order samples whose exact scores tie by sample index (exact fixed-point sums; the "
+                                      "select loop is ~10x faster) instead of replaying the reference's sequential float64 sums, "
+                                      "which is the default because it reproduces the reference's order (not in the reference)")),
+        (("--ref-ties",), dict(action="store_true", help="accepted for explicitness: the default behaviour of --af on one GPU")),
         (("--weights",), dict(type=str, default=None, help="TSV of sample<TAB>weight; scores are multiplied by it")),
         (("--subset",), dict(type=str, default=None, action="append",
                              help="only these samples can be picked: a file of names or a comma separated list (repeatable)")),
@@ -422,9 +426,16 @@ def select_main(cmdargs):
     global MAXMEM  # pylint: disable=global-statement
     args = parse_args(cmdargs)
     comm = _torchrun_comm(args)
-    flags = _native.F_REF_TIES if (args.ref_ties and args.af) else 0
-    if flags and comm is not None:
-        _fail("--ref-ties is not available on several GPUs")
+    # --af: the reference's own order at exact-arithmetic ties unless --exact-ties; several GPUs
+    # only have the exact order
+    ref_ties = not args.exact_ties
+    if ref_ties and comm is not None:
+        if args.ref_ties:
+            _fail("--ref-ties is not available on several GPUs")
+        if args.af:
+            logging.warning("several GPUs: --af ties are ordered by exact sums and sample index (--exact-ties)")
+        ref_ties = False
+    flags = _native.F_REF_TIES if ref_ties else 0           # only AF matrices look at it (load_files)
     data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device, flags=flags, comm=comm)
     stored_af = data["data"].dtype != bool                   # float data = GT * AF, made with --af
     if args.af and not stored_af:
