@@ -170,7 +170,9 @@ class DeviceMatrix:
         self.af_mode = af_mode
         self.num_vars = None
         self.var_count = None
-        flags |= int(os.environ.get("UTMOS_B200_FLAGS", "0"))     # test / debugging override of the kernel flavour
+        env_flags = int(os.environ.get("UTMOS_B200_FLAGS", "0"))  # test / debugging override of the kernel flavour
+        if env_flags:
+            flags = (flags & ~F_REF_TIES) | env_flags             # an explicit flavour wins over the tie-replay flavour
         check(lib().utmos_create(ctypes.byref(self._ctx), device, self.n_samples, int(rows_hint), af_mode, flags))
 
     # -- ingestion ---------------------------------------------------------------------------------
