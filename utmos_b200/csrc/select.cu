@@ -612,28 +612,42 @@ __device__ __forceinline__ void cover_chunk(const SelParams &p, int b, long long
 // (the lanes locate the set bits, the adds stay strictly sequential), times the weight (:47); the first maximum wins (:48).
 __device__ __forceinline__ double replay_reference_sum(const SelParams &p, int t, int lane)
 {
-    const uint32_t *col = p.cols + (long long)t * p.colPitchW;
-    const long long words = (p.V + 31) >> 5;
+    // a lane takes four consecutive words (128 rows) per turn with one 128-bit load of the column and of the live mask
+    // (colPitchW is a multiple of 8 words and the words past V are zero in both); lanes are served in ascending order,
+    // a lane adds its rows in ascending order: the reference's row order
+    const uint4 *col = reinterpret_cast<const uint4 *>(p.cols + (long long)t * p.colPitchW);
+    const uint4 *lv = reinterpret_cast<const uint4 *>(p.live);
+    const long long n4 = p.colPitchW >> 2;
     double acc = 0.0;
-    for (long long w0 = 0; w0 < words; w0 += 32) {
-        const long long w = w0 + lane;
-        uint32_t x = w < words ? (__ldg(col + w) & __ldcg(p.live + w)) : 0u;
-        unsigned int m = __ballot_sync(0xffffffffu, x != 0u);
+    for (long long q0 = 0; q0 < n4; q0 += 32) {
+        const long long q = q0 + lane;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (q < n4) {
+            const uint4 c = __ldg(col + q);
+            const uint4 l = __ldcg(lv + q);
+            x = make_uint4(c.x & l.x, c.y & l.y, c.z & l.z, c.w & l.w);
+        }
+        unsigned int m = __ballot_sync(0xffffffffu, (x.x | x.y | x.z | x.w) != 0u);
         while (m) {
-            const int l = __ffs(m) - 1;
+            const int ln = __ffs(m) - 1;
             m &= m - 1;
-            if (lane == l) {
+            if (lane == ln) {
                 double a = acc;
-                while (x) {
-                    const long long r = (w << 5) + (__ffs(x) - 1);
-                    x &= x - 1;
-                    double v = __ldg(p.af_vals + r);
-                    if (p.af_f32) v = (double)(float)v;          // hdf5 flavour: float32 GT*AF rows (utmos/select.py:218-223)
-                    a += v;
+                const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t y = w[k];
+                    while (y) {
+                        const long long r = (((q << 2) + k) << 5) + (__ffs(y) - 1);
+                        y &= y - 1;
+                        double v = __ldg(p.af_vals + r);
+                        if (p.af_f32) v = (double)(float)v;      // hdf5 flavour: float32 GT*AF rows (utmos/select.py:218-223)
+                        a += v;
+                    }
                 }
                 acc = a;
             }
-            acc = __shfl_sync(0xffffffffu, acc, l);
+            acc = __shfl_sync(0xffffffffu, acc, ln);
         }
     }
     return acc;
