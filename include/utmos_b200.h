@@ -228,7 +228,9 @@ int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);
  * [7]=selection kernel flavour used: 0 step kernels, 1 grid-wide persistent, 2 one-cluster DSMEM,
  *   3 single-CTA list-driven tail (after a head run by flavour 1 or 2), 4 multi-GPU kernel (per-step exchange),
  *   5 multi-GPU head followed by the replicated tail;
- * [8]=32-bit words of the live-row mask (utmos_select_export / _import) */
+ * [8]=32-bit words of the live-row mask (utmos_select_export / _import);
+ * [9]=1 when the reference tie order (UTMOS_F_REF_TIES) is in effect (after utmos_finalize: it falls back to the exact
+ *   order when the sample-major copy does not exist) */
 int utmos_info(utmos_ctx *ctx, int64_t *info, int n);
 
 /* Device-side (CUDA event) milliseconds accumulated since utmos_create / the last reset:

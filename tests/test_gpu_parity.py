@@ -231,6 +231,28 @@ def test_ref_ties_full_af_ordering_and_cli(tmp_path):
     assert out.read_text() == H.answer_key("select_af_h5.txt")
 
 
+def test_ref_ties_falls_back_without_the_sample_major_copy():
+    """UTMOS_F_REF_TIES needs sample-major rows: without them the context says so (info["ref_ties"] == 0) and gives the
+    exact-arithmetic order; with UTMOS_F_FORCE_TRANSPOSE semantics untouched."""
+    parts = H.load_jl_parts(["chunk0.jl"])
+    n = 2504
+    outs = []
+    for flags in (_native.F_REF_TIES | _native.F_NO_TRANSPOSE, 0):
+        dm = _native.DeviceMatrix(n, _native.AF_F64, flags=flags)
+        dm.append_packed(parts[0]["GT"], parts[0]["AF"])
+        dm.finalize()
+        assert dm.info()["ref_ties"] == 0
+        dm.begin(np.ones(n, np.uint8))
+        outs.append(dm.steps(60))
+        dm.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][2], outs[1][2])
+    dm = _native.DeviceMatrix(n, _native.AF_F64, flags=_native.F_REF_TIES)
+    dm.append_packed(parts[0]["GT"], parts[0]["AF"])
+    dm.finalize()
+    assert dm.info()["ref_ties"] == 1
+    dm.close()
+
+
 def test_step_batches_equal_one_shot():
     """utmos_select_steps is resumable: 7-step batches give the same rows as one call."""
     gold = H.golden_json("full_order_count.json")

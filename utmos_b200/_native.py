@@ -353,10 +353,10 @@ class DeviceMatrix:
         check(lib().utmos_set_option(self._ctx, 1, int(rows)))
 
     def info(self):
-        arr = np.zeros(9, dtype=np.int64)
-        check(lib().utmos_info(self._ctx, _ptr(arr), 9))
+        arr = np.zeros(10, dtype=np.int64)
+        check(lib().utmos_info(self._ctx, _ptr(arr), 10))
         keys = ["num_vars", "row_pitch_bytes", "has_sample_major", "device_bytes", "fixed_scale", "af_inexact",
-                "kernel_launches", "flavour", "live_words"]
+                "kernel_launches", "flavour", "live_words", "ref_ties"]
         return dict(zip(keys, (int(x) for x in arr)))
 
     def timings(self, reset=False):

@@ -1209,8 +1209,13 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
         }
     }
     if ((c->flags & UTMOS_F_REF_TIES) && v > 0 && !c->d_cols) {
-        set_error("finalize: UTMOS_F_REF_TIES needs the sample-major copy (it does not fit, or UTMOS_F_NO_TRANSPOSE is set)");
-        return UTMOS_E_NOMEM;
+        // the replay walks sample-major rows: without that copy (it does not fit, or UTMOS_F_NO_TRANSPOSE) the context falls
+        // back to the exact-arithmetic order and says so in utmos_info()[9]; UTMOS_F_FORCE_TRANSPOSE makes it an error
+        if (c->flags & UTMOS_F_FORCE_TRANSPOSE) {
+            set_error("finalize: UTMOS_F_REF_TIES needs the sample-major copy");
+            return UTMOS_E_NOMEM;
+        }
+        c->flags &= ~(UTMOS_F_REF_TIES | UTMOS_F_STEP_KERNELS);
     }
     tr.lap("sample-major allocation");
     if (c->d_cols) {
@@ -1838,9 +1843,10 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
 int utmos_info(utmos_ctx *c, int64_t *info, int n)
 {
     if (!c || !info) { set_error("info: null argument"); return UTMOS_E_ARG; }
-    const int64_t vals[9] = {c->V, (int64_t)c->pitchW * 4, c->d_cols ? 1 : 0, (int64_t)c->dev_bytes, c->scale,
-                             (int64_t)c->af_inexact, c->n_launch, c->flavour_used, (int64_t)c->colPitchW};
-    for (int i = 0; i < n && i < 9; ++i) info[i] = vals[i];
+    const int64_t vals[10] = {c->V, (int64_t)c->pitchW * 4, c->d_cols ? 1 : 0, (int64_t)c->dev_bytes, c->scale,
+                              (int64_t)c->af_inexact, c->n_launch, c->flavour_used, (int64_t)c->colPitchW,
+                              (c->flags & UTMOS_F_REF_TIES) ? 1 : 0};
+    for (int i = 0; i < n && i < 10; ++i) info[i] = vals[i];
     return UTMOS_OK;
 }
 

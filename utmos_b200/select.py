@@ -438,6 +438,9 @@ def select_main(cmdargs):
     flags = _native.F_REF_TIES if ref_ties else 0           # only AF matrices look at it (load_files)
     data = load_files(args.in_files, args.lowmem, args.buffer, args.af, device=args.device, flags=flags, comm=comm)
     stored_af = data["data"].dtype != bool                   # float data = GT * AF, made with --af
+    if stored_af and flags and hasattr(data["data"], "info") and not data["data"].info().get("ref_ties", 1):
+        logging.warning("no sample-major copy of the matrix in HBM: ties of --af scores are ordered by exact sums and "
+                        "sample index (as with --exact-ties), not by the reference's float64 accumulation order")
     if args.af and not stored_af:
         logging.critical("HDF5 file doesn't appear to be created with --af weighted scores, remove --af or recreate hdf5")
         sys.exit(1)
