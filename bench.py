@@ -67,7 +67,7 @@ def traffic_from_ncu():
 class ClockSampler:
     """nvidia-smi clock / throttle-reason log during the timed region (B200_PROFILING.md)."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -79,12 +79,22 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                          "-i", str(self.gpu_index), "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, windows=()):
+        """windows: (t0, t1) wall-clock pairs of the timed regions; samples inside them are the ones reported (the sampler
+        itself runs from the start of the program, nvidia-smi needs a few hundred ms to deliver its first line)."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -93,7 +103,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        rows = []
         try:
             with open(self.path) as fh:
                 for line in fh:
@@ -101,20 +111,20 @@ class ClockSampler:
                     if len(f) < 9:
                         continue
                     try:
-                        sm.append(float(f[1]))
-                        smax.append(float(f[2]))
+                        rows.append((self._stamp(f[0]), float(f[1]), float(f[2]),
+                                     [name for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                                 "sw_power_cap"], f[5:9]) if val.lower().startswith("active")]))
                     except ValueError:
                         continue
-                    for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
-                                         f[5:9]):
-                        if val.lower().startswith("active"):
-                            reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        inside = [r for r in rows if r[0] is not None and any(a - 0.02 <= r[0] <= b + 0.02 for a, b in windows)]
+        use = inside if len(inside) >= 3 else rows
+        if use:
+            out = {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
+                   "reasons": sorted({name for r in use for name in r[3]}), "samples": len(use),
+                   "samples_inside_timed_regions": len(inside), "samples_whole_run": len(rows), "period_ms": 20}
         return out
 
 
@@ -250,6 +260,10 @@ def main():
             dist.barrier()
 
     device = local_rank
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()                              # early: nvidia-smi needs a few hundred ms before its first sample
+    timed_windows = []
     n_vars, n_samples = args.vars, N_SAMPLES
     pitch = (n_samples + 7) // 8
     packed_bytes = n_vars * pitch
@@ -330,9 +344,11 @@ def main():
         barrier()
         _native.timer_start(device)                  # device synchronised, CUDA event recorded
         t0 = time.perf_counter()
+        w0 = time.time()
         outs = [one_selection(resident) for _ in range(args.steps)]
         wall = time.perf_counter() - t0              # every selection ends synchronised (results copied to host)
         elapsed = _native.timer_stop(device) / 1e3   # device synchronised again; event-to-event seconds
+        timed_windows.append((w0, time.time()))
         wall_vs_event.append((wall, elapsed))
         barrier()
         if dist is not None:
@@ -342,12 +358,9 @@ def main():
             elapsed = float(t.item())
         return elapsed, outs
 
-    sampler = ClockSampler(device)
-    if rank == 0:
-        sampler.start()
     t_res, outs_res = timed(True)
     t_e2e, outs_e2e = timed(False)
-    clocks = sampler.stop() if rank == 0 else {}
+    clocks = sampler.stop(timed_windows) if rank == 0 else {}
 
     idx, new, score, stop, var_count, info, _ = outs_res[-1]
     idx2, new2 = outs_e2e[-1][0], outs_e2e[-1][1]
