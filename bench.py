@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--tail-rows", type=int, default=-1, help="override the tail hand-over threshold")
     ap.add_argument("--regain-rows", type=int, default=-1, help="override the heavy-pick threshold (UTMOS_OPT_REGAIN_ROWS)")
     ap.add_argument("--single-rows", type=int, default=-1, help="override the cluster-tail -> single-CTA-tail threshold")
+    ap.add_argument("--heavy-rows", type=int, default=-1, help="override the entry-divided-cluster -> shared-memory tail threshold")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -323,6 +324,8 @@ def main():
             dm.set_option(5, args.single_rows)
         if args.regain_rows >= 0:
             dm.set_option(1, args.regain_rows)
+        if args.heavy_rows >= 0:
+            dm.set_option(10, args.heavy_rows)
         sm.begin(msk, wts)
         t.append(time.perf_counter())
         idx, new, score, stop = sm.steps(n_samples)
@@ -545,7 +548,7 @@ def main():
             "roofline": roofline, "streaming_kernels": streaming, "phases_ms": phases,
             "select_parts_ms": {"head": phases.get("head_ms"), "hand_over": phases.get("handover_ms"), "tail": phases.get("tail_ms")},
             "configs": configs, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "step_profile": step_profile, "host_ms_create_append_finalize_begin_steps_close": {"resident": np.mean([o[6]["host_ms"] for o in outs_res], axis=0).round(3).tolist(), "e2e": np.mean([o[6]["host_ms"] for o in outs_e2e], axis=0).round(3).tolist()}, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:13]], "timing": {"clock": "CUDA events around the K timed steps (utmos_timer_start/stop: device synchronised on both sides), max over ranks", "host_wall_s_resident_e2e": [round(w, 6) for w, _ in wall_vs_event], "event_s_resident_e2e": [round(e, 6) for _, e in wall_vs_event]}, "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
+            "step_profile": step_profile, "host_ms_create_append_finalize_begin_steps_close": {"resident": np.mean([o[6]["host_ms"] for o in outs_res], axis=0).round(3).tolist(), "e2e": np.mean([o[6]["host_ms"] for o in outs_e2e], axis=0).round(3).tolist()}, "phase_cycles": [int(x) for x in outs_res[-1][6]["counters"][:16]], "timing": {"clock": "CUDA events around the K timed steps (utmos_timer_start/stop: device synchronised on both sides), max over ranks", "host_wall_s_resident_e2e": [round(w, 6) for w, _ in wall_vs_event], "event_s_resident_e2e": [round(e, 6) for _, e in wall_vs_event]}, "select_time_s": phases["select_ms"] / 1e3, "us_per_greedy_step": phases["select_ms"] * 1e3 / max(n_steps, 1)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -491,7 +491,8 @@ def test_synthetic_reduced_shape_vs_c_oracle(use_af, flags):
 @pytest.mark.parametrize("weighted", [False, True], ids=["plain", "weights"])
 @pytest.mark.parametrize("single_rows,tail_rows", [(1, 1 << 30), (64, 1 << 30), (0, 1 << 30), (32, 512)],
                          ids=["cluster_tail_only", "cluster_then_single", "single_tail_from_step0", "cluster_late"])
-def test_tail_flavours_vs_c_oracle(use_af, weighted, single_rows, tail_rows):
+@pytest.mark.parametrize("heavy_rows", [0, 1, 200], ids=["smem_tail", "entry_cluster_always", "entry_cluster_then_smem"])
+def test_tail_flavours_vs_c_oracle(use_af, weighted, single_rows, tail_rows, heavy_rows):
     """The list-driven tail from the very first pick (heavy picks: the staging area overflows into the direct
     path) in its one-CTA flavour and in the 8-CTA owner-computes cluster flavour, against the exact oracle."""
     n_vars, n_samples = 30000, 1777
@@ -504,6 +505,7 @@ def test_tail_flavours_vs_c_oracle(use_af, weighted, single_rows, tail_rows):
     dm.finalize()
     dm.set_option(3, tail_rows)
     dm.set_option(5, single_rows)
+    dm.set_option(10, heavy_rows)
     dm.begin(mask, wts)
     i1, n1, s1, _ = dm.steps(150)
     i2, n2, s2, _ = dm.steps(n_samples)
@@ -541,18 +543,19 @@ def test_cohorts_whose_state_does_not_fit_one_sm(mode, tail_rows, n_samples):
     mask = np.ones(n_samples, np.uint8)
     mask[7::101] = 2
     results = []
-    for flags in (0, _native.F_NO_TAIL):
+    for flags, heavy_rows in ((0, 0), (_native.F_NO_TAIL, 0), (0, 1), (0, 60)):
         dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE, flags=flags)
         dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
         dm.finalize()
         dm.set_option(3, tail_rows)
+        dm.set_option(10, heavy_rows)                   # 0: sliced shared-memory tail; > 0: entry-divided cluster first
         dm.begin(mask, wts)
         i1, n1, s1, _ = dm.steps(100)
         i2, n2, s2, _ = dm.steps(steps - 100)
         results.append((np.concatenate([i1, i2]), np.concatenate([n1, n2]), np.concatenate([s1, s2]), dm.info()["flavour"]))
         dm.close()
     coh.close()
-    assert results[0][3] == 3 and results[1][3] != 3
+    assert results[0][3] == 3 and results[1][3] != 3 and results[2][3] == 3
     o_idx, o_new, o_score, _ = orc.greedy_c(gt, n_samples, mask, wts, af if use_af else None, steps, exact=True)
     for idx, new, score, _ in results:
         assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score)

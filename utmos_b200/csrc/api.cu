@@ -144,6 +144,8 @@ struct utmos_ctx {
     unsigned long long *d_local0_lo = nullptr, *d_local0_hi = nullptr, *d_local_lo = nullptr, *d_local_hi = nullptr;
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
+    unsigned int tail_heavy_rows = 1024;  // list-driven tail: picks that cover at least this many rows are run by the entry-divided
+                                          // 16-CTA cluster kernel (gains in L2), lighter ones from one SM's shared memory (0 = never)
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
                                           // (measured on the 1kGP shape: not faster than one CTA, so off by default)
     uint32_t *d_newmask = nullptr;        // rows newly covered by the pick that ended a head launch (cover_decrement_kernel)
@@ -1416,7 +1418,13 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         };
         while (true) {
             SelParams q = make_params(c, false);
-            if (c->lists_valid) {
+            if (c->lists_valid && c->tail_heavy_rows > 0 && !st.tail_single && listcluster_fits(q)) {
+                // heavy picks: the entries of the pick divided over a 16-CTA cluster, gains in L2 (select_listcluster_kernel);
+                // it hands over (st.tail_single) once a pick covers fewer than tail_heavy_rows rows
+                UT_TRY(launch_listcluster(c->stream, q, c->lists_total, c->tail_heavy_rows, &c->n_launch));
+                UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                c->flavour_used = multi ? 5 : 3;
+            } else if (c->lists_valid) {
                 // heavy picks: cluster of 8 CTAs, each applying the decrements of the samples it owns; light picks: one CTA
                 const unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
                 const bool cluster = single_rows > 0 || tail_cluster_size(q, false) != 1;     // wide / mid-size cohorts: sliced state
@@ -1835,6 +1843,7 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
     if (option == UTMOS_OPT_GLOBAL_ROWS) { c->global_rows = value; return UTMOS_OK; }
     if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
+    if (option == UTMOS_OPT_TAIL_HEAVY_ROWS) { c->tail_heavy_rows = (unsigned int)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_SINGLE_ROWS) { c->tail_single_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");
     return UTMOS_E_ARG;

@@ -285,6 +285,9 @@ int launch_gather_done(cudaStream_t stream, const GatherParams &g, int *n_launch
 unsigned long long mgpu_pool_share(unsigned long long live_bits);
 int launch_tail(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, bool cluster,
                 unsigned int single_rows, uint32_t *live_priv, int *n_launch);
+bool listcluster_fits(const SelParams &p);
+int launch_listcluster(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int light_rows,
+                       int *n_launch);
 int tail_live_in_smem(const SelParams &p, bool cluster);
 int tail_cluster_size(const SelParams &p, bool cluster);
 int tail_possible(long long S, int af);

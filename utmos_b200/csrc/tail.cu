@@ -763,6 +763,300 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
     if (CL > 1) cg::this_cluster().sync();           // nobody leaves while a peer may still write into its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// List-driven tail, ENTRY-DIVIDED over a cluster: the entries of the pick split over 16 CTAs, the per-sample state sliced
+// over their shared memories, decrements sent to the owner's slice with remote shared-memory atomics.
+//
+// select_tail_kernel applies every decrement of a step with the shared-memory atomics of ONE SM (2 cycles per lane), and its
+// owner-computes cluster flavour makes every CTA walk ALL the entries of the pick.  That is the right trade while a pick
+// covers a few hundred rows and the wrong one when it covers thousands: the merged lists of N GPUs hold N times the rows
+// per pick (8 GPUs: 12 M decrements = 18 ms of a 20 ms tail), and so does one GPU with a large matrix.  Here
+//   * CTA r keeps the gains / mask / list positions of the samples s with s % CL == r in its shared memory (loaded from
+//     global at entry, written back at exit) and scans only those for its local best;
+//   * the CL local winners (with their list position) meet through distributed shared memory, one cluster barrier;
+//   * the pick's entries are dealt out warp by warp over all CL x 32 warps of the cluster; the live bit is cleared with a
+//     global atomic that returns the old word (that decides "newly covered"); each carrier's decrement is a remote
+//     shared-memory atomic on the owner's slice (64-bit limbs as two 32-bit atomics with carry, like smem_add64); pooled
+//     carrier lists are queued in shared memory and retired a warp per row;
+//   * a second cluster barrier (release/acquire over shared::cluster) ends the step: no fence, no L2 round trip for gains.
+// Same lists, same pool, same recompaction protocol, same pick order (np.argmax, utmos/select.py:48) as select_tail_kernel.
+// ------------------------------------------------------------------------------------------------
+// shared::cluster address of `local` (a pointer into this CTA's shared memory) in the CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local, unsigned int rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_red_add(uint32_t addr, unsigned int v)
+{
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int dsmem_atom_add(uint32_t addr, unsigned int v)
+{
+    unsigned int old;
+    asm volatile("atom.relaxed.cluster.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+// 64-bit add on a peer's shared memory as two 32-bit atomics with carry (cf. smem_add64)
+__device__ __forceinline__ void dsmem_add64(uint32_t addr, unsigned long long v)
+{
+    const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
+    const unsigned int old = dsmem_atom_add(addr, lo);
+    const unsigned int carry = (old + lo) < old ? 1u : 0u;
+    if (hi + carry) dsmem_red_add(addr + 4, hi + carry);
+}
+
+struct ListClusterCfg {
+    int n_own_max;       // samples per CTA slice
+    int off_lo, off_hi, off_mask, off_loff, off_llen;   // byte offsets into dynamic shared memory (counts at 0)
+    int stage_lists;     // list positions staged in shared memory (else read through the read-only path)
+    unsigned int min_recompact;
+};
+
+template <int ESTRIDE, int CL, bool WIDE>
+__global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p, ListClusterCfg cfg, unsigned long long lists_total,
+                                                                     unsigned int light_rows)
+{
+    constexpr bool AF = ESTRIDE == 2;
+    constexpr int kInl = WIDE ? 2 : kInline;
+    constexpr unsigned int kPad = WIDE ? 0xffffffffu : 0xffffu;
+    constexpr int kQueue = 2048;
+    extern __shared__ __align__(16) unsigned char lc_smem[];
+    __shared__ Cand s_red[32];
+    __shared__ unsigned long long s_sum[32];
+    __shared__ uint4 s_xbest[2][16];
+    __shared__ uint4 s_xlist[2][16];                 // {sum of owned gains lo, hi, list offset, list length}
+    __shared__ uint4 s_q[kQueue];                    // pooled rows this CTA found: {pool base, carriers, entry index, 0}
+    __shared__ unsigned int s_qn;
+    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(lc_smem);
+    unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(lc_smem + cfg.off_lo);
+    unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(lc_smem + cfg.off_hi);
+    unsigned char *s_mask = lc_smem + cfg.off_mask;
+    unsigned int *s_loff = reinterpret_cast<unsigned int *>(lc_smem + cfg.off_loff);
+    unsigned int *s_llen = reinterpret_cast<unsigned int *>(lc_smem + cfg.off_llen);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool has_w = p.weights != nullptr;
+    SelState *st = p.st;
+    const int n_own = p.S > crank ? (p.S - crank + CL - 1) / CL : 0;
+    long long step = st->step, tot = st->tot;
+    const long long limit = st->limit;
+    int stop = st->stop, recompact = 0, want_light = 0, xpar = 0, since_check = 0;
+    const unsigned int *pool32 = reinterpret_cast<const unsigned int *>(p.pool);
+    for (int li = tid; li < n_own; li += blockDim.x) {
+        const int s = crank + CL * li;
+        s_cnt[li] = p.gain_cnt[s];
+        if (AF) { s_lo[li] = p.gain_lo[s]; s_hi[li] = p.gain_hi[s]; }
+        s_mask[li] = p.mask[s];
+        if (cfg.stage_lists) { s_loff[li] = p.list_off[s]; s_llen[li] = p.list_len[s]; }
+    }
+    __syncthreads();
+    cluster.sync();
+    // the slice of sample c: CTA c % CL, slot c / CL
+    auto retire = [&](unsigned int c, unsigned long long nl, unsigned long long nh) {
+        const unsigned int owner = c % CL, slot = c / CL;
+        dsmem_red_add(dsmem_addr(s_cnt + slot, owner), 0xffffffffu);
+        if (AF) {
+            dsmem_add64(dsmem_addr(s_lo + slot, owner), nl);
+            dsmem_add64(dsmem_addr(s_hi + slot, owner), nh);
+        }
+    };
+
+    while (stop == 0 && step < limit) {
+        // ---- argmax over the samples this CTA owns
+        Cand b{0u, 0u, 0x7fffffff, 0u};
+        unsigned long long acc = 0;
+        if (tid == 0) s_qn = 0;                       // read last before the barrier that ended the previous step
+        for (int li = tid; li < n_own; li += blockDim.x) {
+            const int s = crank + CL * li;
+            const unsigned int c = s_cnt[li];
+            double g = 0.0;
+            if (s_mask[li] == 1) {
+                g = AF ? fixed_to_double(s_lo[li], s_hi[li], p.L, p.scale) : (double)c;
+                if (has_w) g *= __ldg(p.weights + s);
+                acc += c;
+            }
+            const unsigned long long k = score_key(g);
+            const Cand c2{(unsigned int)(k >> 32), (unsigned int)k, s, c};
+            if (cand_better(c2, b)) b = c2;
+        }
+        b = warp_argmax(b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { s_red[warp] = b; s_sum[warp] = acc; }
+        __syncthreads();
+        if (warp == 0) {
+            b = warp_argmax(s_red[lane]);
+            acc = s_sum[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane < CL) {
+                unsigned int off = 0, len = 0;
+                if (b.idx != 0x7fffffff) {
+                    const int li = (b.idx - crank) / CL;
+                    off = cfg.stage_lists ? s_loff[li] : __ldg(p.list_off + b.idx);
+                    len = cfg.stage_lists ? s_llen[li] : __ldg(p.list_len + b.idx);
+                }
+                cluster.map_shared_rank(&s_xbest[xpar][0], lane)[crank] = make_uint4(b.hi, b.lo, (unsigned int)b.idx, b.cnt);
+                cluster.map_shared_rank(&s_xlist[xpar][0], lane)[crank] = make_uint4((unsigned int)acc, (unsigned int)(acc >> 32), off, len);
+            }
+        }
+        cluster.sync();
+        unsigned int off, len;
+        {
+            const uint4 o = lane < CL ? s_xbest[xpar][lane] : make_uint4(0u, 0u, 0x7fffffffu, 0u);
+            const uint4 l = lane < CL ? s_xlist[xpar][lane] : make_uint4(0u, 0u, 0u, 0u);
+            b = warp_argmax(Cand{o.x, o.y, (int)o.z, o.w});
+            acc = ((unsigned long long)l.y << 32) | l.x;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+            const int src = b.idx == 0x7fffffff ? 0 : b.idx % CL;             // the winner's CTA holds its list position
+            off = __shfl_sync(0xffffffffu, l.z, src);
+            len = __shfl_sync(0xffffffffu, l.w, src);
+            xpar ^= 1;
+        }
+        const int best_idx = b.idx;
+        const unsigned int best_cnt = b.cnt;
+        const double best_score = key_score(b.hi, b.lo);
+        if (p.S == 0 || best_idx == 0x7fffffff || best_score == 0.0) {        // utmos/select.py:51-52
+            stop = UTMOS_STOP_ZERO;
+            break;
+        }
+        if (++since_check >= 64) {
+            since_check = 0;
+            if (acc >= cfg.min_recompact && acc * 2 <= lists_total && limit - step > 128) { recompact = 1; break; }
+        }
+        if (light_rows && best_cnt < light_rows) { want_light = 1; break; }   // light picks: one SM from shared memory is faster
+        if (tid == 0) {
+            if (crank == 0) {
+                p.out_idx[step] = best_idx;
+                p.out_new[step] = best_cnt;
+                p.out_score[step] = best_score;
+                if (p.dbg_time) p.out_time[step] = global_timer_ns();
+            }
+            if (best_idx % CL == crank) {
+                // every live row of the pick is covered by the end of this step and nobody decrements the pick itself
+                const int li = best_idx / CL;
+                s_cnt[li] = 0u;
+                if (AF) { s_lo[li] = 0ull; s_hi[li] = 0ull; }
+                s_mask[li] = 0;                                               // utmos/select.py:100
+            }
+        }
+        step += 1;
+        tot += best_cnt;
+        if (tot >= p.V) {                                                     // utmos/select.py:110-112
+            stop = UTMOS_STOP_ALL;
+            break;
+        }
+        // ---- walk: the pick's entries dealt out warp by warp over the whole cluster
+        const uint4 *lst = p.lists + (size_t)off * ESTRIDE;
+        for (unsigned int i = ((unsigned int)warp * CL + (unsigned int)crank) * 32u + (unsigned int)lane; i < len;
+             i += (unsigned int)CL * 1024u) {
+            const uint4 e = __ldg(lst + (size_t)i * ESTRIDE);
+            const unsigned int r = e.x;
+            const uint32_t bit = 1u << (r & 31);
+            const uint32_t old = atomicAnd(p.live + (r >> 5), ~bit);
+            if (!(old & bit)) continue;                                       // covered earlier
+            const unsigned int n = WIDE ? e.y : (e.y & 0xffffu);
+            const bool pooled = WIDE ? n == 0xffffffffu : n == kPooled;
+            if (!pooled) {
+                unsigned int c[kInline];
+                if (WIDE) { c[0] = e.z; c[1] = e.w; c[2] = c[3] = c[4] = 0; }
+                else { c[0] = e.y >> 16; c[1] = e.z & 0xffffu; c[2] = e.z >> 16; c[3] = e.w & 0xffffu; c[4] = e.w >> 16; }
+                unsigned long long nl = 0, nh = 0;
+                if (AF && n) {
+                    const uint4 qv = __ldg(lst + (size_t)i * ESTRIDE + 1);
+                    nl = 0ull - (((unsigned long long)qv.y << 32) | qv.x);
+                    nh = 0ull - (((unsigned long long)qv.w << 32) | qv.z);
+                }
+#pragma unroll
+                for (int j = 0; j < kInl; ++j)
+                    if (j < (int)n) retire(c[j], nl, nh);
+            } else {
+                const unsigned int slot = atomicAdd(&s_qn, 1u);
+                if (slot < (unsigned int)kQueue) {
+                    s_q[slot] = make_uint4(e.z, e.w, i, 0u);
+                } else {                                                      // queue full: this thread retires the row itself
+                    unsigned long long nl = 0, nh = 0;
+                    if (AF) {
+                        const uint4 qv = __ldg(lst + (size_t)i * ESTRIDE + 1);
+                        nl = 0ull - (((unsigned long long)qv.y << 32) | qv.x);
+                        nh = 0ull - (((unsigned long long)qv.w << 32) | qv.z);
+                    }
+                    for (unsigned int k = 0; k < e.w; ++k) {
+                        const unsigned int cs = WIDE ? pool32[e.z + k] : (unsigned int)p.pool[e.z + k];
+                        if (cs == kPad || (int)cs == best_idx) continue;
+                        retire(cs, nl, nh);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const unsigned int nq = min(s_qn, (unsigned int)kQueue);
+            for (unsigned int q = warp; q < nq; q += 32) {                    // a warp per pooled row
+                const uint4 row = s_q[q];
+                unsigned long long nl = 0, nh = 0;
+                if (AF) {
+                    const uint4 qv = __ldg(lst + (size_t)row.z * ESTRIDE + 1);
+                    nl = 0ull - (((unsigned long long)qv.y << 32) | qv.x);
+                    nh = 0ull - (((unsigned long long)qv.w << 32) | qv.z);
+                }
+                for (unsigned int k = lane; k < row.y; k += 32) {
+                    const unsigned int cs = WIDE ? pool32[row.x + k] : (unsigned int)p.pool[row.x + k];
+                    if (cs == kPad || (int)cs == best_idx) continue;          // the pick's own gain was reset above
+                    retire(cs, nl, nh);
+                }
+            }
+        }
+        cluster.sync();                               // all decrements of this step have landed before anybody scans again
+    }
+    cluster.sync();                                   // nobody writes into a peer's slice any more
+    for (int li = tid; li < n_own; li += blockDim.x) {
+        const int s = crank + CL * li;
+        p.gain_cnt[s] = s_cnt[li];
+        if (AF) { p.gain_lo[s] = s_lo[li]; p.gain_hi[s] = s_hi[li]; }
+        p.mask[s] = s_mask[li];
+    }
+    if (crank == 0 && tid == 0) {
+        st->step = step;
+        st->tot = tot;
+        st->stop = stop;
+        st->winner = -1;
+        st->regain = 0;
+        st->recompact = recompact;
+        if (want_light) st->tail_single = 1;
+        if (p.dbg) p.dbg[11] += 1;
+    }
+}
+
+// shared-memory layout of select_listcluster_kernel; 0 when a slice does not fit one SM
+int listcluster_layout(const SelParams &p, int CL, ListClusterCfg *cfg, size_t *smem_bytes)
+{
+    if (p.V >= 0xffffffffll || p.S <= 0) return 0;
+    const size_t n = ((size_t)p.S + CL - 1) / CL;
+    const size_t budget = 190 * 1024;                       // + 41 KB static (queue of pooled rows, exchange slots)
+    for (int stage = 1; stage >= 0; --stage) {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int)o; };
+        take(n * 4);
+        cfg->off_lo = take(p.af ? n * 8 : 0);
+        cfg->off_hi = take(p.af ? n * 8 : 0);
+        cfg->off_mask = take(n);
+        cfg->off_loff = take(stage ? n * 4 : 0);
+        cfg->off_llen = take(stage ? n * 4 : 0);
+        if (off > budget) continue;
+        cfg->n_own_max = (int)n;
+        cfg->stage_lists = stage;
+        cfg->min_recompact = 1u << 16;
+        *smem_bytes = off;
+        return 1;
+    }
+    return 0;
+}
+
 // CL: CTAs that share the per-sample state (1 = everything in one CTA)
 int tail_layout(const SelParams &p, int CL, TailCfg *cfg, size_t *smem_bytes)
 {
@@ -920,6 +1214,53 @@ static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg 
     lc.attrs = attr;
     lc.numAttrs = 1;
     UT_CUDA(cudaLaunchKernelEx(&lc, kernel, p, cfg, lists_total));
+    return UTMOS_OK;
+}
+
+template <int ESTRIDE, int CL, bool WIDE>
+static int launch_listcluster_t(cudaStream_t stream, const SelParams &p, const ListClusterCfg &cfg, size_t smem,
+                                unsigned long long lists_total, unsigned int light_rows)
+{
+    auto kernel = select_listcluster_kernel<ESTRIDE, CL, WIDE>;
+    UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (CL > 8) UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(CL);
+    lc.blockDim = dim3(1024);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    UT_CUDA(cudaLaunchKernelEx(&lc, kernel, p, cfg, lists_total, light_rows));
+    return UTMOS_OK;
+}
+
+// does the entry-divided cluster flavour exist for this problem (a slice of the per-sample state must fit one SM)?
+bool listcluster_fits(const SelParams &p)
+{
+    ListClusterCfg cfg;
+    size_t smem = 0;
+    return listcluster_layout(p, 16, &cfg, &smem) != 0;
+}
+
+// The entry-divided cluster flavour of the tail (select_listcluster_kernel); it returns with st->tail_single set once a pick
+// covers fewer than light_rows rows (0 = never) so that the single-SM tail can take over.
+int launch_listcluster(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int light_rows,
+                       int *n_launch)
+{
+    ListClusterCfg cfg;
+    size_t smem = 0;
+    if (!listcluster_layout(p, 16, &cfg, &smem)) { set_error("entry-divided tail: a slice of the state does not fit one SM"); return UTMOS_E_ARG; }
+    const bool wide = p.S > 65535;
+    if (p.af && wide) UT_TRY((launch_listcluster_t<2, 16, true>(stream, p, cfg, smem, lists_total, light_rows)));
+    else if (p.af) UT_TRY((launch_listcluster_t<2, 16, false>(stream, p, cfg, smem, lists_total, light_rows)));
+    else if (wide) UT_TRY((launch_listcluster_t<1, 16, true>(stream, p, cfg, smem, lists_total, light_rows)));
+    else UT_TRY((launch_listcluster_t<1, 16, false>(stream, p, cfg, smem, lists_total, light_rows)));
+    *n_launch += 1;
+    UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
 }
 
