@@ -237,6 +237,7 @@ def main():
     ap.add_argument("--tail-rows", type=int, default=-1, help="override the tail hand-over threshold")
     ap.add_argument("--regain-rows", type=int, default=-1, help="override the heavy-pick threshold (UTMOS_OPT_REGAIN_ROWS)")
     ap.add_argument("--single-rows", type=int, default=-1, help="override the cluster-tail -> single-CTA-tail threshold")
+    ap.add_argument("--list-budget", type=int, default=-1, help="override the edge-list budget (entries) of the list-driven tail")
     ap.add_argument("--heavy-rows", type=int, default=-1, help="override the entry-divided-cluster -> shared-memory tail threshold")
     args = ap.parse_args()
 
@@ -306,6 +307,8 @@ def main():
             dm = sm.local
         else:
             sm = dm = _native.DeviceMatrix(n_samples, mode, rows_hint=rows_n, device=device, flags=fl)
+        if args.list_budget >= 0:
+            dm.set_option(11, args.list_budget)
         t.append(time.perf_counter())
         if resident:
             parts = rows_dev if rows_dev is not None else [(cohort.rows.ptr, n_vars, cohort.af.ptr)]

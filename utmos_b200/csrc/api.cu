@@ -56,7 +56,10 @@ struct Trace {
 };
 constexpr size_t kStageBytes = 64ull << 20;      // per staging buffer (two pinned host + two device)
 constexpr int kGraphSteps = 32;                  // step pairs per CUDA graph replay
-constexpr unsigned long long kListBudget = 1ull << 24;       // edge-list entries (16 B each; 32 B for AF flavours)
+// edge-list entries (16 B each; 32 B for AF flavours).  2^24 until the entry-divided cluster tail existed; with it a heavy
+// tail step costs ~5 us where a head step costs 20-60 us, so the hand-over may come as early as the lists fit 1-2 GB
+// (8 x 1,103,547 rows on one GPU: 36.5 -> 32.1 ms; the 1kGP shape hands over on the rows-per-pick rule either way)
+constexpr unsigned long long kListBudget = 1ull << 26;
 constexpr unsigned long long kListBudgetWide = 1ull << 28;   // S > 65,535: the rare variants of a 100k-sample cohort alone
                                                              // hold more than 2^24 bits, and the head costs ~20-100 us per step
 enum { T_H2D = 0, T_INGEST = 1, T_TRANSPOSE = 2, T_GAIN = 3, T_SELECT = 4, T_COUNT = 5 };
@@ -144,6 +147,7 @@ struct utmos_ctx {
     unsigned long long *d_local0_lo = nullptr, *d_local0_hi = nullptr, *d_local_lo = nullptr, *d_local_hi = nullptr;
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
+    unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
     unsigned int tail_heavy_rows = 1024;  // list-driven tail: picks that cover at least this many rows are run by the entry-divided
                                           // 16-CTA cluster kernel (gains in L2), lighter ones from one SM's shared memory (0 = never)
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
@@ -656,7 +660,7 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     }
     p.tail_budget = c->tail_budget;
     // N ranks: N times the rows per pick at the same sparsity (measured on 4 x B200: 1536 per rank beats 2048)
-    p.tail_rows = c->mg_world > 1 ? std::min(c->tail_rows, 1536u) * (unsigned int)c->mg_world : c->tail_rows;
+    p.tail_rows = c->mg_world > 1 && c->tail_rows == 2048u ? 1536u * (unsigned int)c->mg_world : c->tail_rows;
     // one GPU, many rows: a pick covers rows in proportion to V, so the hand-over point moves with it (8 x 1,103,547 rows
     // x 2,504 samples: 46.5 ms with 16,384 against 73.1 ms with 2,048; the 1kGP shape keeps 2,048)
     if (c->mg_world == 1 && c->tail_rows == 2048u && c->S <= 65535)
@@ -1366,7 +1370,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         // Tail: one CTA runs all remaining steps from the lists (on every rank, identically, when multi-GPU).
         const bool wide = c->S > 65535;
         const size_t pool_elem = wide ? 4 : 2;
-        const unsigned long long list_budget = multi ? c->mg_list_cap - 64 : (wide ? kListBudgetWide : kListBudget);
+        const unsigned long long list_budget = multi ? c->mg_list_cap - 64 : (c->list_budget ? c->list_budget : (wide ? kListBudgetWide : kListBudget));
         const size_t estride = af ? 2 : 1;
         c->tail_budget = tail_ok ? list_budget : 0;
         auto reserve_lists = [&](int which, unsigned long long entries) -> int {
@@ -1734,7 +1738,7 @@ int utmos_mgpu_export(utmos_ctx *c, int rank, int world, uint8_t *handle_out)
     c->mg_list_cap = 0;
     if (c->mg_allow_tail && c->mg_merged_rows > 0 && c->mg_merged_rows < 0xffffffffll && tail_possible(c->S, af ? 1 : 0) &&
         !(c->flags & (UTMOS_F_NO_TAIL | UTMOS_F_NO_TRANSPOSE)))
-        c->mg_list_cap = std::min<unsigned long long>(c->S > 65535 ? kListBudgetWide : kListBudget, c->total_bits) + 64;
+        c->mg_list_cap = std::min<unsigned long long>(c->list_budget ? c->list_budget : (c->S > 65535 ? kListBudgetWide : kListBudget), c->total_bits) + 64;
     const MgLayout l = mg_layout(S, world, af, c->mg_list_cap, c->mg_merged_rows);
     cudaIpcMemHandle_t h;
     UT_TRY(mg_block_acquire(c->device, l.bytes, &c->mg_block, &h));
@@ -1843,6 +1847,11 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
     if (option == UTMOS_OPT_GLOBAL_ROWS) { c->global_rows = value; return UTMOS_OK; }
     if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
+    if (option == UTMOS_OPT_LIST_BUDGET) {
+        if (c->finalized) { set_error("set_option: the list budget is fixed at finalize"); return UTMOS_E_ARG; }
+        c->list_budget = (unsigned long long)std::max<int64_t>(0, std::min<int64_t>(value, 1ll << 30));
+        return UTMOS_OK;
+    }
     if (option == UTMOS_OPT_TAIL_HEAVY_ROWS) { c->tail_heavy_rows = (unsigned int)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_SINGLE_ROWS) { c->tail_single_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");
