@@ -148,7 +148,7 @@ struct utmos_ctx {
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
     unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
-    unsigned int tail_heavy_rows = 1024;  // list-driven tail: picks that cover at least this many rows are run by the entry-divided
+    unsigned int tail_heavy_rows = 768;   // list-driven tail: picks that cover at least this many rows are run by the entry-divided
                                           // 16-CTA cluster kernel (gains in L2), lighter ones from one SM's shared memory (0 = never)
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
                                           // (measured on the 1kGP shape: not faster than one CTA, so off by default)
@@ -1422,15 +1422,15 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         };
         while (true) {
             SelParams q = make_params(c, false);
-            if (c->lists_valid && c->tail_heavy_rows > 0 && !st.tail_single && listcluster_fits(q)) {
+            if (c->lists_valid && c->tail_heavy_rows > 0 && !(st.tail_single & 2u) && listcluster_fits(q)) {
                 // heavy picks: the entries of the pick divided over a 16-CTA cluster, gains in L2 (select_listcluster_kernel);
-                // it hands over (st.tail_single) once a pick covers fewer than tail_heavy_rows rows
+                // it hands over (bit 1 of st.tail_single) once a pick covers fewer than tail_heavy_rows rows
                 UT_TRY(launch_listcluster(c->stream, q, c->lists_total, c->tail_heavy_rows, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 c->flavour_used = multi ? 5 : 3;
             } else if (c->lists_valid) {
                 // heavy picks: cluster of 8 CTAs, each applying the decrements of the samples it owns; light picks: one CTA
-                const unsigned int single_rows = st.tail_single ? 0u : c->tail_single_rows;
+                const unsigned int single_rows = (st.tail_single & 1u) ? 0u : c->tail_single_rows;
                 const bool cluster = single_rows > 0 || tail_cluster_size(q, false) != 1;     // wide / mid-size cohorts: sliced state
                 uint32_t *live_priv = nullptr;
                 if (cluster && !tail_live_in_smem(q, cluster)) {

@@ -43,7 +43,8 @@ struct SelState {
     unsigned int want_tail;    // head kernel returned because the tail kernel should take over
     unsigned int recompact;    // tail kernel returned because at most half of its list entries are still live
     unsigned int regain;       // 1 = gains are stale: the pick retired too many rows to subtract, recompute them
-    unsigned int tail_single;  // the cluster flavour of the tail kernel handed over to the single-CTA flavour
+    unsigned int tail_single;  // bit 0: the owner-computes cluster tail handed over to the single-CTA flavour; bit 1: the
+                               // entry-divided cluster tail handed over to the shared-memory flavours (picks got light)
     unsigned long long mgpu_seq;    // multi-GPU exchange sequence number (monotonic over the selection)
     unsigned long long live_bits;   // sum of all gains = set bits in rows not yet covered (sum_gains_kernel)
 };

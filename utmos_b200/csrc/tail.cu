@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(1024, 1) select_tail_kernel(SelParams p, TailC
             st->winner = -1;
             st->regain = 0;
             st->recompact = recompact;
-            if (want_single) st->tail_single = 1;
+            if (want_single) st->tail_single |= 1u;
         }
     }
 #undef UT_OWNED
@@ -792,19 +792,12 @@ __device__ __forceinline__ void dsmem_red_add(uint32_t addr, unsigned int v)
 {
     asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned int dsmem_atom_add(uint32_t addr, unsigned int v)
-{
-    unsigned int old;
-    asm volatile("atom.relaxed.cluster.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-    return old;
-}
-// 64-bit add on a peer's shared memory as two 32-bit atomics with carry (cf. smem_add64)
+// 64-bit add on a slice of the cluster's shared memory.  SASS: one ATOM.E.ADD.64 that the memory system performs when the
+// address is a peer's (15 of 16 cases; nothing comes back), and the ATOMS.CAST.SPIN compare-and-swap loop when it is this
+// CTA's own.  (Two 32-bit atomics with carry, as in smem_add64, need the old low word back: a remote round trip per limb.)
 __device__ __forceinline__ void dsmem_add64(uint32_t addr, unsigned long long v)
 {
-    const unsigned int lo = (unsigned int)v, hi = (unsigned int)(v >> 32);
-    const unsigned int old = dsmem_atom_add(addr, lo);
-    const unsigned int carry = (old + lo) < old ? 1u : 0u;
-    if (hi + carry) dsmem_red_add(addr + 4, hi + carry);
+    asm volatile("red.relaxed.cluster.shared::cluster.add.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 
 struct ListClusterCfg {
@@ -1027,7 +1020,7 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         st->winner = -1;
         st->regain = 0;
         st->recompact = recompact;
-        if (want_light) st->tail_single = 1;
+        if (want_light) st->tail_single |= 2u;
         if (p.dbg) p.dbg[11] += 1;
     }
 }
@@ -1246,7 +1239,7 @@ bool listcluster_fits(const SelParams &p)
     return listcluster_layout(p, 16, &cfg, &smem) != 0;
 }
 
-// The entry-divided cluster flavour of the tail (select_listcluster_kernel); it returns with st->tail_single set once a pick
+// The entry-divided cluster flavour of the tail (select_listcluster_kernel); it returns with bit 1 of st->tail_single set once a pick
 // covers fewer than light_rows rows (0 = never) so that the single-SM tail can take over.
 int launch_listcluster(cudaStream_t stream, const SelParams &p, unsigned long long lists_total, unsigned int light_rows,
                        int *n_launch)
