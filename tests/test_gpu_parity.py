@@ -584,6 +584,32 @@ def test_hand_over_without_gain_recompute_on_a_large_input():
         assert np.array_equal(idx, results[0][0]) and np.array_equal(new, results[0][1]) and stop == results[0][2]
 
 
+@pytest.mark.parametrize("mode", ["count", "af"])
+def test_list_budget_moves_the_hand_over_not_the_answer(mode):
+    """UTMOS_OPT_LIST_BUDGET (before finalize): a budget the live bits exceed for most of the selection keeps the head
+    kernels running longer, a generous one hands over at once; the report rows are the oracle's either way.  After
+    finalize the option is refused."""
+    n_vars, n_samples = 60_000, 1200
+    coh = synth.DeviceCohort(5, n_vars, n_samples)
+    gt, af = coh.to_host()
+    use_af = mode == "af"
+    mask = np.ones(n_samples, np.uint8)
+    o_idx, o_new, o_score, _ = orc.greedy_c(gt, n_samples, mask, None, af if use_af else None, n_samples, exact=True)
+    for budget in (1 << 12, 1 << 18, 0):
+        dm = _native.DeviceMatrix(n_samples, _native.AF_F64 if use_af else _native.AF_NONE, rows_hint=n_vars)
+        dm.set_option(11, budget)
+        dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr if use_af else 0)
+        dm.finalize()
+        with pytest.raises(_native.NativeError):
+            dm.set_option(11, 1 << 20)
+        dm.set_option(3, 1 << 30)                                    # rows-per-pick rule out of the way: the budget decides
+        dm.begin(mask)
+        idx, new, score, _ = dm.steps(n_samples)
+        dm.close()
+        assert np.array_equal(idx, o_idx) and np.array_equal(new, o_new) and np.array_equal(score, o_score), budget
+    coh.close()
+
+
 def test_full_shape_properties_and_mode_agreement():
     """1kGP chr22 shape (2,504 x 1,103,547), --count -1: invariants the greedy loop must satisfy at any size,
     and all four kernel flavours must give the same ordering."""

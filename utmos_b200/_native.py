@@ -345,7 +345,9 @@ class DeviceMatrix:
         return out
 
     def set_option(self, option, value):
-        """utmos_set_option: 1 regain rows, 2 per-step timestamps, 3 tail hand-over rows."""
+        """utmos_set_option (include/utmos_b200.h UTMOS_OPT_*): 1 regain rows, 2 per-step timestamps, 3 tail hand-over rows,
+        5 owner-computes-cluster -> single-SM rows, 10 entry-divided-cluster -> shared-memory tail rows, 11 list budget
+        (before finalize)."""
         check(lib().utmos_set_option(self._ctx, int(option), int(value)))
 
     def set_regain_rows(self, rows):

@@ -148,7 +148,8 @@ struct utmos_ctx {
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
     unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
-    unsigned int tail_heavy_rows = 768;   // list-driven tail: picks that cover at least this many rows are run by the entry-divided
+    unsigned int tail_heavy_rows = 0xffffffffu;   // (0xffffffff = default: 768 in count mode, 1 = every tail step with AF)
+                                          // list-driven tail: picks that cover at least this many rows are run by the entry-divided
                                           // 16-CTA cluster kernel (gains in L2), lighter ones from one SM's shared memory (0 = never)
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
                                           // (measured on the 1kGP shape: not faster than one CTA, so off by default)
@@ -1422,10 +1423,13 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         };
         while (true) {
             SelParams q = make_params(c, false);
-            if (c->lists_valid && c->tail_heavy_rows > 0 && !(st.tail_single & 2u) && listcluster_fits(q)) {
+            // count mode: one SM retires a light pick faster (1.5 us + 3.8 ns per row against 3.5 us flat); AF: two 64-bit
+            // shared-memory adds per decrement make one SM the slower choice whatever the pick covers
+            const unsigned int heavy_rows = c->tail_heavy_rows != 0xffffffffu ? c->tail_heavy_rows : (af ? 1u : 768u);
+            if (c->lists_valid && heavy_rows > 0 && !(st.tail_single & 2u) && listcluster_fits(q)) {
                 // heavy picks: the entries of the pick divided over a 16-CTA cluster, gains in L2 (select_listcluster_kernel);
                 // it hands over (bit 1 of st.tail_single) once a pick covers fewer than tail_heavy_rows rows
-                UT_TRY(launch_listcluster(c->stream, q, c->lists_total, c->tail_heavy_rows, &c->n_launch));
+                UT_TRY(launch_listcluster(c->stream, q, c->lists_total, heavy_rows, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 c->flavour_used = multi ? 5 : 3;
             } else if (c->lists_valid) {
@@ -1852,7 +1856,7 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
         c->list_budget = (unsigned long long)std::max<int64_t>(0, std::min<int64_t>(value, 1ll << 30));
         return UTMOS_OK;
     }
-    if (option == UTMOS_OPT_TAIL_HEAVY_ROWS) { c->tail_heavy_rows = (unsigned int)std::max<int64_t>(0, std::min<int64_t>(value, 0x7fffffff)); return UTMOS_OK; }
+    if (option == UTMOS_OPT_TAIL_HEAVY_ROWS) { c->tail_heavy_rows = value < 0 ? 0xffffffffu : (unsigned int)std::min<int64_t>(value, 0x7fffffff); return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_SINGLE_ROWS) { c->tail_single_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
     set_error("set_option: unknown option");
     return UTMOS_E_ARG;

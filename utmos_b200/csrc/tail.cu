@@ -792,6 +792,35 @@ __device__ __forceinline__ void dsmem_red_add(uint32_t addr, unsigned int v)
 {
     asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// 16 bytes into a peer's shared memory, counted on the PEER's mbarrier when they have landed (st.async): the winners'
+// exchange needs no cluster barrier (a MEMBAR.ALL.GPU + arrive/wait + L1 invalidate, ~1,100 cycles), only this round trip
+__device__ __forceinline__ void dsmem_store16_tx(uint32_t addr, uint4 v, uint32_t bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_init(unsigned long long *bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void lc_mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LC_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni LC_WAIT_DONE;\n\t"
+        "bra.uni LC_WAIT_LOOP;\n\t"
+        "LC_WAIT_DONE:\n\t"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 // 64-bit add on a slice of the cluster's shared memory.  SASS: one ATOM.E.ADD.64 that the memory system performs when the
 // address is a peer's (15 of 16 cases; nothing comes back), and the ATOMS.CAST.SPIN compare-and-swap loop when it is this
 // CTA's own.  (Two 32-bit atomics with carry, as in smem_add64, need the old low word back: a remote round trip per limb.)
@@ -807,7 +836,18 @@ struct ListClusterCfg {
     unsigned int min_recompact;
 };
 
-template <int ESTRIDE, int CL, bool WIDE>
+// FAST: count mode without weights -> candidates are (gain count of a selectable sample, index): two REDUX per reduction
+template <bool FAST>
+__device__ __forceinline__ Cand lc_warp_best(Cand c)
+{
+    if (FAST) {
+        const uint2 w = warp_argmax_u32(c.lo, (unsigned int)c.idx);
+        return Cand{0u, w.x, (int)w.y, w.x};
+    }
+    return warp_argmax(c);
+}
+
+template <int ESTRIDE, bool FAST, int CL, bool WIDE>
 __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p, ListClusterCfg cfg, unsigned long long lists_total,
                                                                      unsigned int light_rows)
 {
@@ -821,7 +861,8 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
     __shared__ uint4 s_xbest[2][16];
     __shared__ uint4 s_xlist[2][16];                 // {sum of owned gains lo, hi, list offset, list length}
     __shared__ uint4 s_q[kQueue];                    // pooled rows this CTA found: {pool base, carriers, entry index, 0}
-    __shared__ unsigned int s_qn;
+    __shared__ unsigned int s_qn[2];                 // pooled rows queued in this step / zeroed for the next one
+    __shared__ __align__(8) unsigned long long s_xbar;   // counts the 2 x CL 16-byte slots of one exchange
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(lc_smem);
     unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(lc_smem + cfg.off_lo);
     unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(lc_smem + cfg.off_hi);
@@ -845,6 +886,7 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         s_mask[li] = p.mask[s];
         if (cfg.stage_lists) { s_loff[li] = p.list_off[s]; s_llen[li] = p.list_len[s]; }
     }
+    if (tid == 0) { lc_mbar_init(&s_xbar, 1u); s_qn[0] = s_qn[1] = 0u; }
     __syncthreads();
     cluster.sync();
     // the slice of sample c: CTA c % CL, slot c / CL
@@ -857,54 +899,80 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         }
     };
 
+    // integer keys: one warp scans a slice of up to 512 samples alone (16 per lane) -- no block barrier, no second reduction
+    // level.  Float64 scores (a 128-bit fixed-point conversion per sample) want every warp: C3 tail 5.75 ms against 6.86 ms.
+    const bool one_warp = n_own <= (FAST ? 512 : 32);
     while (stop == 0 && step < limit) {
-        // ---- argmax over the samples this CTA owns
+        // ---- argmax over the samples this CTA owns; the sum of their gains only on the steps that look at it
+        const bool check = since_check + 1 >= 64;
+        const int qp = xpar;
         Cand b{0u, 0u, 0x7fffffff, 0u};
         unsigned long long acc = 0;
-        if (tid == 0) s_qn = 0;                       // read last before the barrier that ended the previous step
-        for (int li = tid; li < n_own; li += blockDim.x) {
-            const int s = crank + CL * li;
-            const unsigned int c = s_cnt[li];
-            double g = 0.0;
-            if (s_mask[li] == 1) {
-                g = AF ? fixed_to_double(s_lo[li], s_hi[li], p.L, p.scale) : (double)c;
-                if (has_w) g *= __ldg(p.weights + s);
-                acc += c;
-            }
-            const unsigned long long k = score_key(g);
-            const Cand c2{(unsigned int)(k >> 32), (unsigned int)k, s, c};
-            if (cand_better(c2, b)) b = c2;
+        if (tid == 0) {
+            s_qn[qp ^ 1] = 0;                         // next step's queue: last read before the barrier that ended the previous step
+            lc_mbar_expect_tx(&s_xbar, (unsigned int)CL * 32u);
         }
-        b = warp_argmax(b);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) { s_red[warp] = b; s_sum[warp] = acc; }
-        __syncthreads();
-        if (warp == 0) {
-            b = warp_argmax(s_red[lane]);
-            acc = s_sum[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane < CL) {
-                unsigned int off = 0, len = 0;
-                if (b.idx != 0x7fffffff) {
-                    const int li = (b.idx - crank) / CL;
-                    off = cfg.stage_lists ? s_loff[li] : __ldg(p.list_off + b.idx);
-                    len = cfg.stage_lists ? s_llen[li] : __ldg(p.list_len + b.idx);
+        if (!one_warp || warp == 0) {
+            for (int li = one_warp ? lane : tid; li < n_own; li += one_warp ? 32 : (int)blockDim.x) {
+                const int s = crank + CL * li;
+                const unsigned int c = s_cnt[li];
+                const bool ok = s_mask[li] == 1;
+                Cand c2;
+                if (FAST) {
+                    c2 = Cand{0u, ok ? c : 0u, s, ok ? c : 0u};
+                } else {
+                    double g = 0.0;
+                    if (ok) {
+                        g = AF ? fixed_to_double(s_lo[li], s_hi[li], p.L, p.scale) : (double)c;
+                        if (has_w) g *= __ldg(p.weights + s);
+                    }
+                    const unsigned long long kk = score_key(g);
+                    c2 = Cand{(unsigned int)(kk >> 32), (unsigned int)kk, s, c};
                 }
-                cluster.map_shared_rank(&s_xbest[xpar][0], lane)[crank] = make_uint4(b.hi, b.lo, (unsigned int)b.idx, b.cnt);
-                cluster.map_shared_rank(&s_xlist[xpar][0], lane)[crank] = make_uint4((unsigned int)acc, (unsigned int)(acc >> 32), off, len);
+                if (ok) acc += c;
+                if (cand_better(c2, b)) b = c2;
+            }
+            b = lc_warp_best<FAST>(b);
+            if (check) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             }
         }
-        cluster.sync();
+        if (!one_warp) {
+            if (lane == 0) { s_red[warp] = b; s_sum[warp] = acc; }
+            __syncthreads();
+            if (warp == 0) {
+                b = lc_warp_best<FAST>(s_red[lane]);
+                if (check) {
+                    acc = s_sum[lane];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                }
+            }
+        }
+        if (warp == 0 && lane < CL) {
+            unsigned int off = 0, len = 0;
+            if (b.idx != 0x7fffffff) {
+                const int li = (b.idx - crank) / CL;
+                off = cfg.stage_lists ? s_loff[li] : __ldg(p.list_off + b.idx);
+                len = cfg.stage_lists ? s_llen[li] : __ldg(p.list_len + b.idx);
+            }
+            const uint32_t bar = dsmem_addr(&s_xbar, (unsigned int)lane);
+            dsmem_store16_tx(dsmem_addr(&s_xbest[xpar][crank], (unsigned int)lane), make_uint4(b.hi, b.lo, (unsigned int)b.idx, b.cnt), bar);
+            dsmem_store16_tx(dsmem_addr(&s_xlist[xpar][crank], (unsigned int)lane),
+                             make_uint4((unsigned int)acc, (unsigned int)(acc >> 32), off, len), bar);
+        }
+        lc_mbar_wait(&s_xbar, (unsigned int)xpar);   // exchange number n completes phase n of the mbarrier: parity = xpar
         unsigned int off, len;
         {
             const uint4 o = lane < CL ? s_xbest[xpar][lane] : make_uint4(0u, 0u, 0x7fffffffu, 0u);
             const uint4 l = lane < CL ? s_xlist[xpar][lane] : make_uint4(0u, 0u, 0u, 0u);
-            b = warp_argmax(Cand{o.x, o.y, (int)o.z, o.w});
-            acc = ((unsigned long long)l.y << 32) | l.x;
+            b = lc_warp_best<FAST>(Cand{o.x, o.y, (int)o.z, o.w});
+            if (check) {
+                acc = ((unsigned long long)l.y << 32) | l.x;
 #pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+                for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+            }
             const int src = b.idx == 0x7fffffff ? 0 : b.idx % CL;             // the winner's CTA holds its list position
             off = __shfl_sync(0xffffffffu, l.z, src);
             len = __shfl_sync(0xffffffffu, l.w, src);
@@ -912,7 +980,7 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         }
         const int best_idx = b.idx;
         const unsigned int best_cnt = b.cnt;
-        const double best_score = key_score(b.hi, b.lo);
+        const double best_score = FAST ? (double)b.lo : key_score(b.hi, b.lo);
         if (p.S == 0 || best_idx == 0x7fffffff || best_score == 0.0) {        // utmos/select.py:51-52
             stop = UTMOS_STOP_ZERO;
             break;
@@ -968,7 +1036,7 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
                 for (int j = 0; j < kInl; ++j)
                     if (j < (int)n) retire(c[j], nl, nh);
             } else {
-                const unsigned int slot = atomicAdd(&s_qn, 1u);
+                const unsigned int slot = atomicAdd(&s_qn[qp], 1u);
                 if (slot < (unsigned int)kQueue) {
                     s_q[slot] = make_uint4(e.z, e.w, i, 0u);
                 } else {                                                      // queue full: this thread retires the row itself
@@ -988,7 +1056,7 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         }
         __syncthreads();
         {
-            const unsigned int nq = min(s_qn, (unsigned int)kQueue);
+            const unsigned int nq = min(s_qn[qp], (unsigned int)kQueue);
             for (unsigned int q = warp; q < nq; q += 32) {                    // a warp per pooled row
                 const uint4 row = s_q[q];
                 unsigned long long nl = 0, nh = 0;
@@ -1210,11 +1278,11 @@ static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg 
     return UTMOS_OK;
 }
 
-template <int ESTRIDE, int CL, bool WIDE>
+template <int ESTRIDE, bool FAST, int CL, bool WIDE>
 static int launch_listcluster_t(cudaStream_t stream, const SelParams &p, const ListClusterCfg &cfg, size_t smem,
                                 unsigned long long lists_total, unsigned int light_rows)
 {
-    auto kernel = select_listcluster_kernel<ESTRIDE, CL, WIDE>;
+    auto kernel = select_listcluster_kernel<ESTRIDE, FAST, CL, WIDE>;
     UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CL > 8) UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t lc = {};
@@ -1248,10 +1316,11 @@ int launch_listcluster(cudaStream_t stream, const SelParams &p, unsigned long lo
     size_t smem = 0;
     if (!listcluster_layout(p, 16, &cfg, &smem)) { set_error("entry-divided tail: a slice of the state does not fit one SM"); return UTMOS_E_ARG; }
     const bool wide = p.S > 65535;
-    if (p.af && wide) UT_TRY((launch_listcluster_t<2, 16, true>(stream, p, cfg, smem, lists_total, light_rows)));
-    else if (p.af) UT_TRY((launch_listcluster_t<2, 16, false>(stream, p, cfg, smem, lists_total, light_rows)));
-    else if (wide) UT_TRY((launch_listcluster_t<1, 16, true>(stream, p, cfg, smem, lists_total, light_rows)));
-    else UT_TRY((launch_listcluster_t<1, 16, false>(stream, p, cfg, smem, lists_total, light_rows)));
+#define UT_LC(E, F, W) UT_TRY((launch_listcluster_t<E, F, 16, W>(stream, p, cfg, smem, lists_total, light_rows)))
+    if (p.af) { if (wide) UT_LC(2, false, true); else UT_LC(2, false, false); }
+    else if (p.weights) { if (wide) UT_LC(1, false, true); else UT_LC(1, false, false); }
+    else { if (wide) UT_LC(1, true, true); else UT_LC(1, true, false); }
+#undef UT_LC
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
     return UTMOS_OK;
