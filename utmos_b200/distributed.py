@@ -92,19 +92,22 @@ class ShardedMatrix:
     def finalize(self):
         comm = self.comm
         kept = self.local.rows()
-        rows_all = comm.all_gather_bytes(np.array([kept], dtype=np.int64).view(np.uint8)).view(np.int64).reshape(-1)
-        total = int(rows_all.sum())
-        self.local.set_option(4, total)                       # same fixed-point scale on every rank
+        with_af = self.af_mode != _native.AF_NONE
+        rows_all = None
+        if with_af or comm.world == 1:
+            # AF limbs are fixed point: every rank must use the scale of the WHOLE matrix before it reduces its columns
+            rows_all = comm.all_gather_bytes(np.array([kept], dtype=np.int64).view(np.uint8)).view(np.int64).reshape(-1)
+            self.local.set_option(4, int(rows_all.sum()))
         local_vc = self.local.finalize()
         local_vc = np.asarray(local_vc, dtype=np.int64)
         if comm.world > 1:
             # ONE all-gather carries everything the ranks have to sum: step-0 gains (counts, and the AF limbs when there
-            # are any), var_count and "I have a sample-major copy"; every rank adds the shares up in rank order, so the
-            # sums are identical everywhere.  (Six gloo collectives per finalize used to cost ~5 ms on 8 ranks.)
+            # are any), var_count, "I have a sample-major copy" and the rank's row count; every rank adds the shares up in
+            # rank order, so the sums are identical everywhere.  (Six gloo collectives per finalize used to cost ~5 ms on
+            # 8 ranks; count mode needs nothing from its peers before this point.)
             cnt, lo, hi = self.local.get_gains0()
             has_cols = int(self.local.info()["has_sample_major"])
-            with_af = self.af_mode != _native.AF_NONE
-            parts = [cnt.astype(np.int64), local_vc, np.array([has_cols], dtype=np.int64)]
+            parts = [cnt.astype(np.int64), local_vc, np.array([has_cols, kept], dtype=np.int64)]
             if with_af:
                 parts += [lo.view(np.int64), hi.view(np.int64)]
             mine = np.concatenate(parts)
@@ -113,9 +116,11 @@ class ShardedMatrix:
                 summed = shares.sum(axis=0, dtype=np.int64)              # limbs wrap modulo 2^64 like on the device
             n = self.n_samples
             cnt_sum, vc_sum, cols_sum = summed[:n], summed[n:2 * n], int(summed[2 * n])
+            rows_all = shares[:, 2 * n + 1].copy()
+            total = int(rows_all.sum())
             if with_af:
-                lo = summed[2 * n + 1:3 * n + 1].view(np.uint64)
-                hi = summed[3 * n + 1:4 * n + 1].view(np.uint64)
+                lo = summed[2 * n + 2:3 * n + 2].view(np.uint64)
+                hi = summed[3 * n + 2:4 * n + 2].view(np.uint64)
             self.local.set_gains0(cnt_sum.astype(np.uint32), lo, hi, total)
             # merged row numbering for the hand-over to the replicated tail (every rank's rows padded to 32)
             padded = (rows_all + 31) // 32 * 32
@@ -124,6 +129,7 @@ class ShardedMatrix:
             self.local.mgpu_connect(comm.all_gather_bytes(handle))
             self.var_count = vc_sum.copy()
         else:
+            total = int(rows_all.sum())
             self.var_count = comm.all_reduce_sum(local_vc)
         self.num_vars = total
         comm.barrier()
