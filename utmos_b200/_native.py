@@ -174,6 +174,9 @@ class DeviceMatrix:
         if env_flags:
             flags = (flags & ~F_REF_TIES) | env_flags             # an explicit flavour wins over the tie-replay flavour
         check(lib().utmos_create(ctypes.byref(self._ctx), device, self.n_samples, int(rows_hint), af_mode, flags))
+        for item in filter(None, os.environ.get("UTMOS_B200_OPTIONS", "").split(",")):   # "10=1,3=4096": A/B runs of the tuning options
+            option, value = item.split("=")
+            self.set_option(int(option), int(value))
 
     # -- ingestion ---------------------------------------------------------------------------------
     def append_packed(self, gt, af=None):
