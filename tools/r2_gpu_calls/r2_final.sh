@@ -12,6 +12,9 @@ echo "ncu launches rc=$?"
 python bench.py --steps 1 --warmup 1 --no-cpu --no-verify > gpurun_out/r2_plain_for_ncu2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:select_tail_kernel -s 6 -c 6 -o gpurun_out/r2_tail_final python bench.py --steps 1 --warmup 1 --no-cpu --no-verify > gpurun_out/r2_ncu_tail.log 2>&1
 echo "ncu tail rc=$?"
+python bench.py --config c3 --steps 1 --warmup 1 --no-cpu --no-verify > gpurun_out/r2_plain_for_ncu3.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:select_listcluster_kernel -s 1 -c 1 -o gpurun_out/r2_entry_cluster_c3 python bench.py --config c3 --steps 1 --warmup 1 --no-cpu --no-verify > gpurun_out/r2_ncu_entry_cluster.log 2>&1
+echo "ncu entry-divided tail rc=$?"
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/r2_bench_final.json").read().strip().splitlines()[-1])
