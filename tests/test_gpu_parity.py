@@ -184,10 +184,17 @@ def test_random_cases_match_reference_and_exact_oracle(flags):
     assert near_ties == H.NEAR_TIE_CASES
 
 
-def test_ref_ties_reproduces_the_reference_order_on_every_recorded_af_case():
+REF_TIE_FLAVOURS = {"steps_then_replaying_tail": _native.F_REF_TIES, "step_kernels_only": _native.F_REF_TIES | _native.F_STEP_KERNELS}
+
+
+@pytest.mark.parametrize("flavour", list(REF_TIE_FLAVOURS))
+def test_ref_ties_reproduces_the_reference_order_on_every_recorded_af_case(flavour):
     """UTMOS_F_REF_TIES: candidates whose exact scores (nearly) tie are ordered by replaying the reference's sequential
     float64 sums (utmos/select.py:37-48).  All 72 recorded `--af` cases -- including the 13 pinned near-tie cases that the
-    exact-arithmetic order gets differently -- must give the unmodified reference's report, and scores within 1e-9."""
+    exact-arithmetic order gets differently -- must give the unmodified reference's report, and scores within 1e-9.
+    Both flavours: per-step kernels handing over to the entry-divided tail with the replay inside, and per-step kernels
+    all the way."""
+    ref_flags = REF_TIE_FLAVOURS[flavour]
     cases, arrays = H.random_cases()
     checked = 0
     for pos, case in enumerate(cases):
@@ -202,7 +209,7 @@ def test_ref_ties_reproduces_the_reference_order_on_every_recorded_af_case():
         steps = orc.resolve_count(opt["count"], n)
         parts = [packed[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
         afs = [af[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
-        idx, new, score, _stop, var_count, num_vars, _ = run_gpu(parts, afs, n, mask, wts, steps, _native.AF_F64, _native.F_REF_TIES)
+        idx, new, score, _stop, var_count, num_vars, _ = run_gpu(parts, afs, n, mask, wts, steps, _native.AF_F64, ref_flags)
         rows = orc.report_rows(names, var_count, idx, new, num_vars)
         got = [[r[0], r[1], r[2], r[3], str(r[4])] for r in rows]
         gold = [[g[0], g[1], g[2], g[3], g[5]] for g in case["rows"]]
@@ -646,7 +653,8 @@ def test_full_shape_properties_and_mode_agreement():
     assert np.array_equal(vc, gold["var_count"])
 
 
-def test_full_shape_c3_ref_ties_matches_reference_order_oracle():
+@pytest.mark.parametrize("flavour", list(REF_TIE_FLAVOURS))
+def test_full_shape_c3_ref_ties_matches_reference_order_oracle(flavour):
     """Config C3 at its named shape with UTMOS_F_REF_TIES: every pick and new_count equals the plain-C oracle's run in the
     REFERENCE's arithmetic (mode 0: sequential float64 sums in row order, utmos/select.py:37-41; 150 s on one CPU core),
     which parts from the exact-arithmetic order at pick 225 of 1,239; winning scores within 1e-12."""
@@ -659,11 +667,12 @@ def test_full_shape_c3_ref_ties_matches_reference_order_oracle():
     mask = np.where(np.isin(names, names[: n_samples // 2]), 1, 2).astype(np.uint8)
     mask = np.where(np.isin(names, names[::97]), 2, mask).astype(np.uint8)
     coh = synth.DeviceCohort(0, n_vars, n_samples)
-    dm = _native.DeviceMatrix(n_samples, _native.AF_F64, rows_hint=n_vars, flags=_native.F_REF_TIES)
+    dm = _native.DeviceMatrix(n_samples, _native.AF_F64, rows_hint=n_vars, flags=REF_TIE_FLAVOURS[flavour])
     dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
     dm.finalize()
     dm.begin(mask, weights)
     idx, new, score, stop = dm.steps(n_samples)
+    assert dm.info()["ref_ties"] == 1 and dm.info()["flavour"] == (3 if flavour == "steps_then_replaying_tail" else 0)
     dm.close()
     coh.close()
     assert np.array_equal(idx, gold["idx"]) and np.array_equal(new, gold["new"]) and stop == int(gold["stop"])

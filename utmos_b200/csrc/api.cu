@@ -147,6 +147,7 @@ struct utmos_ctx {
     unsigned long long *d_local0_lo = nullptr, *d_local0_hi = nullptr, *d_local_lo = nullptr, *d_local_hi = nullptr;
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
+    bool ref_hybrid = false;              // UTMOS_F_REF_TIES without UTMOS_F_STEP_KERNELS: step kernels, then the REFT tail
     unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
     unsigned int tail_heavy_rows = 0xffffffffu;   // (0xffffffff = default: 768 in count mode, 1 = every tail step with AF or S > 65,535)
                                           // list-driven tail: picks that cover at least this many rows are run by the entry-divided
@@ -640,7 +641,7 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.selw = c->d_selw;
     p.weights = c->has_weights ? c->d_weights : nullptr;
     p.af_vals = c->d_af;
-    p.ref_ties = (c->flags & UTMOS_F_REF_TIES) ? 1 : 0;
+    p.ref_ties = ((c->flags & UTMOS_F_REF_TIES) && c->mg_world <= 1) ? 1 : 0;
     p.af_f32 = c->af_mode == UTMOS_AF_F32 ? 1 : 0;
     p.out_idx = c->d_out_idx;
     p.out_new = c->d_out_new;
@@ -775,8 +776,11 @@ int utmos_create(utmos_ctx **ctx_out, int device, int64_t n_samples, int64_t row
     c->af_mode = af_mode;
     c->flags = flags;
     if (flags & UTMOS_F_REF_TIES) {
-        if (af_mode != UTMOS_AF_NONE) c->flags |= UTMOS_F_STEP_KERNELS;    // the replay lives in argmax_step_kernel
-        else c->flags &= ~UTMOS_F_REF_TIES;                                 // count mode has no float sums to replay
+        // the replay lives in argmax_step_kernel and in the REFT flavour of select_listcluster_kernel: per-step kernels (with
+        // a streaming recompute after heavy picks) until the lists can be built, the entry-divided tail from there on.
+        // UTMOS_F_STEP_KERNELS given as well: per-step kernels all the way (the round-2 flavour, kept for A/B runs).
+        if (af_mode == UTMOS_AF_NONE) c->flags &= ~UTMOS_F_REF_TIES;        // count mode has no float sums to replay
+        else if (!(flags & UTMOS_F_STEP_KERNELS)) c->ref_hybrid = true;
     }
     // --af: the 8-CTA owner-computes flavour of the tail until a pick covers fewer than 64 rows (three shared-memory
     // atomics per decrement, two of them 64-bit: measured 10.0 ms against 11.9 ms for the tail of config C3)
@@ -1223,6 +1227,7 @@ int utmos_finalize(utmos_ctx *c, int64_t *num_vars_out, int64_t *var_count_out)
             return UTMOS_E_NOMEM;
         }
         c->flags &= ~(UTMOS_F_REF_TIES | UTMOS_F_STEP_KERNELS);
+        c->ref_hybrid = false;
     }
     tr.lap("sample-major allocation");
     if (c->d_cols) {
@@ -1353,8 +1358,10 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
         const bool multi = c->mg_world > 1;
         const bool af = c->af_mode != UTMOS_AF_NONE;
         int CL = 0, tail_ok = 0;
-        if (!multi && !(c->flags & UTMOS_F_NO_CLUSTER)) UT_TRY(cluster_plan(p, &CL));
+        const bool hybrid = c->ref_hybrid && !multi && p.ref_ties;
+        if (!multi && !hybrid && !(c->flags & UTMOS_F_NO_CLUSTER)) UT_TRY(cluster_plan(p, &CL));
         if (!multi && !(c->flags & UTMOS_F_NO_TAIL)) UT_TRY(tail_plan(p, &tail_ok));
+        if (hybrid) tail_ok = tail_ok && listcluster_fits(p);      // the only tail flavour with the replay
         if (multi) tail_ok = c->mg_list_cap > 0;          // same decision on every rank (utmos_mgpu_export)
         // heavy picks in count mode: subtract the newly covered rows (cover_decrement_kernel) instead of recomputing
         // every gain from the sample-major copy (regain_kernel).  Default since round 2 (full GPU suite green with it,
@@ -1427,7 +1434,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             // shared-memory adds per decrement make one SM the slower choice whatever the pick covers
             // more than 65,535 samples: the alternative is the owner-computes cluster tail, where every CTA walks every entry
             // (50,000 x 2 M: 6.3 against 8.0 us per step; 100,000 x 2 M: 7.4 against 9.3)
-            const unsigned int heavy_rows = c->tail_heavy_rows != 0xffffffffu ? c->tail_heavy_rows : ((af || wide) ? 1u : 768u);
+            const unsigned int heavy_rows = hybrid ? 1u : c->tail_heavy_rows != 0xffffffffu ? c->tail_heavy_rows : ((af || wide) ? 1u : 768u);
             if (c->lists_valid && heavy_rows > 0 && !(st.tail_single & 2u) && listcluster_fits(q)) {
                 // heavy picks: the entries of the pick divided over a 16-CTA cluster, gains in L2 (select_listcluster_kernel);
                 // it hands over (bit 1 of st.tail_single) once a pick covers fewer than tail_heavy_rows rows
@@ -1456,6 +1463,15 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
                 UT_TRY(launch_mgpu(c->stream, q, m, c->mg_grid, c->mg_block_threads, c->d_bar, c->d_partials, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
                 c->flavour_used = 4;
+            } else if (hybrid) {
+                // reference tie order, head: per-step kernels (argmax with the replay, cover; a pick that covers >= regain_rows
+                // rows only clears live bits and leaves st->regain set for the streaming recompute), a few steps per host check
+                for (int rep = 0; rep < 4; ++rep) {
+                    UT_TRY(launch_step_pair(c->stream, q, c->n_sms, &c->n_launch));
+                    UT_TRY(launch_regain(c->stream, q, &c->n_launch));
+                }
+                UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                c->flavour_used = 0;
             } else {
                 // a few launches are queued between host checks; once the live part is sparse enough the queued
                 // head kernels return immediately (they test st->live_bits at launch)
@@ -1485,6 +1501,21 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             tr.lap(c->lists_valid ? "tail launch" : "head launches");
             part_lap(c->lists_valid ? P_TAIL : P_HEAD);
             if (st.stop != 0 || st.step >= limit || st.abort_flag) break;
+            if (hybrid && c->lists_valid && st.tie_step) {
+                // a tie candidate with more live rows than the tail's sort buffer: this one step by the per-step kernels
+                UT_CUDA(cudaMemsetAsync(&c->d_state->tie_step, 0, sizeof(unsigned int), c->stream));
+                UT_TRY(launch_step_pair(c->stream, q, c->n_sms, &c->n_launch));
+                UT_TRY(launch_regain(c->stream, q, &c->n_launch));
+                UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
+                st.tie_step = 0;
+                continue;
+            }
+            if (hybrid && !c->lists_valid && tail_ok && st.step > 0) {
+                // the step kernels do not look at the hand-over rule: the host does, from the last pick's new_count
+                long long last_new = 0;
+                UT_CUDA(cudaMemcpy(&last_new, c->d_out_new + (st.step - 1), sizeof(last_new), cudaMemcpyDeviceToHost));
+                st.want_tail = last_new < (long long)q.tail_rows ? 1u : 0u;
+            }
             if (tail_ok && !c->lists_valid && st.want_tail && st.live_bits <= list_budget) {
                 if (multi) {
                     // replicated tail: every rank writes its live rows into the merged lists of all ranks (mgpu.cu)

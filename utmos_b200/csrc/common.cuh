@@ -45,6 +45,8 @@ struct SelState {
     unsigned int regain;       // 1 = gains are stale: the pick retired too many rows to subtract, recompute them
     unsigned int tail_single;  // bit 0: the owner-computes cluster tail handed over to the single-CTA flavour; bit 1: the
                                // entry-divided cluster tail handed over to the shared-memory flavours (picks got light)
+    unsigned int tie_step;     // reference tie order: the tail met a candidate it cannot replay; run this step with the step kernels
+    unsigned int pad0;
     unsigned long long mgpu_seq;    // multi-GPU exchange sequence number (monotonic over the selection)
     unsigned long long live_bits;   // sum of all gains = set bits in rows not yet covered (sum_gains_kernel)
 };

@@ -681,6 +681,7 @@ __global__ void __launch_bounds__(1024) argmax_step_kernel(SelParams p)
         const int holders = __syncthreads_count(mine > 0);                  // threads that hold a candidate
         const bool several = __syncthreads_or(mine > 1) || holders > 1;
         if (several) {
+            if (threadIdx.x == 0 && p.dbg) p.dbg[12] += 1;                  // steps decided by the replay
             Best rb{-1.0e308, 0x7fffffff, 0u};
             for (int base = 0; base < p.S; base += 1024) {                 // at most 1,024 candidates per round
                 const int s = base + (int)threadIdx.x;
@@ -731,12 +732,19 @@ __global__ void __launch_bounds__(1024) argmax_step_kernel(SelParams p)
 __global__ void __launch_bounds__(256) cover_step_kernel(SelParams p)
 {
     const int b = p.st->winner;
-    if (b < 0) return;
+    if (b < 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.st->regain = 0;
+        return;
+    }
+    // a pick that newly covers >= regain_rows rows (0 = never): only the live bits are cleared here, the gains are
+    // recomputed by the regain_kernel that follows (one streaming pass instead of one atomic per set bit of those rows)
+    const bool heavy = p.regain_rows && p.cols && p.out_new[p.st->step - 1] >= (long long)p.regain_rows;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.st->regain = heavy ? 1u : 0u;
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long nchunks = (p.colPitchW + 31) / 32;
-    for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(p, b, c, lane);
+    for (long long c = warp0; c < nchunks; c += nwarps) cover_chunk(p, b, c, lane, !heavy);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -834,6 +834,8 @@ struct ListClusterCfg {
     int off_lo, off_hi, off_mask, off_loff, off_llen;   // byte offsets into dynamic shared memory (counts at 0)
     int stage_lists;     // list positions staged in shared memory (else read through the read-only path)
     unsigned int min_recompact;
+    int off_rows, off_vals;      // REFT: sort buffer of one candidate's live rows / their AF values
+    unsigned int row_cap;        // REFT: rows the buffers hold (a power of two; 0 = no room, REFT not available)
 };
 
 // FAST: count mode without weights -> candidates are (gain count of a selectable sample, index): two REDUX per reduction
@@ -847,7 +849,15 @@ __device__ __forceinline__ Cand lc_warp_best(Cand c)
     return warp_argmax(c);
 }
 
-template <int ESTRIDE, bool FAST, int CL, bool WIDE>
+// REFT (--af with UTMOS_F_REF_TIES): the reference's tie order inside the tail.  The exact fixed-point scores decide a step
+// unless two or more samples lie within 2^-30 (relative) of the best one; then every such candidate's score is replayed the
+// way the reference computes it -- float64 AF of its uncovered rows added one after the other in ascending row order
+// (utmos/select.py:37-40), times the weight (:47) -- and the first maximum of the replayed values wins (:48), exactly as in
+// argmax_step_kernel.  Here the candidate's uncovered rows come from its edge list (filtered by the live mask), are sorted
+// in shared memory (bitonic, one CTA per candidate, the candidates of different CTAs in parallel) and summed by one thread.
+// A candidate with more live rows than the sort buffer holds ends the launch with st->tie_step set: the host runs that one
+// step with the per-step kernels and comes back.
+template <int ESTRIDE, bool FAST, int CL, bool WIDE, bool REFT>
 __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p, ListClusterCfg cfg, unsigned long long lists_total,
                                                                      unsigned int light_rows)
 {
@@ -863,6 +873,10 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
     __shared__ uint4 s_q[kQueue];                    // pooled rows this CTA found: {pool base, carriers, entry index, 0}
     __shared__ unsigned int s_qn[2];                 // pooled rows queued in this step / zeroed for the next one
     __shared__ __align__(8) unsigned long long s_xbar;   // counts the 2 x CL 16-byte slots of one exchange
+    __shared__ __align__(8) unsigned long long s_xbar2, s_xbar3;   // REFT: candidate counts / replayed winners
+    __shared__ uint4 s_xcnt[2][16];                  // REFT: {candidates within the tie window in that CTA's slice, 0, 0, 0}
+    __shared__ uint4 s_xrep[2][16], s_xrepl[2][16];  // REFT: replayed local winner {key hi, key lo, sample, count}, {list offset, length, 0, 0}
+    __shared__ unsigned int s_ncand, s_nrow;
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(lc_smem);
     unsigned long long *s_lo = reinterpret_cast<unsigned long long *>(lc_smem + cfg.off_lo);
     unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(lc_smem + cfg.off_hi);
@@ -877,7 +891,10 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
     const int n_own = p.S > crank ? (p.S - crank + CL - 1) / CL : 0;
     long long step = st->step, tot = st->tot;
     const long long limit = st->limit;
-    int stop = st->stop, recompact = 0, want_light = 0, xpar = 0, since_check = 0;
+    int stop = st->stop, recompact = 0, want_light = 0, xpar = 0, since_check = 0, ph2 = 0, ph3 = 0, tie_fallback = 0;
+    unsigned int *s_rows = reinterpret_cast<unsigned int *>(lc_smem + cfg.off_rows);     // REFT: live rows of one candidate
+    double *s_vals = reinterpret_cast<double *>(lc_smem + cfg.off_vals);                 // REFT: their AF values, row order
+    int *s_cand = reinterpret_cast<int *>(s_q);                                          // REFT: slots of this CTA's candidates
     const unsigned int *pool32 = reinterpret_cast<const unsigned int *>(p.pool);
     for (int li = tid; li < n_own; li += blockDim.x) {
         const int s = crank + CL * li;
@@ -886,7 +903,11 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         s_mask[li] = p.mask[s];
         if (cfg.stage_lists) { s_loff[li] = p.list_off[s]; s_llen[li] = p.list_len[s]; }
     }
-    if (tid == 0) { lc_mbar_init(&s_xbar, 1u); s_qn[0] = s_qn[1] = 0u; }
+    if (tid == 0) {
+        lc_mbar_init(&s_xbar, 1u);
+        if (REFT) { lc_mbar_init(&s_xbar2, 1u); lc_mbar_init(&s_xbar3, 1u); }
+        s_qn[0] = s_qn[1] = 0u;
+    }
     __syncthreads();
     cluster.sync();
     // the slice of sample c: CTA c % CL, slot c / CL
@@ -977,6 +998,115 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
             off = __shfl_sync(0xffffffffu, l.z, src);
             len = __shfl_sync(0xffffffffu, l.w, src);
             xpar ^= 1;
+        }
+        if (REFT && b.idx != 0x7fffffff && key_score(b.hi, b.lo) > 0.0) {
+            // ---- how many samples lie within the tie window of the exact winner?  (one: it stands)
+            const double thr = key_score(b.hi, b.lo) * (1.0 - 9.313225746154785e-10);         // 2^-30
+            auto in_window = [&](int li) {
+                if (s_mask[li] != 1) return false;
+                double g = fixed_to_double(s_lo[li], s_hi[li], p.L, p.scale);
+                if (has_w) g *= __ldg(p.weights + crank + CL * li);
+                return g >= thr;
+            };
+            int mine = 0;
+            for (int li = tid; li < n_own; li += blockDim.x) mine += in_window(li) ? 1 : 0;
+            const int holders = __syncthreads_count(mine > 0);
+            const int crowded = __syncthreads_or(mine > 1);
+            if (tid == 0) lc_mbar_expect_tx(&s_xbar2, (unsigned int)CL * 16u);
+            if (warp == 0 && lane < CL)
+                dsmem_store16_tx(dsmem_addr(&s_xcnt[ph2][crank], (unsigned int)lane),
+                                 make_uint4((unsigned int)holders + (crowded ? 1u : 0u), 0u, 0u, 0u), dsmem_addr(&s_xbar2, (unsigned int)lane));
+            lc_mbar_wait(&s_xbar2, (unsigned int)ph2);
+            unsigned int total = lane < CL ? s_xcnt[ph2][lane].x : 0u;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o2);
+            ph2 ^= 1;
+            if (total >= 2u) {
+                // ---- replay: this CTA's candidates one after the other, the CTAs in parallel
+                if (tid == 0) { s_ncand = 0; lc_mbar_expect_tx(&s_xbar3, (unsigned int)CL * 32u); }
+                __syncthreads();
+                for (int li = tid; li < n_own; li += blockDim.x)
+                    if (in_window(li)) s_cand[atomicAdd(&s_ncand, 1u)] = li;
+                __syncthreads();
+                const int ncand = (int)s_ncand;
+                Cand rb{0u, 0u, 0x7fffffff, 0u};
+                unsigned int roff = 0, rlen = 0;
+                int overflow = 0;
+                for (int ci = 0; ci < ncand; ++ci) {
+                    const int li = s_cand[ci], t = crank + CL * li;
+                    const unsigned int toff = cfg.stage_lists ? s_loff[li] : __ldg(p.list_off + t);
+                    const unsigned int tlen = cfg.stage_lists ? s_llen[li] : __ldg(p.list_len + t);
+                    const uint4 *tl = p.lists + (size_t)toff * ESTRIDE;
+                    if (tid == 0) s_nrow = 0;
+                    __syncthreads();
+                    for (unsigned int i = tid; i < tlen; i += blockDim.x) {
+                        const unsigned int r = __ldg(tl + (size_t)i * ESTRIDE).x;
+                        if ((__ldcg(p.live + (r >> 5)) >> (r & 31)) & 1u) {
+                            const unsigned int slot = atomicAdd(&s_nrow, 1u);
+                            if (slot < cfg.row_cap) s_rows[slot] = r;
+                        }
+                    }
+                    __syncthreads();
+                    const unsigned int n = s_nrow;
+                    if (n > cfg.row_cap) { overflow = 1; continue; }
+                    unsigned int N = 1;
+                    while (N < n) N <<= 1;
+                    for (unsigned int i = n + tid; i < N; i += blockDim.x) s_rows[i] = 0xffffffffu;
+                    __syncthreads();
+                    for (unsigned int k2 = 2; k2 <= N; k2 <<= 1) {
+                        for (unsigned int j = k2 >> 1; j > 0; j >>= 1) {
+                            for (unsigned int i = tid; i < N; i += blockDim.x) {
+                                const unsigned int x = i ^ j;
+                                if (x > i) {
+                                    const unsigned int va = s_rows[i], vb = s_rows[x];
+                                    if ((va > vb) == ((i & k2) == 0)) { s_rows[i] = vb; s_rows[x] = va; }
+                                }
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    for (unsigned int i = tid; i < n; i += blockDim.x) {
+                        double v = __ldg(p.af_vals + s_rows[i]);
+                        if (p.af_f32) v = (double)(float)v;                   // hdf5 flavour: float32 GT*AF rows (utmos/select.py:218-223)
+                        s_vals[i] = v;
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        double acc2 = 0.0;
+                        for (unsigned int i = 0; i < n; ++i) acc2 += s_vals[i];       // strictly sequential, ascending rows
+                        if (has_w) acc2 *= __ldg(p.weights + t);
+                        const unsigned long long kk = score_key(acc2);
+                        const Cand c2{(unsigned int)(kk >> 32), (unsigned int)kk, t, s_cnt[li]};
+                        if (cand_better(c2, rb)) { rb = c2; roff = toff; rlen = tlen; }
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {
+                    rb.hi = __shfl_sync(0xffffffffu, rb.hi, 0);
+                    rb.lo = __shfl_sync(0xffffffffu, rb.lo, 0);
+                    rb.idx = __shfl_sync(0xffffffffu, rb.idx, 0);
+                    rb.cnt = __shfl_sync(0xffffffffu, rb.cnt, 0);
+                    roff = __shfl_sync(0xffffffffu, roff, 0);
+                    rlen = __shfl_sync(0xffffffffu, rlen, 0);
+                    if (lane < CL) {
+                        const uint32_t bar = dsmem_addr(&s_xbar3, (unsigned int)lane);
+                        dsmem_store16_tx(dsmem_addr(&s_xrep[ph3][crank], (unsigned int)lane),
+                                         make_uint4(rb.hi, rb.lo, overflow ? 0x7ffffffeu : (unsigned int)rb.idx, rb.cnt), bar);
+                        dsmem_store16_tx(dsmem_addr(&s_xrepl[ph3][crank], (unsigned int)lane), make_uint4(roff, rlen, 0u, 0u), bar);
+                    }
+                }
+                lc_mbar_wait(&s_xbar3, (unsigned int)ph3);
+                {
+                    const uint4 o = lane < CL ? s_xrep[ph3][lane] : make_uint4(0u, 0u, 0x7fffffffu, 0u);
+                    const uint4 l = lane < CL ? s_xrepl[ph3][lane] : make_uint4(0u, 0u, 0u, 0u);
+                    ph3 ^= 1;
+                    if (__any_sync(0xffffffffu, o.z == 0x7ffffffeu)) { tie_fallback = 1; break; }
+                    b = warp_argmax(Cand{o.x, o.y, (int)o.z, o.w});
+                    const int src = b.idx == 0x7fffffff ? 0 : b.idx % CL;
+                    off = __shfl_sync(0xffffffffu, l.x, src);
+                    len = __shfl_sync(0xffffffffu, l.y, src);
+                }
+            }
         }
         const int best_idx = b.idx;
         const unsigned int best_cnt = b.cnt;
@@ -1089,6 +1219,7 @@ __global__ void __launch_bounds__(1024, 1) select_listcluster_kernel(SelParams p
         st->regain = 0;
         st->recompact = recompact;
         if (want_light) st->tail_single |= 2u;
+        if (REFT) st->tie_step = tie_fallback ? 1u : 0u;
         if (p.dbg) p.dbg[11] += 1;
     }
 }
@@ -1112,6 +1243,20 @@ int listcluster_layout(const SelParams &p, int CL, ListClusterCfg *cfg, size_t *
         cfg->n_own_max = (int)n;
         cfg->stage_lists = stage;
         cfg->min_recompact = 1u << 16;
+        cfg->off_rows = cfg->off_vals = 0;
+        cfg->row_cap = 0;
+        if (p.ref_ties && p.af) {
+            // the replay's sort buffer takes what is left: 12 bytes per row, a power of two of rows
+            unsigned int cap = 1u << 13;
+            while (cap >= 1024u && off + (size_t)cap * 12 + 32 > budget) cap >>= 1;
+            if (cap >= 1024u && n <= 8192) {                // (the candidate slots alias the 32 KB queue of pooled rows)
+                cfg->off_rows = take((size_t)cap * 4);
+                cfg->off_vals = take((size_t)cap * 8);
+                cfg->row_cap = cap;
+            } else if (stage) {
+                continue;                                   // try again without the staged list positions
+            }
+        }
         *smem_bytes = off;
         return 1;
     }
@@ -1278,11 +1423,11 @@ static int launch_tail_t(cudaStream_t stream, const SelParams &p, const TailCfg 
     return UTMOS_OK;
 }
 
-template <int ESTRIDE, bool FAST, int CL, bool WIDE>
+template <int ESTRIDE, bool FAST, int CL, bool WIDE, bool REFT>
 static int launch_listcluster_t(cudaStream_t stream, const SelParams &p, const ListClusterCfg &cfg, size_t smem,
                                 unsigned long long lists_total, unsigned int light_rows)
 {
-    auto kernel = select_listcluster_kernel<ESTRIDE, FAST, CL, WIDE>;
+    auto kernel = select_listcluster_kernel<ESTRIDE, FAST, CL, WIDE, REFT>;
     UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (CL > 8) UT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t lc = {};
@@ -1304,7 +1449,8 @@ bool listcluster_fits(const SelParams &p)
 {
     ListClusterCfg cfg;
     size_t smem = 0;
-    return listcluster_layout(p, 16, &cfg, &smem) != 0;
+    if (!listcluster_layout(p, 16, &cfg, &smem)) return false;
+    return !(p.ref_ties && p.af) || (cfg.row_cap > 0 && p.af_vals != nullptr);
 }
 
 // The entry-divided cluster flavour of the tail (select_listcluster_kernel); it returns with bit 1 of st->tail_single set once a pick
@@ -1316,10 +1462,14 @@ int launch_listcluster(cudaStream_t stream, const SelParams &p, unsigned long lo
     size_t smem = 0;
     if (!listcluster_layout(p, 16, &cfg, &smem)) { set_error("entry-divided tail: a slice of the state does not fit one SM"); return UTMOS_E_ARG; }
     const bool wide = p.S > 65535;
-#define UT_LC(E, F, W) UT_TRY((launch_listcluster_t<E, F, 16, W>(stream, p, cfg, smem, lists_total, light_rows)))
-    if (p.af) { if (wide) UT_LC(2, false, true); else UT_LC(2, false, false); }
-    else if (p.weights) { if (wide) UT_LC(1, false, true); else UT_LC(1, false, false); }
-    else { if (wide) UT_LC(1, true, true); else UT_LC(1, true, false); }
+#define UT_LC(E, F, W, R) UT_TRY((launch_listcluster_t<E, F, 16, W, R>(stream, p, cfg, smem, lists_total, light_rows)))
+    if (p.af && p.ref_ties) {
+        if (!cfg.row_cap || !p.af_vals) { set_error("entry-divided tail: no room for the reference-tie replay"); return UTMOS_E_ARG; }
+        if (wide) UT_LC(2, false, true, true); else UT_LC(2, false, false, true);
+    }
+    else if (p.af) { if (wide) UT_LC(2, false, true, false); else UT_LC(2, false, false, false); }
+    else if (p.weights) { if (wide) UT_LC(1, false, true, false); else UT_LC(1, false, false, false); }
+    else { if (wide) UT_LC(1, true, true, false); else UT_LC(1, true, false, false); }
 #undef UT_LC
     *n_launch += 1;
     UT_CUDA(cudaGetLastError());
