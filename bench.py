@@ -492,7 +492,7 @@ def main():
             configs["c3"]["reference_tie_order"] = {
                 "ms_per_selection": r_ms, "select_ms": r_tim["select_ms"], "verified_vs_reference_order_golden": r_ok,
                 "picks_in_the_same_position_as_the_exact_order": int(np.sum(r_idx == c_idx)) if len(r_idx) == len(c_idx) else None,
-                "note": "per-step kernels + one warp per tied candidate replaying the reference's sequential float64 sum"}
+                "note": "UTMOS_F_REF_TIES: per-step kernels (argmax with the replay, cover, streaming recompute after heavy picks) until the edge lists can be built, then the entry-divided cluster tail with the replay of near-tie candidates inside (rows from the edge lists, sorted in shared memory, summed sequentially in float64)"}
 
     # ---- CPU baseline: the unmodified reference, complete run on a reduced row count, and this repo on the same rows
     cpu_baseline = None

@@ -53,7 +53,9 @@ typedef struct utmos_ctx utmos_ctx;
 #define UTMOS_F_NO_CLUSTER 8u        /* grid-wide persistent kernel instead of the one-cluster DSMEM kernel */
 #define UTMOS_F_NO_TAIL 16u          /* never switch to the single-CTA list-driven tail kernel */
 #define UTMOS_F_REF_TIES 64u         /* --af: order exact-arithmetic (near-)ties by replaying the reference's sequential float64 sums
-                                      * (utmos/select.py:37-48); implies UTMOS_F_STEP_KERNELS and needs the sample-major copy */
+                                      * (utmos/select.py:37-48): per-step kernels for the head, the entry-divided cluster tail with the replay
+                                      * inside from the hand-over on; with UTMOS_F_STEP_KERNELS: per-step kernels all the way.  Needs the
+                                      * sample-major copy, one GPU */
 #define UTMOS_F_DSMEM_GAINS 32u      /* cluster kernel keeps the gains in distributed shared memory (default: L2 atomics) */
 
 /* stop reasons reported by utmos_select_steps (utmos/select.py:91, :51-52/:93-96, :110-112) */
