@@ -219,6 +219,46 @@ def test_ref_ties_reproduces_the_reference_order_on_every_recorded_af_case(flavo
     assert checked == 72
 
 
+def test_ref_ties_candidates_too_long_for_the_tail_go_through_the_step_kernels():
+    """UTMOS_OPT_TIE_ROW_CAP = 4: nearly every near-tie candidate has more uncovered rows than the tail's sort buffer, so the
+    tail kernel hands those steps to the per-step kernels (st->tie_step) and resumes; same picks, counts and scores as the
+    per-step flavour on the fixtures' full `--af` ordering and on a seeded cohort with weights."""
+    gold = H.golden_json("full_order_af.json")
+    parts = H.load_jl_parts(gold["files"])
+    names = np.asarray(parts[0]["samples"]).astype(str)
+    n = len(names)
+    outs = []
+    for flags, cap in ((_native.F_REF_TIES | _native.F_STEP_KERNELS, 0), (_native.F_REF_TIES, 4), (_native.F_REF_TIES, 0)):
+        dm = _native.DeviceMatrix(n, _native.AF_F64, flags=flags)
+        dm.set_option(12, cap)
+        for p in parts:
+            dm.append_packed(p["GT"], p["AF"])
+        dm.finalize()
+        dm.begin(np.ones(n, np.uint8))
+        outs.append(dm.steps(n))
+        dm.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
+    assert [names[i] for i in outs[1][0]] == [g[0] for g in gold["rows"]]
+    n_vars, n_samples = 40_000, 600
+    coh = synth.DeviceCohort(9, n_vars, n_samples)
+    wts = synth.synthetic_weights(n_samples)
+    outs = []
+    for flags, cap in ((_native.F_REF_TIES | _native.F_STEP_KERNELS, 0), (_native.F_REF_TIES, 2), (_native.F_REF_TIES, 64)):
+        dm = _native.DeviceMatrix(n_samples, _native.AF_F64, rows_hint=n_vars, flags=flags)
+        dm.set_option(12, cap)
+        dm.append_packed_device(coh.rows.ptr, n_vars, coh.pitch, coh.af.ptr)
+        dm.finalize()
+        dm.begin(np.ones(n_samples, np.uint8), wts)
+        a = dm.steps(200)
+        b = dm.steps(n_samples)
+        outs.append([np.concatenate([a[i], b[i]]) for i in range(3)] + [b[3]])
+        dm.close()
+    coh.close()
+    for o in outs[1:]:
+        assert all(np.array_equal(o[i], outs[0][i]) for i in range(3)) and o[3] == outs[0][3]
+
+
 def test_ref_ties_full_af_ordering_and_cli(tmp_path):
     """The 855-row `--af` ordering of the fixtures and the `--af` answer keys with --ref-ties (same reports as without:
     the fixtures have no near-tie that the exact order resolves differently)."""

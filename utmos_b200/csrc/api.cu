@@ -147,6 +147,7 @@ struct utmos_ctx {
     unsigned long long *d_local0_lo = nullptr, *d_local0_hi = nullptr, *d_local_lo = nullptr, *d_local_hi = nullptr;
     bool lists_external = false;       // d_lists[0] / d_pool live inside the exchange block (not owned)
     unsigned int tail_rows = 2048;        // hand over to the list-driven tail once picks cover fewer rows than this
+    unsigned int tie_row_cap = 0;         // UTMOS_OPT_TIE_ROW_CAP
     bool ref_hybrid = false;              // UTMOS_F_REF_TIES without UTMOS_F_STEP_KERNELS: step kernels, then the REFT tail
     unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
     unsigned int tail_heavy_rows = 0xffffffffu;   // (0xffffffff = default: 768 in count mode, 1 = every tail step with AF or S > 65,535)
@@ -642,6 +643,7 @@ SelParams make_params(const utmos_ctx *c, bool step0)
     p.weights = c->has_weights ? c->d_weights : nullptr;
     p.af_vals = c->d_af;
     p.ref_ties = ((c->flags & UTMOS_F_REF_TIES) && c->mg_world <= 1) ? 1 : 0;
+    p.tie_row_cap = c->tie_row_cap;
     p.af_f32 = c->af_mode == UTMOS_AF_F32 ? 1 : 0;
     p.out_idx = c->d_out_idx;
     p.out_new = c->d_out_new;
@@ -1884,6 +1886,7 @@ int utmos_set_option(utmos_ctx *c, int option, int64_t value)
     if (option == UTMOS_OPT_GLOBAL_ROWS) { c->global_rows = value; return UTMOS_OK; }
     if (option == UTMOS_OPT_STEP_TIMES) { c->dbg_time = value != 0; return UTMOS_OK; }
     if (option == UTMOS_OPT_TAIL_ROWS) { c->tail_rows = (unsigned int)std::max<int64_t>(0, value); return UTMOS_OK; }
+    if (option == UTMOS_OPT_TIE_ROW_CAP) { c->tie_row_cap = (unsigned int)std::max<int64_t>(0, std::min<int64_t>(value, 8192)); return UTMOS_OK; }
     if (option == UTMOS_OPT_LIST_BUDGET) {
         if (c->finalized) { set_error("set_option: the list budget is fixed at finalize"); return UTMOS_E_ARG; }
         c->list_budget = (unsigned long long)std::max<int64_t>(0, std::min<int64_t>(value, 1ll << 30));

@@ -72,6 +72,7 @@ struct SelParams {
     const double *weights;             // [S] or null
     const double *af_vals;             // [V] per-row AF as given (UTMOS_F_REF_TIES replays the reference's float64 sums from it)
     int ref_ties;                      // 1: order exact-arithmetic near-ties like the reference does (step-kernel flavour)
+    unsigned int tie_row_cap;          // REFT tail: rows of a candidate the replay may sort (0 = what fits, at most 8,192)
     int af_f32;                        // 1: the rows are float32 GT*AF (hdf5 flavour): AF rounds through float first
     long long *out_idx;                // [S] report rows
     long long *out_new;

@@ -1249,7 +1249,12 @@ int listcluster_layout(const SelParams &p, int CL, ListClusterCfg *cfg, size_t *
             // the replay's sort buffer takes what is left: 12 bytes per row, a power of two of rows
             unsigned int cap = 1u << 13;
             while (cap >= 1024u && off + (size_t)cap * 12 + 32 > budget) cap >>= 1;
-            if (cap >= 1024u && n <= 8192) {                // (the candidate slots alias the 32 KB queue of pooled rows)
+            if (p.tie_row_cap) {                            // UTMOS_OPT_TIE_ROW_CAP: a smaller buffer (tests of the fall-back step)
+                unsigned int want = 2;
+                while (want * 2 <= p.tie_row_cap) want <<= 1;
+                if (cap >= 1024u && want < cap) cap = want;
+            }
+            if ((cap >= 1024u || p.tie_row_cap) && cap >= 2u && n <= 8192) {   // (the candidate slots alias the 32 KB queue of pooled rows)
                 cfg->off_rows = take((size_t)cap * 4);
                 cfg->off_vals = take((size_t)cap * 8);
                 cfg->row_cap = cap;
