@@ -491,6 +491,7 @@ def main():
             assert r_ok, "config C3 with UTMOS_F_REF_TIES differs from the reference-order oracle (tests/golden/c3ref_full_order.npz)"
             configs["c3"]["reference_tie_order"] = {
                 "ms_per_selection": r_ms, "select_ms": r_tim["select_ms"], "verified_vs_reference_order_golden": r_ok,
+                "select_parts_ms": {"head": r_tim.get("head_ms"), "hand_over": r_tim.get("handover_ms"), "tail": r_tim.get("tail_ms")},
                 "picks_in_the_same_position_as_the_exact_order": int(np.sum(r_idx == c_idx)) if len(r_idx) == len(c_idx) else None,
                 "note": "UTMOS_F_REF_TIES: per-step kernels (argmax with the replay, cover, streaming recompute after heavy picks) until the edge lists can be built, then the entry-divided cluster tail with the replay of near-tie candidates inside (rows from the edge lists, sorted in shared memory, summed sequentially in float64)"}
 
