@@ -212,7 +212,8 @@ int utmos_debug_gains(utmos_ctx *ctx, int64_t *count_out, double *score_out);
 int utmos_debug_step_times(utmos_ctx *ctx, int64_t first, int64_t n, int64_t *ns_out);
 
 /* Profiling counters of the selection kernel: out16[0..3] = clock cycles spent (CTA 0, thread 0) in argmax,
- * barrier 1, cover, barrier 2, summed over steps; out16[4] = kernel launches. */
+ * barrier 1, cover, barrier 2, summed over steps; out16[4] = kernel launches; out16[11] = launches of the entry-divided
+ * tail; out16[12] = steps of the per-step kernels that the reference-tie replay decided. */
 int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
 
 /* Tunables.  UTMOS_OPT_REGAIN_ROWS: a pick that newly covers >= value rows triggers one streaming recompute of
