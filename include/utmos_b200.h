@@ -227,7 +227,7 @@ int utmos_debug_counters(utmos_ctx *ctx, int64_t *out16);
 #define UTMOS_OPT_TIE_ROW_CAP 12      /* UTMOS_F_REF_TIES: uncovered rows of a near-tie candidate the tail kernel replays itself (a power of two,
                                        * default what fits, at most 8,192); a candidate with more is handed to the per-step kernels */
 #define UTMOS_OPT_TAIL_HEAVY_ROWS 10  /* list-driven tail: picks covering >= value rows run on the entry-divided 16-CTA cluster kernel
-                                       * (gains sliced over the cluster's shared memories); lighter picks from one SM's shared memory (0 = never; -1 = default: 768 in count mode, 1 with AF or more than 65,535 samples) */
+                                       * (gains sliced over the cluster's shared memories); lighter picks from one SM's shared memory (0 = never; -1 = default: 768 in count mode, 1 with AF or when the per-sample state does not fit one SM) */
 #define UTMOS_OPT_TAIL_SINGLE_ROWS 5  /* tail kernel: 8-CTA owner-computes cluster until a pick covers fewer rows
                                          (default 0 = single CTA only) */
 int utmos_set_option(utmos_ctx *ctx, int option, int64_t value);

@@ -150,7 +150,7 @@ struct utmos_ctx {
     unsigned int tie_row_cap = 0;         // UTMOS_OPT_TIE_ROW_CAP
     bool ref_hybrid = false;              // UTMOS_F_REF_TIES without UTMOS_F_STEP_KERNELS: step kernels, then the REFT tail
     unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
-    unsigned int tail_heavy_rows = 0xffffffffu;   // (0xffffffff = default: 768 in count mode, 1 = every tail step with AF or S > 65,535)
+    unsigned int tail_heavy_rows = 0xffffffffu;   // (0xffffffff = default: 768 in count mode, 1 = every tail step with AF or a state that does not fit one SM)
                                           // list-driven tail: picks that cover at least this many rows are run by the entry-divided
                                           // 16-CTA cluster kernel (gains in L2), lighter ones from one SM's shared memory (0 = never)
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
@@ -1436,7 +1436,9 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             // shared-memory adds per decrement make one SM the slower choice whatever the pick covers
             // more than 65,535 samples: the alternative is the owner-computes cluster tail, where every CTA walks every entry
             // (50,000 x 2 M: 6.3 against 8.0 us per step; 100,000 x 2 M: 7.4 against 9.3)
-            const unsigned int heavy_rows = hybrid ? 1u : c->tail_heavy_rows != 0xffffffffu ? c->tail_heavy_rows : ((af || wide) ? 1u : 768u);
+            // the same holds for any cohort whose state does not fit one SM (50,000 x 2 M rows: tail 94.8 against 106.6 ms)
+            const bool sliced = tail_cluster_size(q, false) != 1;
+            const unsigned int heavy_rows = hybrid ? 1u : c->tail_heavy_rows != 0xffffffffu ? c->tail_heavy_rows : ((af || wide || sliced) ? 1u : 768u);
             if (c->lists_valid && heavy_rows > 0 && !(st.tail_single & 2u) && listcluster_fits(q)) {
                 // heavy picks: the entries of the pick divided over a 16-CTA cluster, gains in L2 (select_listcluster_kernel);
                 // it hands over (bit 1 of st.tail_single) once a pick covers fewer than tail_heavy_rows rows
