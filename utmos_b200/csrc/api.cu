@@ -152,7 +152,7 @@ struct utmos_ctx {
     unsigned long long list_budget = 0;   // edge-list entries the tail may be built from (0 = kListBudget / kListBudgetWide)
     unsigned int tail_heavy_rows = 0xffffffffu;   // (0xffffffff = default: 768 in count mode, 1 = every tail step with AF or a state that does not fit one SM)
                                           // list-driven tail: picks that cover at least this many rows are run by the entry-divided
-                                          // 16-CTA cluster kernel (gains in L2), lighter ones from one SM's shared memory (0 = never)
+                                          // 16-CTA cluster kernel (state sliced over its shared memories), lighter ones on one SM (0 = never)
     unsigned int tail_single_rows = 0;    // > 0: 8-CTA owner-computes flavour of the tail until picks cover fewer rows than this
                                           // (measured on the 1kGP shape: not faster than one CTA, so off by default)
     uint32_t *d_newmask = nullptr;        // rows newly covered by the pick that ended a head launch (cover_decrement_kernel)
@@ -1440,7 +1440,7 @@ int utmos_select_steps(utmos_ctx *c, int64_t max_steps, int64_t *idx_out, int64_
             const bool sliced = tail_cluster_size(q, false) != 1;
             const unsigned int heavy_rows = hybrid ? 1u : c->tail_heavy_rows != 0xffffffffu ? c->tail_heavy_rows : ((af || wide || sliced) ? 1u : 768u);
             if (c->lists_valid && heavy_rows > 0 && !(st.tail_single & 2u) && listcluster_fits(q)) {
-                // heavy picks: the entries of the pick divided over a 16-CTA cluster, gains in L2 (select_listcluster_kernel);
+                // heavy picks: the entries of the pick divided over a 16-CTA cluster, state sliced over its shared memories (select_listcluster_kernel);
                 // it hands over (bit 1 of st.tail_single) once a pick covers fewer than tail_heavy_rows rows
                 UT_TRY(launch_listcluster(c->stream, q, c->lists_total, heavy_rows, &c->n_launch));
                 UT_TRY(launch_sum_gains(c->stream, q, &c->n_launch));
