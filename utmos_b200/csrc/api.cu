@@ -1905,7 +1905,7 @@ int utmos_info(utmos_ctx *c, int64_t *info, int n)
     if (!c || !info) { set_error("info: null argument"); return UTMOS_E_ARG; }
     const int64_t vals[10] = {c->V, (int64_t)c->pitchW * 4, c->d_cols ? 1 : 0, (int64_t)c->dev_bytes, c->scale,
                               (int64_t)c->af_inexact, c->n_launch, c->flavour_used, (int64_t)c->colPitchW,
-                              (c->flags & UTMOS_F_REF_TIES) ? 1 : 0};
+                              ((c->flags & UTMOS_F_REF_TIES) && c->mg_world <= 1) ? 1 : 0};
     for (int i = 0; i < n && i < 10; ++i) info[i] = vals[i];
     return UTMOS_OK;
 }
