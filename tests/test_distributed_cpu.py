@@ -127,16 +127,32 @@ def _worker(rank, world, port, out_queue):
     # sharded run on the reference fixtures
     parts = H.load_jl_parts(["chunk0.jl", "chunk1.jl"])
     n = 2504
+    calls = []
+    gather = comm.all_gather_bytes
+    comm.all_gather_bytes = lambda payload: (calls.append(len(payload)), gather(payload))[1]
     sm = ShardedMatrix(n, _native.AF_NONE, comm=comm, matrix_factory=CpuShard)
     for part in parts:
         b, e = shard_bounds(part["GT"].shape[0], rank, world)
         sm.append_packed(part["GT"][b:e])
     var_count = sm.finalize()
+    count_mode_gathers = list(calls)
+    # --af: the fixed-point scale needs the global row count BEFORE the local finalize -> one more all-gather
+    del calls[:]
+    sa = ShardedMatrix(n, _native.AF_F64, comm=comm, matrix_factory=CpuShard)
+    for part in parts:
+        b, e = shard_bounds(part["GT"].shape[0], rank, world)
+        sa.append_packed(part["GT"][b:e], part["AF"][b:e])
+    vc_af = sa.finalize()
+    af_mode_gathers = list(calls)
+    af_rows_known_early = sa.local.global_rows == sm.num_vars and np.array_equal(vc_af, var_count)
+    sa.close()
+    comm.all_gather_bytes = gather
     sm.begin(np.ones(n, np.uint8))
     idx, new, score, stop = sm.steps(120)
     if rank == 0:
         out_queue.put((summed.tolist(), int(wrap[0]), gathered[:, 0].tolist(), sm.num_vars, var_count.tolist(),
-                       idx.tolist(), new.tolist(), stop, sm.local.connected))
+                       idx.tolist(), new.tolist(), stop, sm.local.connected, count_mode_gathers, af_mode_gathers,
+                       bool(af_rows_known_early)))
     sm.close()
     dist.destroy_process_group()
 
@@ -155,7 +171,11 @@ def test_two_rank_gloo_sharded_run_matches_oracle():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    summed, wrap, gathered, num_vars, var_count, idx, new, stop, connected = got
+    summed, wrap, gathered, num_vars, var_count, idx, new, stop, connected, count_gathers, af_gathers, af_early = got
+    n = 2504
+    # count mode: ONE all-gather for gains + var_count + flags + row count, one for the IPC handles; --af: the row counts first
+    assert count_gathers == [8 * (2 * n + 2), 64]
+    assert af_gathers == [8, 8 * (4 * n + 2), 64] and af_early
     assert summed == [3, 20]
     assert wrap == (2 * (2**63 + 5)) % 2**64
     assert gathered == [0, 1] and connected
